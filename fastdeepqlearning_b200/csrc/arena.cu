@@ -1,0 +1,487 @@
+// Replay arena in HBM + the write path (append, episode commit, write-time hindsight flush).
+// Replaces franQ/Replay/replay_memory.py:18-46 (ring), franQ/Replay/wrappers/nstep_return.py:36-72 (return-to-go at
+// episode flush) and franQ/Replay/wrappers/her.py:55-95 (hindsight copy) -- see include/fdql.h for the contract.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "goal_eval.cuh"
+
+namespace fdql {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int upload_reward_spec(const Arena* a, int32_t op, const float* params_host, int32_t n_params, cudaStream_t st,
+                       RewardSpec* out) {
+  out->op = op;
+  out->n_params = n_params;
+  out->params = a->reward_params_dev;
+  if (op == FDQL_REWARD_WEIGHTED_PNORM) {
+    FDQL_REQUIRE(a->dev.wide_ag >= 0, "weighted p-norm reward needs an achieved_goal key");
+    const int need = 2 + a->dev.wide[a->dev.wide_ag].width;
+    FDQL_REQUIRE(params_host != nullptr && n_params == need, "weighted p-norm reward needs %d params {p, thr, w[G]}, got %d",
+                 need, n_params);
+    // pad weights to the slab stride with zeros so the lanes' float4 slices never read past the table
+    float tmp[kMaxRewardParams + 4];
+    memset(tmp, 0, sizeof(tmp));
+    FDQL_REQUIRE(need <= kMaxRewardParams, "goal too wide for the reward parameter table");
+    memcpy(tmp, params_host, sizeof(float) * need);
+    FDQL_CUDA(cudaMemcpyAsync(a->reward_params_dev, tmp, sizeof(float) * (kMaxRewardParams + 4), cudaMemcpyHostToDevice, st));
+    FDQL_CUDA(cudaStreamSynchronize(st));  // tmp is a stack buffer
+  }
+  return FDQL_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// append: dense [n, width] sources -> ring rows top.. (mod capacity)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) append_kernel(ArenaDev A, SrcPtrs src, int64_t n_rows, int64_t top) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < A.n_wide; ++s) {
+    const WideSlab W = A.wide[s];
+    const float* __restrict__ sp = src.p[W.key];
+    const int64_t items = n_rows * W.vecs;
+    const bool vec_ok = (W.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0);
+    for (int64_t i = tid; i < items; i += nthreads) {
+      const int64_t r = i / W.vecs;
+      const int v = (int)(i - r * W.vecs);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* q = sp + r * W.width + 4 * v;
+      if (vec_ok) {
+        x = ld_stream4(q);
+      } else {
+        const int n = min(4, W.width - 4 * v);
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < n; ++c) t[c] = q[c];
+        x = make_float4(t[0], t[1], t[2], t[3]);
+      }
+      const int64_t row = ring_row(top, r % A.capacity, A.capacity);
+      *reinterpret_cast<float4*>(W.base + row * (int64_t)W.stride + 4 * v) = x;
+    }
+  }
+  for (int64_t r = tid; r < n_rows; r += nthreads) {
+    const int64_t row = ring_row(top, r, A.capacity);
+    float* rec = A.rec + row * (int64_t)A.rec_stride;
+    for (int c0 = 0; c0 < A.rec_stride; c0 += 4) {
+      float t[4];
+      for (int c = 0; c < 4; ++c) {
+        const int col = c0 + c;
+        float val = 0.f;
+        if (col < A.n_scal) val = src.p[A.scal_key[col]][r];
+        else if (col == A.col_ep_start || col == A.col_ep_end) val = __int_as_float(-1);
+        t[c] = val;
+      }
+      *reinterpret_cast<float4*>(rec + c0) = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    A.ga[row] = 0.f;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// exact return recurrence of nstep_return.py:69-72: newest row first, each step evaluated in fp64 (unfused
+// multiply then add) and rounded to fp32 on store.  One warp walks one episode from its last row to its first.
+// `r` holds the rewards of rows jb+lane (zero where invalid); returns this lane's G and updates (acc, first).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_return_chunk(float r, int jb, int L, double gamma, float& acc, bool& first) {
+  float mine = 0.f;
+  const int lane = lane_id();
+#pragma unroll 4
+  for (int i = 31; i >= 0; --i) {
+    const float ri = __shfl_sync(kFull, r, i);
+    if (jb + i < L) {
+      acc = first ? ri : (float)__dadd_rn((double)ri, __dmul_rn((double)acc, gamma));
+      first = false;
+    }
+    if (lane == i) mine = acc;
+  }
+  return mine;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+commit_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ ep_begin, const int32_t* __restrict__ ep_len,
+              double gamma, int with_returns, RewardSpec rs) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = lane_id();
+  if (warp >= n_eps) return;
+  const int64_t s = ep_begin[warp];
+  const int L = ep_len[warp];
+  const int64_t e = ring_row(s, L - 1, A.capacity);
+  const bool want_ga = rs.op != FDQL_REWARD_NONE && A.wide_ag >= 0 && A.wide_dg >= 0 && A.col_reward >= 0;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int jb = 0; jb < L; jb += 32) {
+    const int j = jb + lane;
+    const bool valid = j < L;
+    const int64_t row = ring_row(s, valid ? j : 0, A.capacity);
+    float* rec = A.rec + row * (int64_t)A.rec_stride;
+    float Rdg = 0.f;
+    bool d;
+    if (want_ga) eval_chunk<LPR, true>(A, rs, s, jb, L - 1, zero, Rdg, d);
+    if (valid) {
+      rec[A.col_ep_start] = __int_as_float((int)s);
+      rec[A.col_ep_end] = __int_as_float((int)e);
+      if (want_ga) A.ga[row] = (float)((double)rec[A.col_reward] - (double)Rdg);
+    }
+  }
+  if (with_returns && A.col_mc_return >= 0 && A.col_reward >= 0) {
+    float acc = 0.f;
+    bool first = true;
+    for (int jb = ((L - 1) / 32) * 32; jb >= 0; jb -= 32) {
+      const int j = jb + lane;
+      const bool valid = j < L;
+      const int64_t row = ring_row(s, valid ? j : 0, A.capacity);
+      float* rec = A.rec + row * (int64_t)A.rec_stride;
+      const float r = valid ? rec[A.col_reward] : 0.f;
+      const float g = exact_return_chunk(r, jb, L, gamma, acc, first);
+      if (valid) rec[A.col_mc_return] = g;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// write-time hindsight copy, her.py:55-95 (+ the inner NStepReturn flush, quirk Q5): one warp per episode
+// -------------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+her_flush_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ src_begin, const int32_t* __restrict__ ep_len,
+                 const int64_t* __restrict__ dst_begin, const int64_t* __restrict__ goal_row, RewardSpec rs, double gamma,
+                 int with_returns) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = lane_id();
+  if (warp >= n_eps) return;
+  const int64_t s = src_begin[warp], d0 = dst_begin[warp], grow = goal_row[warp];
+  const int L = ep_len[warp];
+  const int64_t dend = ring_row(d0, L - 1, A.capacity);
+  const float4 gstar = load_goal_slice<LPR>(A, grow);
+  // wide keys: verbatim copy, except desired_goal := g*
+  for (int w = 0; w < A.n_wide; ++w) {
+    const WideSlab W = A.wide[w];
+    const int items = L * W.vecs;
+    for (int i = lane; i < items; i += 32) {
+      const int j = i / W.vecs, v = i - j * W.vecs;
+      const int64_t srow = (w == A.wide_dg) ? grow : ring_row(s, j, A.capacity);
+      const WideSlab& S = (w == A.wide_dg) ? A.wide[A.wide_ag] : W;
+      const float4 x = ldg4(S.base + srow * (int64_t)S.stride + 4 * v);
+      *reinterpret_cast<float4*>(W.base + ring_row(d0, j, A.capacity) * (int64_t)W.stride + 4 * v) = x;
+    }
+  }
+  // records: relabelled reward / task_done / episode_step, new extents
+  int seg_first = 0;  // episode-relative index of the first row of the current synthetic episode
+  for (int jb = 0; jb < L; jb += 32) {
+    const int j = jb + lane;
+    const bool valid = j < L;
+    float Rg, Rdg = 0.f;
+    bool dn, dtmp;
+    eval_chunk<LPR, false>(A, rs, s, jb, L - 1, gstar, Rg, dn);
+    if (A.wide_dg >= 0) eval_chunk<LPR, true>(A, rs, s, jb, L - 1, gstar, Rdg, dtmp);
+    const unsigned bal = __ballot_sync(kFull, valid && dn);
+    if (valid) {
+      const int64_t srow = ring_row(s, j, A.capacity), drow = ring_row(d0, j, A.capacity);
+      const float* rs_ = A.rec + srow * (int64_t)A.rec_stride;
+      float* rd = A.rec + drow * (int64_t)A.rec_stride;
+      for (int c = 0; c < A.rec_stride; c += 4)
+        *reinterpret_cast<float4*>(rd + c) = *reinterpret_cast<const float4*>(rs_ + c);
+      const unsigned below = bal & ((1u << lane) - 1u);
+      const int f = below ? (jb + 32 - __clz(below)) : seg_first;
+      const double r = A.col_reward >= 0 ? (double)rs_[A.col_reward] : 0.0;
+      const float ga = (float)(r - (double)Rdg);
+      if (A.col_reward >= 0) rd[A.col_reward] = (float)((r - (double)Rdg) + (double)Rg);
+      if (A.col_task_done >= 0) rd[A.col_task_done] = dn ? 1.f : 0.f;
+      if (A.col_ep_step >= 0) {
+        const float step_f = A.rec[ring_row(s, f, A.capacity) * (int64_t)A.rec_stride + A.col_ep_step];
+        rd[A.col_ep_step] = rs_[A.col_ep_step] - step_f;
+      }
+      rd[A.col_ep_start] = __int_as_float((int)d0);
+      rd[A.col_ep_end] = __int_as_float((int)dend);
+      A.ga[drow] = ga;
+    }
+    if (bal) seg_first = jb + 32 - __clz(bal);
+  }
+  __syncwarp();
+  if (with_returns && A.col_mc_return >= 0 && A.col_reward >= 0) {
+    float acc = 0.f;
+    bool first = true;
+    for (int jb = ((L - 1) / 32) * 32; jb >= 0; jb -= 32) {
+      const int j = jb + lane;
+      const bool valid = j < L;
+      float* rd = A.rec + ring_row(d0, valid ? j : 0, A.capacity) * (int64_t)A.rec_stride;
+      const float r = valid ? rd[A.col_reward] : 0.f;
+      const float g = exact_return_chunk(r, jb, L, gamma, acc, first);
+      if (valid) rd[A.col_mc_return] = g;
+    }
+  }
+}
+
+static void advance_cursor(Arena* a, int64_t n) {
+  const int64_t cap = a->dev.capacity, top = a->top;
+  int64_t mx;
+  if (n >= cap) mx = cap - 1;
+  else if (top + n < cap) mx = top + n;
+  else mx = (top <= cap - 2) ? cap - 1 : top + n - cap;
+  a->top = (top + n) % cap;
+  if (mx > a->len) a->len = mx;  // len = max(top, len) after every row: saturates at capacity-1 (quirk Q1)
+}
+
+}  // namespace fdql
+
+using namespace fdql;
+
+extern "C" {
+
+const char* fdql_last_error(void) { return fdql::g_err; }
+int fdql_version(void) { return 100; }
+
+int fdql_arena_create(int64_t capacity, int32_t n_keys, const int32_t* widths, const int32_t* roles, int32_t device,
+                      fdql_arena** out) {
+  FDQL_REQUIRE(out != nullptr && widths != nullptr, "null argument");
+  FDQL_REQUIRE(capacity >= 2 && capacity < (1ll << 31), "capacity must be in [2, 2^31)");
+  FDQL_REQUIRE(n_keys >= 1 && n_keys <= FDQL_MAX_KEYS, "n_keys must be in [1, %d]", FDQL_MAX_KEYS);
+  FDQL_CUDA(cudaSetDevice(device));
+  fdql_arena* a = new fdql_arena();
+  memset(static_cast<Arena*>(a), 0, sizeof(Arena));
+  a->n_keys = n_keys;
+  a->device = device;
+  ArenaDev& D = a->dev;
+  D.capacity = capacity;
+  D.col_reward = D.col_task_done = D.col_ep_done = D.col_ep_step = D.col_mc_return = -1;
+  D.wide_ag = D.wide_dg = -1;
+  for (int k = 0; k < n_keys; ++k) {
+    const int w = widths[k], role = roles ? roles[k] : FDQL_ROLE_NONE;
+    if (w < 1) {
+      set_error("key %d has width %d", k, w);
+      delete a;
+      return FDQL_EINVAL;
+    }
+    a->widths[k] = w;
+    a->roles[k] = role;
+    a->key_wide[k] = a->key_col[k] = -1;
+    const bool goal = role == FDQL_ROLE_ACHIEVED_GOAL || role == FDQL_ROLE_DESIRED_GOAL;
+    if (w == 1 && !goal) {
+      const int c = D.n_scal++;
+      D.scal_key[c] = k;
+      a->key_col[k] = c;
+      if (role == FDQL_ROLE_REWARD) D.col_reward = c;
+      if (role == FDQL_ROLE_TASK_DONE) D.col_task_done = c;
+      if (role == FDQL_ROLE_EPISODE_DONE) D.col_ep_done = c;
+      if (role == FDQL_ROLE_EPISODE_STEP) D.col_ep_step = c;
+      if (role == FDQL_ROLE_MC_RETURN) D.col_mc_return = c;
+    } else {
+      const int s = D.n_wide++;
+      D.wide[s].width = w;
+      D.wide[s].stride = (w + 3) / 4 * 4;
+      D.wide[s].vecs = D.wide[s].stride / 4;
+      D.wide[s].key = k;
+      a->key_wide[k] = s;
+      if (role == FDQL_ROLE_ACHIEVED_GOAL) D.wide_ag = s;
+      if (role == FDQL_ROLE_DESIRED_GOAL) D.wide_dg = s;
+    }
+  }
+  if (D.wide_ag >= 0 && D.wide_dg >= 0 && D.wide[D.wide_ag].width != D.wide[D.wide_dg].width) {
+    set_error("achieved_goal and desired_goal widths differ");
+    delete a;
+    return FDQL_EINVAL;
+  }
+  D.col_ep_start = D.n_scal;
+  D.col_ep_end = D.n_scal + 1;
+  D.rec_stride = (D.n_scal + 2 + 3) / 4 * 4;
+  size_t total = 0;
+  auto alloc = [&](float** p, size_t n_floats) -> bool {
+    const size_t b = n_floats * sizeof(float);
+    if (cudaMalloc(reinterpret_cast<void**>(p), b) != cudaSuccess) return false;
+    cudaMemset(*p, 0, b);
+    total += b;
+    return true;
+  };
+  bool ok = true;
+  for (int s = 0; s < D.n_wide && ok; ++s) ok = alloc(&D.wide[s].base, (size_t)capacity * D.wide[s].stride);
+  ok = ok && alloc(&D.rec, (size_t)capacity * D.rec_stride);
+  ok = ok && alloc(&D.ga, (size_t)capacity);
+  ok = ok && alloc(&a->reward_params_dev, kMaxRewardParams + 4);
+  if (!ok) {
+    set_error("cudaMalloc failed while allocating the arena (%zu bytes so far): %s", total,
+              cudaGetErrorString(cudaGetLastError()));
+    fdql_arena_destroy(a);
+    return FDQL_ENOMEM;
+  }
+  cudaDeviceGetAttribute(&a->num_sms, cudaDevAttrMultiProcessorCount, device);
+  a->bytes = (int64_t)total;
+  FDQL_CUDA(cudaDeviceSynchronize());
+  *out = a;
+  return FDQL_OK;
+}
+
+int fdql_arena_destroy(fdql_arena* a) {
+  if (!a) return FDQL_OK;
+  for (int s = 0; s < a->dev.n_wide; ++s)
+    if (a->dev.wide[s].base) cudaFree(a->dev.wide[s].base);
+  if (a->dev.rec) cudaFree(a->dev.rec);
+  if (a->dev.ga) cudaFree(a->dev.ga);
+  if (a->reward_params_dev) cudaFree(a->reward_params_dev);
+  if (a->stage_dev) cudaFree(a->stage_dev);
+  if (a->step_dev) cudaFree(a->step_dev);
+  if (a->step_sync_ready) {
+    for (int i = 0; i < 3; ++i) cudaStreamDestroy(a->step_streams[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(a->step_events[i]);
+  }
+  delete a;
+  return FDQL_OK;
+}
+
+int fdql_arena_info(const fdql_arena* a, int64_t* capacity, int64_t* top, int64_t* len, int64_t* bytes) {
+  FDQL_REQUIRE(a != nullptr, "null arena");
+  if (capacity) *capacity = a->dev.capacity;
+  if (top) *top = a->top;
+  if (len) *len = a->len;
+  if (bytes) *bytes = a->bytes;
+  return FDQL_OK;
+}
+
+int fdql_arena_set_cursor(fdql_arena* a, int64_t top, int64_t len) {
+  FDQL_REQUIRE(a != nullptr, "null arena");
+  FDQL_REQUIRE(top >= 0 && top < a->dev.capacity && len >= 0 && len <= a->dev.capacity, "cursor out of range");
+  a->top = top;
+  a->len = len;
+  return FDQL_OK;
+}
+
+int fdql_arena_key_view(const fdql_arena* a, int32_t key, float** base, int64_t* row_stride, int32_t* col) {
+  FDQL_REQUIRE(a != nullptr && key >= 0 && key < a->n_keys, "bad key");
+  if (a->key_wide[key] >= 0) {
+    const WideSlab& W = a->dev.wide[a->key_wide[key]];
+    *base = W.base;
+    *row_stride = W.stride;
+    *col = 0;
+  } else {
+    *base = a->dev.rec;
+    *row_stride = a->dev.rec_stride;
+    *col = a->key_col[key];
+  }
+  return FDQL_OK;
+}
+
+int fdql_arena_meta_view(const fdql_arena* a, int32_t which, float** base, int64_t* row_stride, int32_t* col) {
+  FDQL_REQUIRE(a != nullptr && which >= 0 && which <= 2, "bad meta column");
+  if (which == 2) {
+    *base = a->dev.ga;
+    *row_stride = 1;
+    *col = 0;
+  } else {
+    *base = a->dev.rec;
+    *row_stride = a->dev.rec_stride;
+    *col = which == 0 ? a->dev.col_ep_start : a->dev.col_ep_end;
+  }
+  return FDQL_OK;
+}
+
+int fdql_arena_append(fdql_arena* a, int64_t n_rows, const float* const* src, void* stream) {
+  FDQL_REQUIRE(a != nullptr && src != nullptr, "null argument");
+  FDQL_REQUIRE(n_rows >= 0 && n_rows <= a->dev.capacity, "n_rows must be in [0, capacity]");
+  if (n_rows == 0) return FDQL_OK;
+  SrcPtrs sp;
+  for (int k = 0; k < a->n_keys; ++k) {
+    FDQL_REQUIRE(src[k] != nullptr, "source pointer for key %d is null", k);
+    sp.p[k] = src[k];
+  }
+  int64_t widest = 1;
+  for (int s = 0; s < a->dev.n_wide; ++s) widest = widest > a->dev.wide[s].vecs ? widest : a->dev.wide[s].vecs;
+  int64_t blocks = (n_rows * widest + 255) / 256;
+  const int64_t cap_blocks = (int64_t)a->num_sms * 8;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  append_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a->dev, sp, n_rows, a->top);
+  FDQL_CUDA(cudaGetLastError());
+  advance_cursor(a, n_rows);
+  return FDQL_OK;
+}
+
+int fdql_arena_append_host(fdql_arena* a, int64_t n_rows, const float* const* src_host, void* stream) {
+  FDQL_REQUIRE(a != nullptr && src_host != nullptr, "null argument");
+  FDQL_REQUIRE(n_rows >= 0 && n_rows <= a->dev.capacity, "n_rows must be in [0, capacity]");
+  if (n_rows == 0) return FDQL_OK;
+  size_t need = 0;
+  for (int k = 0; k < a->n_keys; ++k) need += ((size_t)n_rows * a->widths[k] * sizeof(float) + 255) / 256 * 256;
+  if (need > a->stage_bytes) {
+    FDQL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (a->stage_dev) cudaFree(a->stage_dev);
+    a->stage_dev = nullptr;
+    a->stage_bytes = 0;
+    FDQL_CUDA(cudaMalloc(&a->stage_dev, need));
+    a->stage_bytes = need;
+  }
+  const float* dev_ptrs[FDQL_MAX_KEYS];
+  size_t off = 0;
+  for (int k = 0; k < a->n_keys; ++k) {
+    const size_t b = (size_t)n_rows * a->widths[k] * sizeof(float);
+    float* d = reinterpret_cast<float*>(static_cast<char*>(a->stage_dev) + off);
+    FDQL_CUDA(cudaMemcpyAsync(d, src_host[k], b, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    dev_ptrs[k] = d;
+    off += (b + 255) / 256 * 256;
+  }
+  return fdql_arena_append(a, n_rows, dev_ptrs, stream);
+}
+
+int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row) {
+  FDQL_REQUIRE(a != nullptr && n_rows >= 0 && n_rows <= a->dev.capacity, "bad reserve");
+  if (first_row) *first_row = a->top;
+  advance_cursor(a, n_rows);
+  return FDQL_OK;
+}
+
+#define FDQL_DISPATCH_LPR(lpr, ...)                     \
+  switch (lpr) {                                        \
+    case 1: { constexpr int LPR = 1; __VA_ARGS__; } break;   \
+    case 2: { constexpr int LPR = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int LPR = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int LPR = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int LPR = 16; __VA_ARGS__; } break; \
+    default: { constexpr int LPR = 32; __VA_ARGS__; } break; \
+  }
+
+int fdql_commit_episodes(fdql_arena* a, int32_t n_eps, const int64_t* ep_begin, const int32_t* ep_len, double gamma,
+                         int32_t with_returns, int32_t reward_op, const float* reward_params_host, int32_t n_params,
+                         void* stream) {
+  FDQL_REQUIRE(a != nullptr && n_eps >= 0, "bad argument");
+  if (n_eps == 0) return FDQL_OK;
+  FDQL_REQUIRE(ep_begin != nullptr && ep_len != nullptr, "null episode table");
+  RewardSpec rs;
+  int rc = upload_reward_spec(a, reward_op, reward_params_host, n_params, (cudaStream_t)stream, &rs);
+  if (rc) return rc;
+  int lpr = 1;
+  if (a->dev.wide_ag >= 0) {
+    FDQL_REQUIRE(a->dev.wide[a->dev.wide_ag].vecs <= 32, "goal wider than 128 floats is not supported");
+    lpr = lanes_per_row(a->dev.wide[a->dev.wide_ag].vecs);
+  }
+  const unsigned blocks = (unsigned)(((int64_t)n_eps * 32 + 255) / 256);
+  FDQL_DISPATCH_LPR(lpr, (commit_kernel<LPR><<<blocks, 256, 0, (cudaStream_t)stream>>>(a->dev, n_eps, ep_begin, ep_len, gamma,
+                                                                                         with_returns, rs)));
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
+int fdql_her_flush_episodes(fdql_arena* a, int32_t n_eps, const int64_t* src_begin, const int32_t* ep_len,
+                            const int64_t* dst_begin, const int64_t* goal_row, int32_t reward_op,
+                            const float* reward_params_host, int32_t n_params, double gamma, int32_t with_returns,
+                            void* stream) {
+  FDQL_REQUIRE(a != nullptr && n_eps >= 0, "bad argument");
+  if (n_eps == 0) return FDQL_OK;
+  FDQL_REQUIRE(src_begin && ep_len && dst_begin && goal_row, "null episode table");
+  FDQL_REQUIRE(a->dev.wide_ag >= 0, "hindsight flush needs an achieved_goal key");
+  FDQL_REQUIRE(reward_op != FDQL_REWARD_NONE, "hindsight flush needs a reward functor");
+  FDQL_REQUIRE(a->dev.wide[a->dev.wide_ag].vecs <= 32, "goal wider than 128 floats is not supported");
+  RewardSpec rs;
+  int rc = upload_reward_spec(a, reward_op, reward_params_host, n_params, (cudaStream_t)stream, &rs);
+  if (rc) return rc;
+  const int lpr = lanes_per_row(a->dev.wide[a->dev.wide_ag].vecs);
+  const unsigned blocks = (unsigned)(((int64_t)n_eps * 32 + 255) / 256);
+  FDQL_DISPATCH_LPR(lpr, (her_flush_kernel<LPR><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                             a->dev, n_eps, src_begin, ep_len, dst_begin, goal_row, rs, gamma, with_returns)));
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
+}  // extern "C"

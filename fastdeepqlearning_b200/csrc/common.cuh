@@ -1,0 +1,163 @@
+// Shared device/host definitions for libfdql.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fdql.h"
+
+namespace fdql {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define FDQL_CUDA(call)                                                                       \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      fdql::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return FDQL_ECUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+#define FDQL_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      fdql::set_error(__VA_ARGS__);    \
+      return FDQL_EINVAL;              \
+    }                                  \
+  } while (0)
+
+// ---- arena layout in HBM ----------------------------------------------------------------------
+// Wide keys (width >= 2, and goal keys of any width): one slab [capacity, stride], stride = width rounded up
+// to 4 floats so that every row starts 16B-aligned and is moved with 128-bit loads.
+// Width-1 keys: packed side by side into one record per row, [capacity, rec_stride], followed by two int32
+// columns holding the episode extents (first/last row of the row's episode, -1 until committed).
+// ga: [capacity] goal-agnostic reward r - R(ag, dg) (her.py:65-68), its own slab so that episode scans read it
+// as one contiguous run.
+struct WideSlab {
+  float* base;
+  int32_t stride;  // floats, multiple of 4
+  int32_t width;   // floats
+  int32_t key;     // caller's key index
+  int32_t vecs;    // stride / 4
+};
+
+struct ArenaDev {
+  int64_t capacity;
+  int32_t n_wide, n_scal, rec_stride, pad0;
+  WideSlab wide[FDQL_MAX_KEYS];
+  float* rec;
+  float* ga;
+  int32_t scal_key[FDQL_MAX_KEYS];  // record column -> caller's key index
+  int32_t col_ep_start, col_ep_end;
+  int32_t col_reward, col_task_done, col_ep_done, col_ep_step, col_mc_return;  // record column or -1
+  int32_t wide_ag, wide_dg;                                                    // index into wide[] or -1
+};
+
+struct OutPtrs {
+  float* p[FDQL_MAX_KEYS];
+};
+struct SrcPtrs {
+  const float* p[FDQL_MAX_KEYS];
+};
+
+constexpr int kMaxRewardParams = 2 + 128;
+struct RewardSpec {
+  int32_t op;
+  int32_t n_params;
+  const float* params;  // device copy of {p, thr, w...} for WEIGHTED_PNORM, else unused
+};
+
+// ---- small device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming (evict-first) 128-bit load/store for data touched once per launch
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ int64_t ring_row(int64_t base, int64_t off, int64_t cap) {
+  int64_t r = base + off;
+  return r >= cap ? r - cap : r;
+}
+
+__device__ __forceinline__ double shfl_down_f64(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_down_sync(kFull, lo, d);
+  hi = __shfl_down_sync(kFull, hi, d);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_idx_f64(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(kFull, lo, src);
+  hi = __shfl_sync(kFull, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(kFull, lo, m);
+  hi = __shfl_xor_sync(kFull, hi, m);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(kFull, lo, d);
+  hi = __shfl_up_sync(kFull, hi, d);
+  return __hiloint2double(hi, lo);
+}
+
+// host-side view of an arena (definition shared by the translation units)
+struct Arena {
+  ArenaDev dev;
+  int32_t n_keys;
+  int32_t widths[FDQL_MAX_KEYS];
+  int32_t roles[FDQL_MAX_KEYS];
+  int32_t key_wide[FDQL_MAX_KEYS];  // key -> index in dev.wide or -1
+  int32_t key_col[FDQL_MAX_KEYS];   // key -> record column or -1
+  int64_t top, len, bytes;
+  int32_t device;
+  float* reward_params_dev;  // kMaxRewardParams floats
+  // staging for *_host entry points (allocated lazily, grown only when a larger call arrives)
+  void* stage_dev;
+  size_t stage_bytes;
+  void* step_dev;  // fdql_hotpath_step_host: streams, critic outputs, aux, loss, grad
+  size_t step_bytes;
+  cudaStream_t step_streams[3];
+  cudaEvent_t step_events[8];
+  int step_sync_ready;
+  int num_sms;
+};
+
+int upload_reward_spec(const Arena* a, int32_t op, const float* params_host, int32_t n_params, cudaStream_t st,
+                       RewardSpec* out);
+
+}  // namespace fdql
+
+struct fdql_arena;
+namespace fdql {
+int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts,
+                  const uint8_t* flags, const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host,
+                  int32_t n_params, double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out, float* aux_mask,
+                  float* aux_contig, float* aux_weight, cudaStream_t st);
+}
+
+struct fdql_arena : fdql::Arena {};

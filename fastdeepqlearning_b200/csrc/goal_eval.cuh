@@ -1,0 +1,112 @@
+// Warp-cooperative evaluation of the reward functor R(achieved_goal, goal) -> (reward, done) over 32 consecutive
+// rows of one episode (device form of the Python callable franQ's HER wrapper calls per row,
+// franQ/Replay/wrappers/her.py:62,67; functors: franQ/Env/bitflip.py:143-152,
+// franQ/Env/classic_control_goal/classic_goal.py:88-93,306-311, franQ/Env/eleurent_parking.py:42-55).
+//
+// Lane layout: a goal row of `vecs` float4 is covered by LPR lanes (LPR = power of two >= vecs), so one warp-wide
+// 128-bit load touches 32/LPR rows; LPR such passes cover 32 rows.  Per-row results are then transposed to
+// "lane l <-> row jbase+l" with one ballot (flag functors) or one shuffle (norm functor) per pass.
+#pragma once
+#include "common.cuh"
+
+namespace fdql {
+
+template <int LPR>
+struct GoalRegs {
+  float4 g;  // this lane's slice (vec index lane % LPR) of the broadcast goal g*
+};
+
+template <int LPR>
+__device__ __forceinline__ float4 load_goal_slice(const ArenaDev& A, int64_t goal_row) {
+  const WideSlab& ag = A.wide[A.wide_ag];
+  const int v = lane_id() % LPR;
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  return (v < ag.vecs) ? ldg4(ag.base + goal_row * (int64_t)ag.stride + 4 * v) : z;
+}
+
+__device__ __forceinline__ bool flag_partial(int op, int v, const float4& a, const float4& g) {
+  switch (op) {
+    case FDQL_REWARD_BITFLIP:
+      return (a.x == g.x) & (a.y == g.y) & (a.z == g.z) & (a.w == g.w);
+    case FDQL_REWARD_ALL_GEQ:
+      return (a.x >= g.x) & (a.y >= g.y) & (a.z >= g.z) & (a.w >= g.w);
+    default:  // FDQL_REWARD_FIRST_GEQ
+      return v == 0 ? (a.x >= g.x) : true;
+  }
+}
+
+// Results for this lane's row j = jbase + lane (meaningless when j > jmax; callers mask).
+// PER_ROW_GOAL: compare each row against its own desired_goal (the goal-agnostic term, her.py:65-68) instead of g*.
+template <int LPR, bool PER_ROW_GOAL>
+__device__ __forceinline__ void eval_chunk(const ArenaDev& A, const RewardSpec& rs, int64_t ep_first, int32_t jbase,
+                                           int32_t jmax, const float4& gstar, float& reward, bool& done) {
+  constexpr int RPP = 32 / LPR;              // rows per pass
+  constexpr int PB = LPR < 4 ? LPR : 4;      // passes whose loads are issued back to back
+  constexpr unsigned GM = LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u);
+  const int lane = lane_id();
+  const int v = lane % LPR, rloc = lane / LPR;
+  const WideSlab& ag = A.wide[A.wide_ag];
+  const bool vok = v < ag.vecs;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  reward = 0.f;
+  done = false;
+#pragma unroll 1
+  for (int p0 = 0; p0 < LPR; p0 += PB) {
+    float4 a[PB], g[PB];
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int j = jbase + (p0 + q) * RPP + rloc;
+      const bool ok = vok && j <= jmax;
+      const int64_t row = ring_row(ep_first, j, A.capacity);
+      a[q] = ok ? ldg4(ag.base + row * (int64_t)ag.stride + 4 * v) : zero;
+      if (PER_ROW_GOAL) {
+        const WideSlab& dg = A.wide[A.wide_dg];
+        g[q] = ok ? ldg4(dg.base + row * (int64_t)dg.stride + 4 * v) : zero;
+      } else {
+        g[q] = ok ? gstar : zero;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int p = p0 + q;
+      const bool mine = (lane / RPP) == p;
+      const int src = (lane % RPP) * LPR;
+      if (rs.op == FDQL_REWARD_WEIGHTED_PNORM) {
+        double acc = 0.0;
+        if (vok) {
+          const float* w = rs.params + 2 + 4 * v;
+          const int n = min(4, ag.width - 4 * v);
+          const float da[4] = {a[q].x - g[q].x, a[q].y - g[q].y, a[q].z - g[q].z, a[q].w - g[q].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < n) acc += (double)fabsf(da[c]) * (double)w[c];
+        }
+#pragma unroll
+        for (int m = LPR / 2; m >= 1; m >>= 1) acc += shfl_xor_f64(acc, m);
+        const double t = shfl_idx_f64(acc, src);
+        if (mine) {
+          const double r = -pow(t, (double)rs.params[0]);
+          reward = (float)r;
+          done = r > -(double)rs.params[1];
+        }
+      } else {
+        const bool okl = flag_partial(rs.op, v, a[q], g[q]);
+        const unsigned bal = __ballot_sync(kFull, okl);
+        if (mine) {
+          const bool m = ((bal >> src) & GM) == GM;
+          reward = m ? 0.f : -1.f;
+          done = m;
+        }
+      }
+    }
+  }
+}
+
+// lanes-per-row for a goal slab of `vecs` float4 (power of two, <= 32); vecs > 32 is rejected on the host
+inline int lanes_per_row(int vecs) {
+  int l = 1;
+  while (l < vecs) l <<= 1;
+  return l;
+}
+
+}  // namespace fdql

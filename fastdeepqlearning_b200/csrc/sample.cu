@@ -1,0 +1,400 @@
+// Read side of the replay arena: index/goal stream sampling, row gather, and the fused
+// window gather + sample-time hindsight relabel + return recompute.
+//   ReplayMemory.sample / temporal_sample / __getitem__   franQ/Replay/replay_memory.py:48-70
+//   TorchDataLoader fp32 cast                              franQ/Replay/wrappers/torch_dataloader.py:36
+//   HindsightNStepReplay._hindsight_flush                  franQ/Replay/wrappers/her.py:55-95
+//   calculate_montecarlo_return                            franQ/Replay/wrappers/nstep_return.py:60-72
+//   DeepQLearning.get_losses mask / is_contiguous / reduce weights   franQ/Agent/deepQlearning.py:201-203,222-225,249
+//
+// One warp owns one sampled window.  Wide keys move as 128-bit vectors (a row of a key is a run of whole 32 B
+// sectors, see common.cuh); the hindsight scan walks the contiguous tail of the window's episode in the
+// achieved_goal slab, 32 rows per pass, and combines per-pass partial returns with a warp-shuffle scan.
+#include "common.cuh"
+#include "goal_eval.cuh"
+
+namespace fdql {
+
+// ---- counter-based generator (Philox4x32-10) ----------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+  c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+__device__ __forceinline__ uint4 philox4x32(uint64_t ctr_lo, uint64_t ctr_hi, uint64_t key) {
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// starts ~ U[0, len-T) like np.random.randint(0, len-T, B) (replay_memory.py:59); flag ~ Bernoulli(p); goal row by mode
+// over the committed extents of the start row's episode (her.py:48-53).  Uncommitted rows are never relabelled.
+__global__ void __launch_bounds__(256)
+sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int goal_mode, float relabel_prob, uint64_t seed, uint64_t counter,
+                      int64_t* __restrict__ starts, uint8_t* __restrict__ flags, int64_t* __restrict__ goal_rows) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const uint4 x = philox4x32((uint64_t)b, counter, seed);
+  const uint64_t r64 = ((uint64_t)x.x << 32) | x.y;
+  const int64_t s = (int64_t)__umul64hi(r64, (uint64_t)range);
+  starts[b] = s;
+  if (flags == nullptr) return;
+  const float* rec = A.rec + s * (int64_t)A.rec_stride;
+  const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
+  bool f = (es >= 0) && ((float)x.z * 2.3283064365386963e-10f < relabel_prob);
+  int64_t g = s;
+  if (f) {
+    const int64_t cap = A.capacity;
+    if (goal_mode == FDQL_GOAL_FINAL) {
+      g = ee;
+    } else if (goal_mode == FDQL_GOAL_RANDOM) {
+      const int64_t L = (ee - es + (ee < es ? cap : 0)) + 1;
+      g = ring_row(es, (int64_t)__umulhi(x.w, (uint32_t)L), cap);
+    } else {  // FUTURE: a row strictly after the start row, the last row when there is none
+      const int64_t m = ee - s + (ee < s ? cap : 0);
+      g = m == 0 ? ee : ring_row(s, 1 + (int64_t)__umulhi(x.w, (uint32_t)m), cap);
+    }
+  }
+  flags[b] = f ? 1 : 0;
+  if (goal_rows) goal_rows[b] = g;
+}
+
+// ---- fused window gather -------------------------------------------------------------------------
+struct GatherArgs {
+  ArenaDev A;
+  OutPtrs out;  // indexed by the caller's key
+  const int64_t* starts;
+  const uint8_t* flags;
+  const int64_t* goal_rows;
+  int64_t n;    // windows in the whole batch (row pitch of the time-major outputs)
+  int64_t b_begin, b_end;  // slice of windows this launch handles
+  int64_t len;  // modulus of the window indices (replay_memory.py:65)
+  int32_t T;
+  uint32_t opts;
+  RewardSpec rs;
+  double gamma;
+  float inv_bt;  // 1 / (batch * T) for the reduce weights
+  float* aux_mask;
+  float* aux_contig;
+  float* aux_weight;
+};
+
+__device__ __forceinline__ double warp_suffix_scan(double v, double g, int lane) {
+  // inclusive suffix scan of v with ratio g: out_l = sum_{m>=l} g^(m-l) v_m  (pairs (v, c) with c = g^(span))
+  double c = g;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_down_f64(v, d);
+    if (lane + d < 32) v = fma(c, o, v);
+    c = c * c;
+  }
+  return v;
+}
+
+template <int LPR, bool RELABEL>
+__global__ void __launch_bounds__(256) sample_gather_kernel(const __grid_constant__ GatherArgs g) {
+  extern __shared__ float smem[];
+  const ArenaDev& A = g.A;
+  const int lane = lane_id();
+  const int wib = threadIdx.x >> 5;
+  const int T = g.T;
+  // per-warp scratch for the T window rows: relabelled reward, return, done flag, contiguity
+  float* sm_r = smem + (size_t)wib * 4 * T;
+  float* sm_g = sm_r + T;
+  float* sm_d = sm_g + T;
+  float* sm_c = sm_d + T;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t cap = A.capacity;
+  const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
+
+  for (int64_t b = g.b_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; b < g.b_end; b += nwarps) {
+    int64_t s = __ldg(g.starts + b);
+    if (s >= g.len) s %= g.len;
+
+    // ---- relabel set-up: episode extents of the start row, goal vector --------------------------
+    bool relabel = false;
+    int tail_last = -1;  // window-relative index of the episode's last row
+    int64_t grow = 0, ep_first = 0;
+    if (RELABEL) {
+      if (g.flags != nullptr && __ldg(g.flags + b) != 0) {
+        const float* rec = A.rec + s * (int64_t)A.rec_stride;
+        const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
+        if (es >= 0) {
+          relabel = true;
+          ep_first = es;
+          tail_last = (int)(ee - s + (ee < s ? cap : 0));
+          grow = __ldg(g.goal_rows + b);
+        }
+      }
+    }
+
+    // ---- wide keys: [T rows] x [vecs] float4 per key, time-major output -------------------------
+    for (int w = 0; w < A.n_wide; ++w) {
+      const WideSlab W = A.wide[w];
+      float* __restrict__ o = g.out.p[W.key];
+      if (o == nullptr) continue;
+      const bool is_dg = RELABEL && relabel && w == A.wide_dg;
+      const WideSlab S = is_dg ? A.wide[A.wide_ag] : W;
+      const bool vec_store = (W.width & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+      const int items = T * W.vecs;
+      for (int i = lane; i < items; i += 32) {
+        const int t = i / W.vecs, v = i - t * W.vecs;
+        int64_t row = s + t;
+        if (row >= g.len) row -= g.len;
+        const float* src = (is_dg && t <= tail_last) ? S.base + grow * (int64_t)S.stride : W.base + row * (int64_t)W.stride;
+        const float4 x = ldg4(src + 4 * v);
+        float* dst = o + ((int64_t)t * g.n + b) * W.width + 4 * v;
+        if (vec_store) {
+          st_stream4(dst, x);
+        } else {
+          const int m = min(4, W.width - 4 * v);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+          for (int c = 0; c < m; ++c) st_stream1(dst + c, xs[c]);
+        }
+      }
+    }
+
+    // ---- hindsight scan over the episode tail (her.py:62-69 + nstep_return.py:69-72, quirk Q5) ---
+    int seg_first = -1;  // episode-relative index of the first row of the synthetic episode the window starts in; -1 unknown
+    int j0 = 0;          // episode-relative index of the window's first row
+    if (RELABEL && relabel) {
+      const float4 gstar = load_goal_slice<LPR>(A, grow);
+      double carry = 0.0;  // return of the first row after the chunk in flight
+      const double gam = g.gamma;
+      // gamma^(32-lane): weight of the carry for this lane's row
+      double wcar = 1.0;
+      {
+        double p = gam;
+        int e = 32 - lane;
+        while (e) {  // <= 6 iterations
+          if (e & 1) wcar *= p;
+          p *= p;
+          e >>= 1;
+        }
+      }
+      for (int jb = (tail_last >> 5) << 5; jb >= 0; jb -= 32) {
+        float Rg;
+        bool dn;
+        eval_chunk<LPR, false>(A, g.rs, s, jb, tail_last, gstar, Rg, dn);
+        const int j = jb + lane;
+        const bool valid = j <= tail_last;
+        float rnew = 0.f;
+        if (valid) rnew = (float)((double)__ldg(A.ga + ring_row(s, j, cap)) + (double)Rg);
+        double G = warp_suffix_scan(valid ? (double)rnew : 0.0, gam, lane);
+        G = fma(wcar, carry, G);
+        carry = shfl_idx_f64(G, 0);
+        if (valid && j < T) {
+          sm_r[j] = rnew;
+          sm_g[j] = (float)G;
+          sm_d[j] = dn ? 1.f : 0.f;
+        }
+      }
+      j0 = (int)(s - ep_first + (s < ep_first ? cap : 0));
+      if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+        seg_first = 0;
+        for (int jb = ((j0 - 1) >> 5) << 5; jb >= 0 && j0 > 0; jb -= 32) {
+          float Rg;
+          bool dn;
+          eval_chunk<LPR, false>(A, g.rs, ep_first, jb, j0 - 1, gstar, Rg, dn);
+          const unsigned bal = __ballot_sync(kFull, dn && (jb + lane) < j0);
+          if (bal) {
+            seg_first = jb + 32 - __clz(bal);
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- scalar record columns + learner aux, lane <-> window row ---------------------------------
+    float contig_sum = 0.f;
+    float carry_step = 0.f, carry_mask = 0.f;
+    for (int tb = 0; tb < T; tb += 32) {
+      const int t = tb + lane;
+      const bool valid = t < T;
+      int64_t row = s + (valid ? t : 0);
+      if (row >= g.len) row -= g.len;
+      const float* rec = A.rec + row * (int64_t)A.rec_stride;
+      const bool in_ep = RELABEL && relabel && valid && t <= tail_last;
+      float v_step = 0.f, v_done = 0.f;
+      if (A.col_ep_step >= 0) v_step = __ldg(rec + A.col_ep_step);
+      if (A.col_task_done >= 0) v_done = __ldg(rec + A.col_task_done);
+      float v_rew = 0.f, v_ret = 0.f;
+      if (RELABEL && relabel) {
+        const bool dn = in_ep && sm_d[t] != 0.f;
+        const unsigned bal = __ballot_sync(kFull, dn);
+        if (in_ep) {
+          v_rew = sm_r[t];
+          v_ret = sm_g[t];
+          v_done = dn ? 1.f : 0.f;
+          const unsigned below = bal & ((1u << lane) - 1u);
+          const int f = below ? (j0 + tb + 32 - __clz(below)) : seg_first;
+          if (f >= 0 && A.col_ep_step >= 0)
+            v_step = v_step - __ldg(A.rec + ring_row(ep_first, f, cap) * (int64_t)A.rec_stride + A.col_ep_step);
+        }
+        if (bal) seg_first = j0 + tb + 32 - __clz(bal);
+      }
+      if (valid) {
+        for (int c = 0; c < A.n_scal; ++c) {
+          float* o = g.out.p[A.scal_key[c]];
+          if (o == nullptr) continue;
+          float val;
+          if (c == A.col_ep_step) val = v_step;
+          else if (c == A.col_task_done) val = v_done;
+          else if (in_ep && c == A.col_reward) val = v_rew;
+          else if (in_ep && c == A.col_mc_return) val = v_ret;
+          else val = __ldg(rec + c);
+          st_stream1(o + (int64_t)t * g.n + b, val);
+        }
+      }
+      if (want_aux) {
+        // mask = !task_done (deepQlearning.py:201); is_contiguous[t] = (step[t+1]==step[t]+1) & mask[t] (:202-203)
+        const float v_mask = v_done != 0.f ? 0.f : 1.f;
+        if (valid && g.aux_mask) st_stream1(g.aux_mask + (int64_t)t * g.n + b, v_mask);
+        const float nxt = __shfl_down_sync(kFull, v_step, 1);
+        if (lane < 31 && t + 1 < T) {
+          const float c = (nxt == v_step + 1.f && v_mask != 0.f) ? 1.f : 0.f;
+          sm_c[t] = c;
+          contig_sum += c;
+        }
+        const float first_step = __shfl_sync(kFull, v_step, 0);
+        if (tb > 0 && lane == 0) {
+          const float c = (first_step == carry_step + 1.f && carry_mask != 0.f) ? 1.f : 0.f;
+          sm_c[tb - 1] = c;
+          contig_sum += c;
+        }
+        carry_step = __shfl_sync(kFull, v_step, 31);
+        carry_mask = __shfl_sync(kFull, v_mask, 31);
+      }
+    }
+    if (want_aux) {
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) contig_sum += __shfl_xor_sync(kFull, contig_sum, d);
+      __syncwarp();
+      // upstream weight of q_loss[t,b] in the scalar loss: contig / ((sum_t contig + 1e-4) * B * T)  (deepQlearning.py:222-225,249)
+      const float denom = contig_sum + 1e-4f;
+      for (int t = lane; t < T - 1; t += 32) {
+        const float c = sm_c[t];
+        if (g.aux_contig) st_stream1(g.aux_contig + (int64_t)t * g.n + b, c);
+        if (g.aux_weight) st_stream1(g.aux_weight + (int64_t)t * g.n + b, (c / denom) * g.inv_bt);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts, const uint8_t* flags,
+                         const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host, int32_t n_params,
+                         double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out, float* aux_mask,
+                         float* aux_contig, float* aux_weight, cudaStream_t st) {
+  GatherArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = a->dev;
+  for (int k = 0; k < a->n_keys; ++k) g.out.p[k] = out[k];
+  g.starts = starts;
+  g.flags = flags;
+  g.goal_rows = goal_rows;
+  g.n = n;
+  g.b_begin = b_begin;
+  g.b_end = b_end;
+  g.len = len;
+  g.T = T;
+  g.opts = opts;
+  g.gamma = gamma;
+  g.inv_bt = 1.f / ((float)(batch_for_weight > 0 ? batch_for_weight : (int32_t)n) * (float)T);
+  g.aux_mask = aux_mask;
+  g.aux_contig = aux_contig;
+  g.aux_weight = aux_weight;
+  const bool relabel = flags != nullptr;
+  int lpr = 1;
+  if (relabel) {
+    FDQL_REQUIRE(goal_rows != nullptr, "flags without goal_rows");
+    FDQL_REQUIRE(a->dev.wide_ag >= 0 && a->dev.wide_dg >= 0, "relabelling needs achieved_goal and desired_goal keys");
+    FDQL_REQUIRE(reward_op != FDQL_REWARD_NONE, "relabelling needs a reward functor");
+    FDQL_REQUIRE(a->dev.wide[a->dev.wide_ag].vecs <= 32, "goal wider than 128 floats is not supported");
+    int rc = upload_reward_spec(a, reward_op, reward_params_host, n_params, st, &g.rs);
+    if (rc) return rc;
+    lpr = lanes_per_row(a->dev.wide[a->dev.wide_ag].vecs);
+  }
+  const int warps_per_block = 8;
+  const size_t smem = (size_t)warps_per_block * 4 * T * sizeof(float);
+  FDQL_REQUIRE(smem <= 200 * 1024, "temporal_len %d too long for the per-warp window scratch", T);
+  int64_t blocks = (b_end - b_begin + warps_per_block - 1) / warps_per_block;
+  const int64_t max_blocks = (int64_t)a->num_sms * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+#define FDQL_LAUNCH_GATHER(LPRV, REL)                                                                              \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      FDQL_CUDA(cudaFuncSetAttribute(sample_gather_kernel<LPRV, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                                  \
+    sample_gather_kernel<LPRV, REL><<<(unsigned)blocks, warps_per_block * 32, smem, st>>>(g);                      \
+  } while (0)
+  if (!relabel) {
+    FDQL_LAUNCH_GATHER(1, false);
+  } else {
+    switch (lpr) {
+      case 1: FDQL_LAUNCH_GATHER(1, true); break;
+      case 2: FDQL_LAUNCH_GATHER(2, true); break;
+      case 4: FDQL_LAUNCH_GATHER(4, true); break;
+      case 8: FDQL_LAUNCH_GATHER(8, true); break;
+      case 16: FDQL_LAUNCH_GATHER(16, true); break;
+      default: FDQL_LAUNCH_GATHER(32, true); break;
+    }
+  }
+#undef FDQL_LAUNCH_GATHER
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
+}  // namespace fdql
+
+using namespace fdql;
+
+extern "C" {
+
+int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
+                        uint64_t counter, int64_t* starts, uint8_t* flags, int64_t* goal_rows, void* stream) {
+  FDQL_REQUIRE(a != nullptr && starts != nullptr, "null argument");
+  FDQL_REQUIRE(n >= 0 && T >= 0, "bad sizes");
+  FDQL_REQUIRE(goal_mode >= FDQL_GOAL_FINAL && goal_mode <= FDQL_GOAL_FUTURE, "bad goal mode");
+  // replay_memory.py:50,57-58: OversampleError when the ring holds fewer rows than a batch / two windows
+  if (a->len < n || (T > 0 && a->len < 2 * (int64_t)T)) {
+    set_error("OversampleError: ring holds %lld rows, asked for %lld windows of %d", (long long)a->len, (long long)n, T);
+    return FDQL_EOVERSAMPLE;
+  }
+  if (n == 0) return FDQL_OK;
+  const int64_t range = a->len - T;  // T==0: flat sample() over [0, len)
+  FDQL_REQUIRE(range > 0, "empty start range");
+  sample_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->dev, n, range, goal_mode, relabel_prob,
+                                                                                       seed, counter, starts, flags, goal_rows);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
+int fdql_gather_rows(const fdql_arena* a, int64_t n, const int64_t* idx, float* const* out, void* stream) {
+  FDQL_REQUIRE(a != nullptr && idx != nullptr && out != nullptr, "null argument");
+  if (n <= 0) return n == 0 ? FDQL_OK : FDQL_EINVAL;
+  return launch_gather(a, n, 0, n, 1, a->dev.capacity, idx, nullptr, nullptr, FDQL_REWARD_NONE, nullptr, 0, 0.0, 0, 0, out, nullptr,
+                       nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int fdql_sample_gather(const fdql_arena* a, int64_t n_windows, int32_t T, int64_t len, const int64_t* starts,
+                       const uint8_t* flags, const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host,
+                       int32_t n_params, double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out,
+                       float* aux_mask, float* aux_contig, float* aux_weight, void* stream) {
+  FDQL_REQUIRE(a != nullptr && starts != nullptr && out != nullptr, "null argument");
+  FDQL_REQUIRE(T >= 1 && len >= T && len <= a->dev.capacity, "need 1 <= T <= len <= capacity (T=%d len=%lld)", T, (long long)len);
+  if (n_windows <= 0) return n_windows == 0 ? FDQL_OK : FDQL_EINVAL;
+  if (opts & FDQL_OPT_EMIT_LEARNER_AUX)
+    FDQL_REQUIRE(a->dev.col_task_done >= 0 && a->dev.col_ep_step >= 0, "learner aux needs task_done and episode_step keys");
+  return launch_gather(a, n_windows, 0, n_windows, T, len, starts, flags, goal_rows, reward_op, reward_params_host, n_params, gamma, opts,
+                       batch_for_weight, out, aux_mask, aux_contig, aux_weight, (cudaStream_t)stream);
+}
+
+}  // extern "C"

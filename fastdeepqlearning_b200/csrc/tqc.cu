@@ -1,0 +1,440 @@
+// TQC target + quantile-Huber loss, forward and backward in one pass, one warp per transition.
+//   DistributionalSoftActorCritic.q_loss   franQ/Agent/components/distributional_soft_actor_critic.py:50-58,66-67,70,76-82
+//   quantile_huber_loss_f                  franQ/Agent/components/distributional_soft_actor_critic.py:90-103
+//   SoftActorCritic.q_loss                 franQ/Agent/components/soft_actor_critic.py:63-99,134
+//
+// The reference materialises the [n_atoms, K] pairwise tensor (14,375 pair evaluations per transition at 5x25 atoms).
+// Here the pooled target atoms are sorted in registers by a warp-level bitonic network (VPL values per lane), the top
+// n_drop are cut, and because the K kept targets y are sorted, the sum over k for one predicted atom q splits at
+// a = #(y < q-1), b = #(y < q), c = #(y <= q+1) into pieces that are linear in prefix sums of y and y^2
+// (SURVEY.md appendix B6).  y and q are shifted by a per-transition centre first so the fp32 prefix sums do not cancel.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace fdql {
+
+struct TqcArgs {
+  int64_t M;
+  int32_t n_atoms, n_z, n_drop;  // predicted atoms, pooled target atoms, target atoms cut from the top
+  const float* next_z;
+  const float* q_pred;
+  const float* next_log_pi;
+  const float* reward;
+  const float* mask;
+  const float* mc_return;
+  const float* grad_scale;
+  float alpha, gamma;
+  float* loss;
+  float* grad_q;
+  float* td_target;
+  double* stats;
+};
+
+// ---- warp-level bitonic sort of 32*VPL values; sorted position of (lane, slot) is lane*VPL + slot -----------
+template <int VPL, int K, int J>
+__device__ __forceinline__ void bitonic_step(float (&e)[VPL], int lane) {
+  constexpr int N = 32 * VPL;
+  if constexpr (J >= VPL) {
+    constexpr int LM = J / VPL;  // partner lane = lane ^ LM
+    // ascending block iff (i & K) == 0; i = lane*VPL + slot and K >= 2J >= 2*VPL, so only the lane decides
+    const bool asc = (K == N) ? true : ((lane & (K / VPL)) == 0);
+    const bool lower = (lane & LM) == 0;
+    const bool keep_min = (asc == lower);
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      const float o = __shfl_xor_sync(kFull, e[s], LM);
+      e[s] = keep_min ? fminf(e[s], o) : fmaxf(e[s], o);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      if ((s & J) == 0) {
+        const int p = s | J;
+        bool asc;
+        if constexpr (K < VPL) asc = (s & K) == 0;
+        else if constexpr (K == N) asc = true;
+        else asc = (lane & (K / VPL)) == 0;
+        const float lo = fminf(e[s], e[p]), hi = fmaxf(e[s], e[p]);
+        e[s] = asc ? lo : hi;
+        e[p] = asc ? hi : lo;
+      }
+    }
+  }
+}
+template <int VPL, int K, int J>
+__device__ __forceinline__ void bitonic_merge(float (&e)[VPL], int lane) {
+  bitonic_step<VPL, K, J>(e, lane);
+  if constexpr (J > 1) bitonic_merge<VPL, K, J / 2>(e, lane);
+}
+template <int VPL, int K>
+__device__ __forceinline__ void bitonic_sort_from(float (&e)[VPL], int lane) {
+  bitonic_merge<VPL, K, K / 2>(e, lane);
+  if constexpr (K < 32 * VPL) bitonic_sort_from<VPL, K * 2>(e, lane);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+
+// count of sorted[0..N) strictly below x (LE=false) or <= x (LE=true); entries past the kept range hold +inf
+template <int N, bool LE>
+__device__ __forceinline__ int count_below(const float* __restrict__ sorted, float x) {
+  int lo = 0;
+#pragma unroll
+  for (int step = N / 2; step >= 1; step >>= 1) {
+    const float v = sorted[lo + step - 1];
+    const bool take = LE ? (v <= x) : (v < x);
+    lo = take ? lo + step : lo;
+  }
+  return lo;
+}
+
+constexpr int kTqcWarps = 8;
+
+template <int VPL>
+__global__ void __launch_bounds__(kTqcWarps * 32) tqc_loss_kernel(const __grid_constant__ TqcArgs a) {
+  constexpr int N = 32 * VPL;
+  // per warp: sorted centred targets Y[N], exclusive prefix sums P1[N+1], P2[N+1]  (+pad to dodge bank aliasing)
+  constexpr int kStride = 3 * N + 8;
+  __shared__ float sm[kTqcWarps * kStride];
+  __shared__ double sm_stats[3];
+  const int lane = lane_id(), wib = threadIdx.x >> 5;
+  float* Y = sm + wib * kStride;
+  float* P1 = Y + N;
+  float* P2 = P1 + N + 1;
+  const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
+  const float inv_n = 1.f / (float)n;
+  const float inv_nk = 1.f / ((float)n * (float)K);
+  const float half_over_n = (float)(0.5 / (double)n);
+  if (a.stats && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
+  if (a.stats) __syncthreads();
+  double st_sum = 0.0, st_var = 0.0, st_viol = 0.0;
+
+  const int64_t nwarps = (int64_t)gridDim.x * kTqcWarps;
+  for (int64_t m = (int64_t)blockIdx.x * kTqcWarps + wib; m < a.M; m += nwarps) {
+    // ---- load: target atoms (coalesced), predicted atoms, per-transition scalars ---------------
+    const float* __restrict__ zrow = a.next_z + m * nz;
+    const float* __restrict__ qrow = a.q_pred + m * n;
+    float e[VPL], q[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      const int j = lane + 32 * s;
+      e[s] = j < nz ? ld_stream1(zrow + j) : CUDART_INF_F;
+      q[s] = j < n ? ld_stream1(qrow + j) : 0.f;
+    }
+    const float rew = a.reward ? __ldg(a.reward + m) : 0.f, msk = a.mask ? __ldg(a.mask + m) : 1.f;
+    const float ent = a.next_log_pi ? __fmul_rn(a.alpha, -__ldg(a.next_log_pi + m)) : 0.f;
+    const float G = a.mc_return ? __ldg(a.mc_return + m) : 0.f;
+    const float gs = a.grad_scale ? __ldg(a.grad_scale + m) : 1.f;
+    const float mg = __fmul_rn(msk, a.gamma);
+
+    // ---- sort ascending, cut the top n_drop, soft target (:50-58) -------------------------------
+    bitonic_sort_from<VPL, 2>(e, lane);
+    float y[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      float z = e[s];
+      if (a.next_log_pi) z = __fadd_rn(z, ent);
+      y[s] = a.reward ? __fadd_rn(rew, __fmul_rn(mg, z)) : z;  // raw mode (quantile_huber_loss_f): targets as given
+    }
+    if (a.td_target) {
+#pragma unroll
+      for (int s = 0; s < VPL; ++s) {
+        const int i = lane * VPL + s;
+        if (i < K) a.td_target[m * K + i] = y[s];
+      }
+    }
+    // centre: a kept target near the median
+    const float c0 = __shfl_sync(kFull, y[0], (K / 2) / VPL);
+    float l1 = 0.f, l2 = 0.f;  // this lane's sums of centred y, y^2 over its kept slots
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      const int i = lane * VPL + s;
+      y[s] = i < K ? y[s] - c0 : CUDART_INF_F;
+      if (i < K) {
+        l1 += y[s];
+        l2 = fmaf(y[s], y[s], l2);
+      }
+    }
+    float x1 = l1, x2 = l2;  // inclusive scan over lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o1 = __shfl_up_sync(kFull, x1, d), o2 = __shfl_up_sync(kFull, x2, d);
+      if (lane >= d) {
+        x1 += o1;
+        x2 += o2;
+      }
+    }
+    float p1 = __shfl_up_sync(kFull, x1, 1), p2 = __shfl_up_sync(kFull, x2, 1);  // exclusive
+    if (lane == 0) p1 = p2 = 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      const int i = lane * VPL + s;
+      Y[i] = y[s];
+      P1[i] = p1;
+      P2[i] = p2;
+      if (i < K) {
+        p1 += y[s];
+        p2 = fmaf(y[s], y[s], p2);
+      }
+    }
+    if (lane == 31) {
+      P1[N] = p1;
+      P2[N] = p2;
+    }
+    __syncwarp();
+    const float T1 = P1[K];
+
+    // ---- per predicted atom: loss and gradient from the three split points ----------------------
+    float acc = 0.f;  // this lane's share of the per-transition loss
+    float qsum = 0.f;
+    int viol = 0;
+    float gout[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      const int j = lane + 32 * s;
+      const float qc = q[s] - c0;
+      const int ia = count_below<N, false>(Y, qc - 1.f);
+      const int ib = count_below<N, false>(Y, qc);
+      const int ic = count_below<N, true>(Y, qc + 1.f);
+      const float tau = __fadd_rn(__fdiv_rn((float)j, (float)n), half_over_n);  // :98, tau over the pooled atoms
+      const float P1a = P1[ia], P1b = P1[ib], P1c = P1[ic];
+      const float P2a = P2[ia], P2b = P2[ib], P2c = P2[ic];
+      const float na = (float)ia, nab = (float)(ib - ia), nbc = (float)(ic - ib), nc = (float)(K - ic);
+      const float d1ab = P1b - P1a, d1bc = P1c - P1b;
+      // sum over a<=k<b of (y-q)^2 = dP2 - 2q dP1 + n q^2, same for b<=k<c
+      const float sqab = fmaf(qc, fmaf(qc, nab, -2.f * d1ab), P2b - P2a);
+      const float sqbc = fmaf(qc, fmaf(qc, nbc, -2.f * d1bc), P2c - P2b);
+      const float neg = fmaf(na, qc - 0.5f, -P1a) + 0.5f * sqab;               // delta < 0 : weight 1 - tau
+      const float pos = 0.5f * sqbc + ((T1 - P1c) - nc * (qc + 0.5f));         // delta >= 0: weight tau
+      const float lj = fmaf(1.f - tau, neg, tau * pos);
+      // d/dq of the same sum
+      const float gneg = na + fmaf(nab, qc, -d1ab);
+      const float gpos = fmaf(nbc, qc, -d1bc) - nc;
+      float gj = fmaf(1.f - tau, gneg, tau * gpos) * inv_nk;
+      float lbj = 0.f;
+      if (a.mc_return) {  // :76-79 lower bound relu(mc_return - q)
+        lbj = fmaxf(G - q[s], 0.f);
+        if (lbj > 0.f) {
+          gj -= inv_n;
+          if (j < n) ++viol;
+        }
+      }
+      if (j < n) {
+        acc += fmaf(lj, inv_nk, lbj * inv_n);
+        qsum += q[s];
+      }
+      gout[s] = gj * gs;
+    }
+    if (a.grad_q) {
+      float* __restrict__ grow_ = a.grad_q + m * n;
+#pragma unroll
+      for (int s = 0; s < VPL; ++s) {
+        const int j = lane + 32 * s;
+        if (j < n) st_stream1(grow_ + j, gout[s]);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && a.loss) a.loss[m] = acc;
+    if (a.stats) {  // :66-67,80-82 q_pred mean, mean row variance (unbiased), constraint violations
+      const float mean = warp_sum(qsum) * inv_n;
+      float dv = 0.f;
+#pragma unroll
+      for (int s = 0; s < VPL; ++s) {
+        const int j = lane + 32 * s;
+        const float d = q[s] - mean;
+        if (j < n) dv = fmaf(d, d, dv);
+      }
+      dv = warp_sum(dv);
+      const int vsum = __reduce_add_sync(kFull, viol);
+      if (lane == 0) {
+        st_sum += (double)mean * n;
+        st_var += (double)dv / (double)(n - 1);
+        st_viol += (double)vsum;
+      }
+    }
+    __syncwarp();
+  }
+  if (a.stats) {
+    if (lane == 0) {
+      atomicAdd(&sm_stats[0], st_sum);
+      atomicAdd(&sm_stats[1], st_var);
+      atomicAdd(&sm_stats[2], st_viol);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(a.stats + threadIdx.x, sm_stats[threadIdx.x]);
+    if (threadIdx.x == 3 && blockIdx.x == 0) atomicAdd(a.stats + 3, (double)a.M);
+  }
+}
+
+// ---- non-distributional variant: min over atoms, smooth-L1, lower bound replaces the TD term where active ----
+struct SacArgs {
+  int64_t M;
+  int32_t n_atoms;
+  const float* target_z;
+  const float* q_pred;
+  const float* next_log_pi;
+  const float* reward;
+  const float* mask;
+  const float* mc_return;
+  const float* grad_scale;
+  float alpha, gamma;
+  float* loss;
+  float* grad_q;
+  double* stats;
+};
+
+__global__ void __launch_bounds__(256) sac_min_target_kernel(const __grid_constant__ SacArgs a) {
+  __shared__ double sm_stats[3];
+  const int lane = lane_id(), wib = threadIdx.x >> 5;
+  const int n = a.n_atoms;
+  const float inv_n = 1.f / (float)n;
+  if (a.stats && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
+  if (a.stats) __syncthreads();
+  double st_sum = 0.0, st_var = 0.0, st_viol = 0.0;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t m = (int64_t)blockIdx.x * 8 + wib; m < a.M; m += nwarps) {
+    const float* __restrict__ zrow = a.target_z + m * n;
+    const float* __restrict__ qrow = a.q_pred + m * n;
+    const float ent = a.next_log_pi ? __fmul_rn(a.alpha, -__ldg(a.next_log_pi + m)) : 0.f;
+    float zmin = CUDART_INF_F;
+    for (int j = lane; j < n; j += 32) {
+      float z = ld_stream1(zrow + j);
+      if (a.next_log_pi) z = __fadd_rn(z, ent);
+      zmin = fminf(zmin, z);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) zmin = fminf(zmin, __shfl_xor_sync(kFull, zmin, d));
+    const float td = __fadd_rn(__ldg(a.reward + m), __fmul_rn(__fmul_rn(__ldg(a.mask + m), a.gamma), zmin));
+    const float G = a.mc_return ? __ldg(a.mc_return + m) : 0.f;
+    const float gs = a.grad_scale ? __ldg(a.grad_scale + m) : 1.f;
+    float acc = 0.f, qsum = 0.f, qsq = 0.f;
+    int viol = 0;
+    for (int j = lane; j < n; j += 32) {
+      const float q = ld_stream1(qrow + j);
+      const float d = q - td, ad = fabsf(d);
+      float l = ad < 1.f ? 0.5f * d * d : ad - 0.5f;  // F.smooth_l1_loss, beta = 1
+      float gq = fminf(fmaxf(d, -1.f), 1.f);
+      if (a.mc_return) {  // soft_actor_critic.py:93-97: q_loss = q_loss * (lb == 0) + lb
+        const float lb = fmaxf(G - q, 0.f);
+        if (lb != 0.f) {
+          l = lb;
+          gq = -1.f;
+          ++viol;
+        }
+      }
+      acc += l;
+      qsum += q;
+      qsq = fmaf(q, q, qsq);
+      if (a.grad_q) st_stream1(a.grad_q + m * n + j, gq * inv_n * gs);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && a.loss) a.loss[m] = acc * inv_n;
+    if (a.stats) {
+      const float mean = warp_sum(qsum) * inv_n;
+      float dv = 0.f;
+      for (int j = lane; j < n; j += 32) {
+        const float d = __ldg(qrow + j) - mean;
+        dv = fmaf(d, d, dv);
+      }
+      dv = warp_sum(dv);
+      const int vsum = __reduce_add_sync(kFull, viol);
+      if (lane == 0) {
+        st_sum += (double)mean * n;
+        st_var += n > 1 ? (double)dv / (double)(n - 1) : 0.0;
+        st_viol += (double)vsum;
+      }
+    }
+  }
+  if (a.stats) {
+    if (lane == 0) {
+      atomicAdd(&sm_stats[0], st_sum);
+      atomicAdd(&sm_stats[1], st_var);
+      atomicAdd(&sm_stats[2], st_viol);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(a.stats + threadIdx.x, sm_stats[threadIdx.x]);
+    if (threadIdx.x == 3 && blockIdx.x == 0) atomicAdd(a.stats + 3, (double)a.M);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int launch_tqc(const TqcArgs& a, cudaStream_t st) {
+  int64_t blocks = (a.M + kTqcWarps - 1) / kTqcWarps;
+  const int64_t max_blocks = (int64_t)num_sms() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  // the sort network holds n_z - n_drop < 32*VPL kept targets plus +inf padding; atoms ride VPL per lane
+  int need = a.n_atoms > a.n_z ? a.n_atoms : a.n_z;
+  if (a.n_z - a.n_drop + 1 > need) need = a.n_z - a.n_drop + 1;
+  if (need <= 32) tqc_loss_kernel<1><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
+  else if (need <= 64) tqc_loss_kernel<2><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
+  else if (need <= 128) tqc_loss_kernel<4><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
+  else tqc_loss_kernel<8><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
+}  // namespace fdql
+
+using namespace fdql;
+
+extern "C" {
+
+int fdql_tqc_loss(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_z, const float* q_pred,
+                  const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,
+                  const float* grad_scale, float alpha, float gamma, float* loss, float* grad_q, float* td_target,
+                  double* stats, void* stream) {
+  FDQL_REQUIRE(M >= 0, "negative M");
+  FDQL_REQUIRE(n_atoms >= 2 && n_atoms <= 256, "n_atoms must be in [2, 256], got %d", n_atoms);
+  // quirk Q8: int(p*CQ)==0 makes the reference slice [:-0], an empty target -> refuse
+  FDQL_REQUIRE(n_drop >= 1 && n_drop < n_atoms, "n_drop must be in [1, n_atoms) (reference: int(top_quantiles_to_drop*CQ)); got %d",
+               n_drop);
+  FDQL_REQUIRE(next_z && q_pred && reward && mask, "null input");
+  if (M == 0) return FDQL_OK;
+  TqcArgs a{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q,
+            td_target, stats};
+  return launch_tqc(a, (cudaStream_t)stream);
+}
+
+int fdql_quantile_huber(int64_t M, int32_t n_quantiles, int32_t n_samples, const float* quantiles, const float* samples,
+                        const float* grad_scale, float* loss, float* grad_q, void* stream) {
+  FDQL_REQUIRE(M >= 0, "negative M");
+  FDQL_REQUIRE(n_quantiles >= 1 && n_quantiles <= 256 && n_samples >= 1 && n_samples <= 255,
+               "need 1 <= n_quantiles <= 256 and 1 <= n_samples <= 255, got %d, %d", n_quantiles, n_samples);
+  FDQL_REQUIRE(quantiles && samples, "null input");
+  if (M == 0) return FDQL_OK;
+  TqcArgs a{M, n_quantiles, n_samples, 0, samples, quantiles, nullptr, nullptr, nullptr, nullptr, grad_scale, 1.f, 1.f,
+            loss, grad_q, nullptr, nullptr};
+  return launch_tqc(a, (cudaStream_t)stream);
+}
+
+int fdql_sac_min_target_loss(int64_t M, int32_t n_atoms, const float* target_z, const float* q_pred, const float* next_log_pi,
+                             const float* reward, const float* mask, const float* mc_return, const float* grad_scale,
+                             float alpha, float gamma, float* loss, float* grad_q, double* stats, void* stream) {
+  FDQL_REQUIRE(M >= 0 && n_atoms >= 1, "bad sizes");
+  FDQL_REQUIRE(target_z && q_pred && reward && mask, "null input");
+  if (M == 0) return FDQL_OK;
+  SacArgs a{M, n_atoms, target_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q, stats};
+  int64_t blocks = (M + 7) / 8;
+  const int64_t max_blocks = (int64_t)num_sms() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  sac_min_target_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
+}  // extern "C"
