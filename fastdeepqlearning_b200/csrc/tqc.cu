@@ -403,8 +403,8 @@ int fdql_tqc_loss(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_
   // quirk Q8: int(p*CQ)==0 makes the reference slice [:-0], an empty target -> refuse
   FDQL_REQUIRE(n_drop >= 1 && n_drop < n_atoms, "n_drop must be in [1, n_atoms) (reference: int(top_quantiles_to_drop*CQ)); got %d",
                n_drop);
-  FDQL_REQUIRE(next_z && q_pred && reward && mask, "null input");
   if (M == 0) return FDQL_OK;
+  FDQL_REQUIRE(next_z && q_pred && reward && mask, "null input");
   TqcArgs a{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q,
             td_target, stats};
   return launch_tqc(a, (cudaStream_t)stream);
@@ -415,8 +415,8 @@ int fdql_quantile_huber(int64_t M, int32_t n_quantiles, int32_t n_samples, const
   FDQL_REQUIRE(M >= 0, "negative M");
   FDQL_REQUIRE(n_quantiles >= 1 && n_quantiles <= 256 && n_samples >= 1 && n_samples <= 255,
                "need 1 <= n_quantiles <= 256 and 1 <= n_samples <= 255, got %d, %d", n_quantiles, n_samples);
-  FDQL_REQUIRE(quantiles && samples, "null input");
   if (M == 0) return FDQL_OK;
+  FDQL_REQUIRE(quantiles && samples, "null input");
   TqcArgs a{M, n_quantiles, n_samples, 0, samples, quantiles, nullptr, nullptr, nullptr, nullptr, grad_scale, 1.f, 1.f,
             loss, grad_q, nullptr, nullptr};
   return launch_tqc(a, (cudaStream_t)stream);
@@ -426,8 +426,8 @@ int fdql_sac_min_target_loss(int64_t M, int32_t n_atoms, const float* target_z, 
                              const float* reward, const float* mask, const float* mc_return, const float* grad_scale,
                              float alpha, float gamma, float* loss, float* grad_q, double* stats, void* stream) {
   FDQL_REQUIRE(M >= 0 && n_atoms >= 1, "bad sizes");
-  FDQL_REQUIRE(target_z && q_pred && reward && mask, "null input");
   if (M == 0) return FDQL_OK;
+  FDQL_REQUIRE(target_z && q_pred && reward && mask, "null input");
   SacArgs a{M, n_atoms, target_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q, stats};
   int64_t blocks = (M + 7) / 8;
   const int64_t max_blocks = (int64_t)num_sms() * 8;

@@ -189,7 +189,7 @@ def _synthetic(rng, n_eps, max_len, G, obs=5, act=2, p_hit=0.15, fixed_len=None)
     return cols, lengths, starts_ep, ends, ep_of
 
 
-@pytest.mark.parametrize("T,G,max_len", [(1, 16, 40), (2, 16, 130), (5, 3, 70), (50, 64, 200), (2, 130, 33), (33, 8, 90)])
+@pytest.mark.parametrize("T,G,max_len", [(1, 16, 40), (2, 16, 130), (5, 3, 70), (50, 64, 200), (2, 100, 33), (33, 8, 90)])
 def test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len):
     """Windows with hindsight flags vs oracle.sample_time_relabel (defined through the reference's write-time rows):
     windows straddling episode ends, episodes longer than 32/64/128 rows, goal widths that are not multiples of 4."""
@@ -236,9 +236,10 @@ def test_ring_wrap_and_stale_rows(R, fdql):
     cap = 128
     ring = R.ReplayMemory(cap, 8, 2)
     ring.set_reward_op(fdql.RewardOp.bitflip(), 0.98)
-    ring.add_rows(cols, episode_lengths=lengths)
+    for e in range(len(lengths)):
+        ring.add_rows({k: v[starts_ep[e]:ends[e] + 1] for k, v in cols.items()}, episode_lengths=[25])
     assert ring._top == N % cap and len(ring) == cap - 1
-    # the last 4 complete episodes are fully resident; episode index 9 wraps (rows 225..249 -> 97..121), 10 wraps the end
+    # the last 5 episodes are fully resident; episode 10 (rows 250..274 -> 122..127, 0..18) wraps the end of the ring
     e = 10
     phys = (np.arange(starts_ep[e], ends[e] + 1)) % cap
     assert phys[0] > phys[-1]

@@ -85,11 +85,17 @@ def test_tqc_vs_oracle_random(ops, n, n_drop, scale, offset):
     rew = rng.standard_normal((M, 1)).astype(np.float32)
     mask = (rng.random((M, 1)) > 0.2).astype(np.float32)
     mc = (q.mean(-1, keepdims=True) + rng.standard_normal((M, 1)) * scale).astype(np.float32)
-    loss, grad, summ = O.tqc_q_loss(q, z, lp, rew, mask, mc, 0.7, 0.99, n_drop)  # float64 brute force
+    # the reference forms the target in fp32 (sort, slice, affine: bit-exact below) and the pairwise loss from it;
+    # the oracle evaluates that loss by brute force in float64
+    td = O.tqc_td_target(z, lp, rew, mask, 0.7, 0.99, n_drop)
+    loss = O.quantile_huber(q, td)[..., None]
+    grad = O.quantile_huber_grad(q, td)
+    lb = np.maximum(mc.astype(np.float64) - q, 0)
+    loss = loss + lb.mean(-1, keepdims=True)
+    grad = grad - (lb > 0) / n
     r = ops.tqc_loss(dev(q), dev(z), dev(lp), dev(rew), dev(mask), dev(mc), 0.7, 0.99, n_drop, want_target=True)
     np.testing.assert_allclose(r["loss"].cpu().numpy(), loss, rtol=1e-5, atol=1e-6)
     grad_close(r["grad"].cpu().numpy(), grad, grad)
-    td = O.tqc_td_target(z, lp, rew, mask, 0.7, 0.99, n_drop)
     np.testing.assert_array_equal(r["td_target"].cpu().numpy(), td)
 
 
