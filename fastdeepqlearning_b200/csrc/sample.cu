@@ -289,6 +289,285 @@ __global__ void __launch_bounds__(256) sample_gather_kernel(const __grid_constan
   }
 }
 
+// =================================================================================================
+// Fast path: every lane owns up to S fixed "row vectors" (one float4 of one key, or of the scalar record) and keeps the
+// source / destination pointers for them in registers for the whole kernel, so a window row costs one 128-bit load and
+// one 128-bit store per lane and no descriptor look-ups.  Used when a row has at most 32*S float4 (S <= 4).
+// =================================================================================================
+enum { SLOT_NONE = 0, SLOT_WIDE4 = 1, SLOT_WIDEP = 2, SLOT_DG4 = 3, SLOT_DGP = 4, SLOT_REC = 5 };
+enum { RC_PLAIN = 0, RC_REWARD = 1, RC_TASK_DONE = 2, RC_EP_STEP = 3, RC_MC_RETURN = 4, RC_SKIP = 7 };
+
+struct Slot {
+  const float* src;  // slab base + 4*v
+  float* dst;        // output base + 4*v (wide) ; unused for the record
+  uint32_t sstride;  // floats between rows of the slab
+  uint32_t dwidth;   // floats between rows of the output
+  uint32_t meta;     // kind | v << 4 | valid floats << 12 | 4 x 3-bit record role codes << 16
+};
+
+template <int S, int LPR, bool RELABEL>
+__global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid_constant__ GatherArgs g) {
+  extern __shared__ float smem[];
+  __shared__ float* sm_scal_out[FDQL_MAX_KEYS + 4];
+  const ArenaDev& A = g.A;
+  const int lane = lane_id();
+  const int wib = threadIdx.x >> 5;
+  const int T = g.T;
+  // per-warp scratch, one entry per window row: relabelled reward, return, final task_done, final episode_step, contiguity
+  float* sm_r = smem + (size_t)wib * 5 * T;
+  float* sm_g = sm_r + T;
+  float* sm_d = sm_g + T;
+  float* sm_s = sm_d + T;
+  float* sm_c = sm_s + T;
+  const int64_t cap = A.capacity;
+  const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
+  const int rec_vecs = A.rec_stride >> 2;
+
+  if (threadIdx.x < FDQL_MAX_KEYS + 4)
+    sm_scal_out[threadIdx.x] = threadIdx.x < A.n_scal ? g.out.p[A.scal_key[threadIdx.x]] : nullptr;
+
+  // ---- the lane's plan -------------------------------------------------------------------------
+  Slot slot[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    int i = lane + 32 * k;
+    Slot sl;
+    sl.src = nullptr; sl.dst = nullptr; sl.sstride = 0; sl.dwidth = 0; sl.meta = SLOT_NONE;
+    bool found = false;
+    for (int w = 0; w < A.n_wide; ++w) {
+      const int vecs = A.wide[w].vecs;
+      if (!found && i < vecs) {
+        found = true;
+        float* o = g.out.p[A.wide[w].key];
+        if (o != nullptr) {
+          const int width = A.wide[w].width;
+          const bool v4 = (width & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+          const bool dg = RELABEL && w == A.wide_dg;
+          sl.src = A.wide[w].base + 4 * i;
+          sl.dst = o + 4 * i;
+          sl.sstride = A.wide[w].stride;
+          sl.dwidth = width;
+          sl.meta = (dg ? (v4 ? SLOT_DG4 : SLOT_DGP) : (v4 ? SLOT_WIDE4 : SLOT_WIDEP)) | (i << 4) | (min(4, width - 4 * i) << 12);
+        }
+      }
+      i -= vecs;
+    }
+    if (!found && i < rec_vecs) {
+      uint32_t codes = 0;
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = 4 * i + c;
+        uint32_t code = RC_SKIP;
+        if (col < A.n_scal && g.out.p[A.scal_key[col]] != nullptr) {
+          any = true;
+          code = col == A.col_reward ? RC_REWARD : col == A.col_task_done ? RC_TASK_DONE : col == A.col_ep_step ? RC_EP_STEP
+                 : col == A.col_mc_return ? RC_MC_RETURN : RC_PLAIN;
+        }
+        codes |= code << (3 * c);
+      }
+      if (any) {
+        sl.src = A.rec + 4 * i;
+        sl.sstride = A.rec_stride;
+        sl.meta = SLOT_REC | (i << 4) | (codes << 16);
+      }
+    }
+    slot[k] = sl;
+  }
+  __syncthreads();
+
+  // gamma^(32-lane): weight of the carried return for this lane's row inside a 32-row pass
+  double wcar = 1.0;
+  if (RELABEL) {
+    double p = g.gamma;
+    int e = 32 - lane;
+    while (e) {
+      if (e & 1) wcar *= p;
+      p *= p;
+      e >>= 1;
+    }
+  }
+  const WideSlab AG = RELABEL ? A.wide[A.wide_ag] : A.wide[0];
+
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t b = g.b_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; b < g.b_end; b += nwarps) {
+    int64_t s = __ldg(g.starts + b);
+    if (s >= g.len) s %= g.len;
+
+    bool relabel = false;
+    int tail_last = -1;
+    int64_t grow = 0, ep_first = 0;
+    if (RELABEL) {
+      if (__ldg(g.flags + b) != 0) {
+        const float* rec = A.rec + s * (int64_t)A.rec_stride;
+        const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
+        if (es >= 0) {
+          relabel = true;
+          ep_first = es;
+          tail_last = (int)(ee - s + (ee < s ? cap : 0));
+          grow = __ldg(g.goal_rows + b);
+        }
+      }
+    }
+
+    int seg_first = -1, j0 = 0;
+    if (RELABEL && relabel) {
+      const float4 gstar = load_goal_slice<LPR>(A, grow);
+      double carry = 0.0;
+      for (int jb = (tail_last >> 5) << 5; jb >= 0; jb -= 32) {
+        float Rg;
+        bool dn;
+        eval_chunk<LPR, false>(A, g.rs, s, jb, tail_last, gstar, Rg, dn);
+        const int j = jb + lane;
+        const bool valid = j <= tail_last;
+        float rnew = 0.f;
+        if (valid) rnew = (float)((double)__ldg(A.ga + ring_row(s, j, cap)) + (double)Rg);
+        double G = warp_suffix_scan(valid ? (double)rnew : 0.0, g.gamma, lane);
+        G = fma(wcar, carry, G);
+        carry = shfl_idx_f64(G, 0);
+        if (valid && j < T) {
+          sm_r[j] = rnew;
+          sm_g[j] = (float)G;
+          sm_d[j] = dn ? 1.f : 0.f;
+        }
+      }
+      j0 = (int)(s - ep_first + (s < ep_first ? cap : 0));
+      if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+        seg_first = 0;
+        for (int jb = ((j0 - 1) >> 5) << 5; jb >= 0 && j0 > 0; jb -= 32) {
+          float Rg;
+          bool dn;
+          eval_chunk<LPR, false>(A, g.rs, ep_first, jb, j0 - 1, gstar, Rg, dn);
+          const unsigned bal = __ballot_sync(kFull, dn && (jb + lane) < j0);
+          if (bal) {
+            seg_first = jb + 32 - __clz(bal);
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- lane <-> window row: final task_done / episode_step of every row, learner aux --------------------
+    if ((RELABEL && relabel) || want_aux) {
+      float contig_sum = 0.f, carry_step = 0.f, carry_mask = 0.f;
+      for (int tb = 0; tb < T; tb += 32) {
+        const int t = tb + lane;
+        const bool valid = t < T;
+        int64_t row = s + (valid ? t : 0);
+        if (row >= g.len) row -= g.len;
+        const float* rec = A.rec + row * (int64_t)A.rec_stride;
+        float v_step = 0.f, v_done = 0.f;
+        if (A.col_ep_step >= 0) v_step = __ldg(rec + A.col_ep_step);
+        if (A.col_task_done >= 0) v_done = __ldg(rec + A.col_task_done);
+        if (RELABEL && relabel) {
+          const bool in_ep = valid && t <= tail_last;
+          const bool dn = in_ep && sm_d[t] != 0.f;
+          const unsigned bal = __ballot_sync(kFull, dn);
+          if (in_ep) {
+            v_done = dn ? 1.f : 0.f;
+            const unsigned below = bal & ((1u << lane) - 1u);
+            const int f = below ? (j0 + tb + 32 - __clz(below)) : seg_first;
+            if (f >= 0 && A.col_ep_step >= 0)
+              v_step = v_step - __ldg(A.rec + ring_row(ep_first, f, cap) * (int64_t)A.rec_stride + A.col_ep_step);
+          }
+          if (bal) seg_first = j0 + tb + 32 - __clz(bal);
+          if (valid) {
+            sm_d[t] = v_done;
+            sm_s[t] = v_step;
+          }
+        }
+        if (want_aux) {
+          // mask = !task_done (deepQlearning.py:201); is_contiguous[t] = (step[t+1]==step[t]+1) & mask[t] (:202-203)
+          const float v_mask = v_done != 0.f ? 0.f : 1.f;
+          if (valid && g.aux_mask) st_stream1(g.aux_mask + (int64_t)t * g.n + b, v_mask);
+          const float nxt = __shfl_down_sync(kFull, v_step, 1);
+          if (lane < 31 && t + 1 < T) {
+            const float c = (nxt == v_step + 1.f && v_mask != 0.f) ? 1.f : 0.f;
+            sm_c[t] = c;
+            contig_sum += c;
+          }
+          const float first_step = __shfl_sync(kFull, v_step, 0);
+          if (tb > 0 && lane == 0) {
+            const float c = (first_step == carry_step + 1.f && carry_mask != 0.f) ? 1.f : 0.f;
+            sm_c[tb - 1] = c;
+            contig_sum += c;
+          }
+          carry_step = __shfl_sync(kFull, v_step, 31);
+          carry_mask = __shfl_sync(kFull, v_mask, 31);
+        }
+      }
+      if (want_aux) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) contig_sum += __shfl_xor_sync(kFull, contig_sum, d);
+        __syncwarp();
+        // upstream weight of q_loss[t,b]: contig / ((sum_t contig + 1e-4) * B * T)  (deepQlearning.py:222-225,249)
+        const float denom = contig_sum + 1e-4f;
+        for (int t = lane; t < T - 1; t += 32) {
+          const float c = sm_c[t];
+          if (g.aux_contig) st_stream1(g.aux_contig + (int64_t)t * g.n + b, c);
+          if (g.aux_weight) st_stream1(g.aux_weight + (int64_t)t * g.n + b, (c / denom) * g.inv_bt);
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- the rows: one 128-bit load + store per lane and slot -----------------------------------------------
+    const float* galt = nullptr;  // this lane's slice of the hindsight goal row (desired_goal slots)
+    if (RELABEL && relabel) galt = AG.base + grow * (int64_t)AG.stride;
+#pragma unroll 2
+    for (int t = 0; t < T; ++t) {
+      int64_t row = s + t;
+      if (row >= g.len) row -= g.len;
+      const bool in_ep = RELABEL && relabel && t <= tail_last;
+      float4 x[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const uint32_t kind = slot[k].meta & 15u;
+        if (kind != SLOT_NONE) {
+          const float* src = slot[k].src + row * (int64_t)slot[k].sstride;
+          if (RELABEL && in_ep && (kind == SLOT_DG4 || kind == SLOT_DGP)) src = galt + 4 * ((slot[k].meta >> 4) & 255u);
+          x[k] = ldg4(src);
+        }
+      }
+      const int64_t orow = (int64_t)t * g.n + b;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const uint32_t meta = slot[k].meta;
+        const uint32_t kind = meta & 15u;
+        if (kind == SLOT_WIDE4 || kind == SLOT_DG4) {
+          st_stream4(slot[k].dst + orow * slot[k].dwidth, x[k]);
+        } else if (kind == SLOT_REC) {
+          const int v = (meta >> 4) & 255u;
+          const float xs[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t code = (meta >> (16 + 3 * c)) & 7u;
+            if (code == RC_SKIP) continue;
+            float val = xs[c];
+            if (RELABEL && relabel) {
+              if (code == RC_TASK_DONE) val = sm_d[t];
+              else if (code == RC_EP_STEP) val = sm_s[t];
+              else if (in_ep && code == RC_REWARD) val = sm_r[t];
+              else if (in_ep && code == RC_MC_RETURN) val = sm_g[t];
+            }
+            st_stream1(sm_scal_out[4 * v + c] + orow, val);
+          }
+        } else if (kind == SLOT_WIDEP || kind == SLOT_DGP) {
+          const int m = (meta >> 12) & 15u;
+          const float xs[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+          float* dst = slot[k].dst + orow * slot[k].dwidth;
+          for (int c = 0; c < m; ++c) st_stream1(dst + c, xs[c]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+
+int g_force_generic_gather = 0;  // tests flip this to cover the descriptor-walking kernel
+
 int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts, const uint8_t* flags,
                          const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host, int32_t n_params,
                          double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out, float* aux_mask,
@@ -323,9 +602,48 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     lpr = lanes_per_row(a->dev.wide[a->dev.wide_ag].vecs);
   }
   const int warps_per_block = 8;
-  const size_t smem = (size_t)warps_per_block * 4 * T * sizeof(float);
+  const size_t smem = (size_t)warps_per_block * 5 * T * sizeof(float);
   FDQL_REQUIRE(smem <= 200 * 1024, "temporal_len %d too long for the per-warp window scratch", T);
-  int64_t blocks = (b_end - b_begin + warps_per_block - 1) / warps_per_block;
+  const int64_t want_blocks = (b_end - b_begin + warps_per_block - 1) / warps_per_block;
+  int64_t blocks = want_blocks;
+  int row_vecs = a->dev.rec_stride / 4;
+  for (int w = 0; w < a->dev.n_wide; ++w) row_vecs += a->dev.wide[w].vecs;
+  const int slots = (row_vecs + 31) / 32;
+  if (slots <= 4 && !g_force_generic_gather) {
+    // persistent-style grid: as many blocks as stay resident, each warp strides over the windows
+#define FDQL_LAUNCH_FAST(SV, LPRV, REL)                                                                                \
+  do {                                                                                                                 \
+    auto kern = sample_gather_fast_kernel<SV, LPRV, REL>;                                                              \
+    if (smem > 40 * 1024) FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int per_sm = 0;                                                                                                    \
+    FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps_per_block * 32, smem));               \
+    if (per_sm < 1) per_sm = 1;                                                                                        \
+    if (blocks > (int64_t)a->num_sms * per_sm) blocks = (int64_t)a->num_sms * per_sm;                                  \
+    kern<<<(unsigned)blocks, warps_per_block * 32, smem, st>>>(g);                                                     \
+  } while (0)
+#define FDQL_FAST_S(LPRV, REL)                                            \
+  do {                                                                    \
+    if (slots <= 1) FDQL_LAUNCH_FAST(1, LPRV, REL);                       \
+    else if (slots == 2) FDQL_LAUNCH_FAST(2, LPRV, REL);                  \
+    else FDQL_LAUNCH_FAST(4, LPRV, REL);                                  \
+  } while (0)
+    if (!relabel) {
+      FDQL_FAST_S(1, false);
+    } else {
+      switch (lpr) {
+        case 1: FDQL_FAST_S(1, true); break;
+        case 2: FDQL_FAST_S(2, true); break;
+        case 4: FDQL_FAST_S(4, true); break;
+        case 8: FDQL_FAST_S(8, true); break;
+        case 16: FDQL_FAST_S(16, true); break;
+        default: FDQL_FAST_S(32, true); break;
+      }
+    }
+#undef FDQL_FAST_S
+#undef FDQL_LAUNCH_FAST
+    FDQL_CUDA(cudaGetLastError());
+    return FDQL_OK;
+  }
   const int64_t max_blocks = (int64_t)a->num_sms * 8;
   if (blocks > max_blocks) blocks = max_blocks;
 #define FDQL_LAUNCH_GATHER(LPRV, REL)                                                                              \
@@ -357,6 +675,12 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
 using namespace fdql;
 
 extern "C" {
+
+int fdql_debug_force_generic_gather(int on) {
+  const int old = g_force_generic_gather;
+  g_force_generic_gather = on;
+  return old;
+}
 
 int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
                         uint64_t counter, int64_t* starts, uint8_t* flags, int64_t* goal_rows, void* stream) {

@@ -127,6 +127,10 @@ int fdql_sample_gather(const fdql_arena* a, int64_t n_windows, int32_t T, int64_
                        int32_t batch_for_weight, float* const* out, float* aux_mask, float* aux_contig,
                        float* aux_weight, void* stream);
 
+/* test hook: route fdql_sample_gather / fdql_gather_rows through the descriptor-walking kernel that serves rows wider
+ * than 128 float4 (returns the previous setting) */
+int fdql_debug_force_generic_gather(int on);
+
 /* DistributionalSoftActorCritic.q_loss from the MLP outputs onward + quantile_huber_loss_f, forward and backward
  * (franQ/Agent/components/distributional_soft_actor_critic.py:50-58,70,76-82,90-103): pool+sort the n_atoms target
  * atoms, keep the n_atoms-n_drop smallest, y = reward + mask*gamma*(z + alpha*(-log_pi)), quantile-Huber against
