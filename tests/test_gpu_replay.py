@@ -322,3 +322,27 @@ def test_full_size_properties(R, fdql):
     unrel = ~f
     assert torch.equal(out["mc_return"][:, unrel], mem["mc_return"][idx][:, unrel])
     assert torch.equal(out["mask"], 1 - out["task_done"])
+
+
+@pytest.mark.parametrize("T,G,max_len", [(2, 16, 130), (50, 64, 200), (5, 3, 70)])
+def test_descriptor_walking_gather_kernel(R, fdql, T, G, max_len):
+    """Rows wider than 128 float4 take the descriptor-walking kernel; force it on ordinary shapes and repeat the parity run."""
+    lib = fdql.lib()
+    old = lib.fdql_debug_force_generic_gather(1)
+    try:
+        test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len)
+    finally:
+        lib.fdql_debug_force_generic_gather(old)
+
+
+def test_wide_rows_take_the_generic_kernel(R):
+    rng = np.random.default_rng(2)
+    N = 300
+    cols = {"obs": rng.standard_normal((N, 600)).astype(np.float32), "reward": rng.standard_normal((N, 1)).astype(np.float32)}
+    ring = R.ReplayMemory(N + 1, 8, 3)
+    ring.add_rows(cols)
+    starts = rng.integers(0, N - 3, 64)
+    out = ring.temporal_sample(starts=starts)
+    idx = np.arange(3)[:, None] + starts[None]
+    np.testing.assert_array_equal(npy(out["obs"]), cols["obs"][idx])
+    np.testing.assert_array_equal(npy(out["reward"]), cols["reward"][idx])
