@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) append_kernel(ArenaDev A, SrcPtrs src, in
       }
       *reinterpret_cast<float4*>(rec + c0) = make_float4(t[0], t[1], t[2], t[3]);
     }
-    A.ga[row] = 0.f;
+    A.scan[row] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -122,11 +122,16 @@ commit_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ ep_begin, c
     float* rec = A.rec + row * (int64_t)A.rec_stride;
     float Rdg = 0.f;
     bool d;
+    uint64_t h = 0;
+    bool has_nan = false;
     if (want_ga) eval_chunk<LPR, true>(A, rs, s, jb, L - 1, zero, Rdg, d);
+    if (A.wide_ag >= 0) hash_chunk<LPR>(A, s, jb, L - 1, h, has_nan);
     if (valid) {
       rec[A.col_ep_start] = __int_as_float((int)s);
       rec[A.col_ep_end] = __int_as_float((int)e);
-      if (want_ga) A.ga[row] = (float)((double)rec[A.col_reward] - (double)Rdg);
+      const float ga = want_ga ? (float)((double)rec[A.col_reward] - (double)Rdg) : 0.f;
+      A.scan[row] = make_float4(__uint_as_float((uint32_t)h), __uint_as_float((uint32_t)(h >> 32)), ga,
+                                __uint_as_float(has_nan ? 1u : 0u));
     }
   }
   if (with_returns && A.col_mc_return >= 0 && A.col_reward >= 0) {
@@ -177,9 +182,11 @@ her_flush_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ src_begi
     const int j = jb + lane;
     const bool valid = j < L;
     float Rg, Rdg = 0.f;
-    bool dn, dtmp;
+    bool dn, dtmp, has_nan;
+    uint64_t h;
     eval_chunk<LPR, false>(A, rs, s, jb, L - 1, gstar, Rg, dn);
     if (A.wide_dg >= 0) eval_chunk<LPR, true>(A, rs, s, jb, L - 1, gstar, Rdg, dtmp);
+    hash_chunk<LPR>(A, s, jb, L - 1, h, has_nan);  // achieved_goal is copied verbatim: same hash as the source row
     const unsigned bal = __ballot_sync(kFull, valid && dn);
     if (valid) {
       const int64_t srow = ring_row(s, j, A.capacity), drow = ring_row(d0, j, A.capacity);
@@ -199,7 +206,8 @@ her_flush_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ src_begi
       }
       rd[A.col_ep_start] = __int_as_float((int)d0);
       rd[A.col_ep_end] = __int_as_float((int)dend);
-      A.ga[drow] = ga;
+      A.scan[drow] = make_float4(__uint_as_float((uint32_t)h), __uint_as_float((uint32_t)(h >> 32)), ga,
+                                 __uint_as_float(has_nan ? 1u : 0u));
     }
     if (bal) seg_first = jb + 32 - __clz(bal);
   }
@@ -301,7 +309,7 @@ int fdql_arena_create(int64_t capacity, int32_t n_keys, const int32_t* widths, c
   bool ok = true;
   for (int s = 0; s < D.n_wide && ok; ++s) ok = alloc(&D.wide[s].base, (size_t)capacity * D.wide[s].stride);
   ok = ok && alloc(&D.rec, (size_t)capacity * D.rec_stride);
-  ok = ok && alloc(&D.ga, (size_t)capacity);
+  ok = ok && alloc(reinterpret_cast<float**>(&D.scan), (size_t)capacity * 4);
   ok = ok && alloc(&a->reward_params_dev, kMaxRewardParams + 4);
   if (!ok) {
     set_error("cudaMalloc failed while allocating the arena (%zu bytes so far): %s", total,
@@ -321,7 +329,7 @@ int fdql_arena_destroy(fdql_arena* a) {
   for (int s = 0; s < a->dev.n_wide; ++s)
     if (a->dev.wide[s].base) cudaFree(a->dev.wide[s].base);
   if (a->dev.rec) cudaFree(a->dev.rec);
-  if (a->dev.ga) cudaFree(a->dev.ga);
+  if (a->dev.scan) cudaFree(a->dev.scan);
   if (a->reward_params_dev) cudaFree(a->reward_params_dev);
   if (a->stage_dev) cudaFree(a->stage_dev);
   if (a->step_dev) cudaFree(a->step_dev);
@@ -368,9 +376,9 @@ int fdql_arena_key_view(const fdql_arena* a, int32_t key, float** base, int64_t*
 int fdql_arena_meta_view(const fdql_arena* a, int32_t which, float** base, int64_t* row_stride, int32_t* col) {
   FDQL_REQUIRE(a != nullptr && which >= 0 && which <= 2, "bad meta column");
   if (which == 2) {
-    *base = a->dev.ga;
-    *row_stride = 1;
-    *col = 0;
+    *base = reinterpret_cast<float*>(a->dev.scan);
+    *row_stride = 4;
+    *col = 2;
   } else {
     *base = a->dev.rec;
     *row_stride = a->dev.rec_stride;

@@ -35,8 +35,12 @@ void set_error(const char* fmt, ...);
 // to 4 floats so that every row starts 16B-aligned and is moved with 128-bit loads.
 // Width-1 keys: packed side by side into one record per row, [capacity, rec_stride], followed by two int32
 // columns holding the episode extents (first/last row of the row's episode, -1 until committed).
-// ga: [capacity] goal-agnostic reward r - R(ag, dg) (her.py:65-68), its own slab so that episode scans read it
-// as one contiguous run.
+// scan: [capacity] 16-byte scan record per row, written when the row's episode is committed:
+//   .x/.y  64-bit hash of the row's achieved_goal (-0 folded into +0, so equal vectors have equal hashes)
+//   .z     goal-agnostic reward r - R(ag, dg) (her.py:65-68)
+//   .w     bit 0: the achieved_goal holds a NaN (never equal to anything)
+// Episode scans read it as one contiguous run of 16 B per row; for equality rewards the hash decides "differs" exactly
+// and only hash matches are verified against the full vectors.
 struct WideSlab {
   float* base;
   int32_t stride;  // floats, multiple of 4
@@ -50,7 +54,7 @@ struct ArenaDev {
   int32_t n_wide, n_scal, rec_stride, pad0;
   WideSlab wide[FDQL_MAX_KEYS];
   float* rec;
-  float* ga;
+  float4* scan;
   int32_t scal_key[FDQL_MAX_KEYS];  // record column -> caller's key index
   int32_t col_ep_start, col_ep_end;
   int32_t col_reward, col_task_done, col_ep_done, col_ep_step, col_mc_return;  // record column or -1

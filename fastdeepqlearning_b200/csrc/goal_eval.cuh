@@ -102,6 +102,78 @@ __device__ __forceinline__ void eval_chunk(const ArenaDev& A, const RewardSpec& 
   }
 }
 
+// ---- 64-bit hash of achieved_goal rows (lane <-> row jbase+lane on return), same lane layout as eval_chunk -------------
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  return h;
+}
+__device__ __forceinline__ uint32_t canon_bits(float x) { return x == 0.f ? 0u : __float_as_uint(x); }
+
+template <int LPR>
+__device__ __forceinline__ void hash_chunk(const ArenaDev& A, int64_t ep_first, int32_t jbase, int32_t jmax, uint64_t& hash,
+                                           bool& has_nan) {
+  constexpr int RPP = 32 / LPR;
+  const int lane = lane_id();
+  const int v = lane % LPR, rloc = lane / LPR;
+  const WideSlab& ag = A.wide[A.wide_ag];
+  const bool vok = v < ag.vecs;
+  hash = 0;
+  has_nan = false;
+#pragma unroll 1
+  for (int p = 0; p < LPR; ++p) {
+    const int j = jbase + p * RPP + rloc;
+    const bool ok = vok && j <= jmax;
+    const int64_t row = ring_row(ep_first, j, A.capacity);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) a = ldg4(ag.base + row * (int64_t)ag.stride + 4 * v);
+    const int m = min(4, ag.width - 4 * v);  // floats of this slice that belong to the key
+    const float xs[4] = {a.x, a.y, a.z, a.w};
+    uint64_t h = 0;
+    bool nan = false;
+    if (ok) {
+      h = 0x9E3779B97F4A7C15ull * (uint64_t)(v + 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < m) {
+          h = mix64(h ^ ((uint64_t)canon_bits(xs[c]) + ((uint64_t)(c + 1) << 32)));
+          nan |= (xs[c] != xs[c]);
+        }
+    }
+    uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+#pragma unroll
+    for (int mk = LPR / 2; mk >= 1; mk >>= 1) {
+      lo ^= __shfl_xor_sync(kFull, lo, mk);
+      hi ^= __shfl_xor_sync(kFull, hi, mk);
+    }
+    const unsigned nb = __ballot_sync(kFull, nan);
+    const int src = (lane % RPP) * LPR;
+    const uint32_t tlo = __shfl_sync(kFull, lo, src), thi = __shfl_sync(kFull, hi, src);
+    if ((lane / RPP) == p) {
+      constexpr unsigned GM = LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u);
+      hash = ((uint64_t)thi << 32) | tlo;
+      has_nan = ((nb >> src) & GM) != 0u;
+    }
+  }
+}
+
+// full-vector equality of achieved_goal[row] and achieved_goal[goal_row], by one lane (verification of a hash match)
+__device__ __forceinline__ bool rows_equal(const ArenaDev& A, int64_t row, int64_t goal_row) {
+  const WideSlab& ag = A.wide[A.wide_ag];
+  const float* a = ag.base + row * (int64_t)ag.stride;
+  const float* g = ag.base + goal_row * (int64_t)ag.stride;
+  bool eq = true;
+  for (int c = 0; c < ag.width; c += 4) {
+    const float4 x = ldg4(a + c), y = ldg4(g + c);
+    const int m = ag.width - c;
+    eq &= (x.x == y.x) & (m < 2 || x.y == y.y) & (m < 3 || x.z == y.z) & (m < 4 || x.w == y.w);
+  }
+  return eq;
+}
+
 // lanes-per-row for a goal slab of `vecs` float4 (power of two, <= 32); vecs > 32 is rejected on the host
 inline int lanes_per_row(int vecs) {
   int l = 1;

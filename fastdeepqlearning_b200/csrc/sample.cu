@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) sample_gather_kernel(const __grid_constan
         const int j = jb + lane;
         const bool valid = j <= tail_last;
         float rnew = 0.f;
-        if (valid) rnew = (float)((double)__ldg(A.ga + ring_row(s, j, cap)) + (double)Rg);
+        if (valid) rnew = (float)((double)__ldg(reinterpret_cast<const float*>(A.scan + ring_row(s, j, cap)) + 2) + (double)Rg);
         double G = warp_suffix_scan(valid ? (double)rnew : 0.0, gam, lane);
         G = fma(wcar, carry, G);
         carry = shfl_idx_f64(G, 0);
@@ -293,6 +293,12 @@ __global__ void __launch_bounds__(256) sample_gather_kernel(const __grid_constan
 // Fast path: every lane owns up to S fixed "row vectors" (one float4 of one key, or of the scalar record) and keeps the
 // source / destination pointers for them in registers for the whole kernel, so a window row costs one 128-bit load and
 // one 128-bit store per lane and no descriptor look-ups.  Used when a row has at most 32*S float4 (S <= 4).
+//   MODE 0  plain gather
+//   MODE 1  hindsight relabel, reward functor evaluated on the full goal vectors (any functor)
+//   MODE 2  hindsight relabel for equality rewards (bitflip): the 16-byte scan records of the episode tail are read
+//           128 rows at a time (4 independent 128-bit loads per lane), "differs" is decided by the stored 64-bit hash
+//           and only hash matches are verified on the full vectors -> exact, at 16 B instead of 4*G+4 B per tail row.
+// The loads of the first two window rows are issued before the relabel scan, so their latency hides behind it.
 // =================================================================================================
 enum { SLOT_NONE = 0, SLOT_WIDE4 = 1, SLOT_WIDEP = 2, SLOT_DG4 = 3, SLOT_DGP = 4, SLOT_REC = 5 };
 enum { RC_PLAIN = 0, RC_REWARD = 1, RC_TASK_DONE = 2, RC_EP_STEP = 3, RC_MC_RETURN = 4, RC_SKIP = 7 };
@@ -305,8 +311,10 @@ struct Slot {
   uint32_t meta;     // kind | v << 4 | valid floats << 12 | 4 x 3-bit record role codes << 16
 };
 
-template <int S, int LPR, bool RELABEL>
-__global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid_constant__ GatherArgs g) {
+template <int S, int LPR, int MODE>
+__global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_kernel(const __grid_constant__ GatherArgs g) {
+  constexpr bool RELABEL = MODE != 0;
+  constexpr int HEAD = 2;  // window rows whose loads are issued ahead of the scan
   extern __shared__ float smem[];
   __shared__ float* sm_scal_out[FDQL_MAX_KEYS + 4];
   const ArenaDev& A = g.A;
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid
     bool found = false;
     for (int w = 0; w < A.n_wide; ++w) {
       const int vecs = A.wide[w].vecs;
-      if (!found && i < vecs) {
+      if (!found && i >= 0 && i < vecs) {
         found = true;
         float* o = g.out.p[A.wide[w].key];
         if (o != nullptr) {
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid
       }
       i -= vecs;
     }
-    if (!found && i < rec_vecs) {
+    if (!found && i >= 0 && i < rec_vecs) {
       uint32_t codes = 0;
       bool any = false;
 #pragma unroll
@@ -388,60 +396,142 @@ __global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid
     }
   }
   const WideSlab AG = RELABEL ? A.wide[A.wide_ag] : A.wide[0];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t b = g.b_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; b < g.b_end; b += nwarps) {
     int64_t s = __ldg(g.starts + b);
+    bool flag = false;
+    int64_t grow = 0;
+    if (RELABEL) {
+      flag = __ldg(g.flags + b) != 0;
+      grow = __ldg(g.goal_rows + b);
+    }
     if (s >= g.len) s %= g.len;
 
-    bool relabel = false;
-    int tail_last = -1;
-    int64_t grow = 0, ep_first = 0;
+    // ---- issue the loads that depend on the streams only: episode extents, head rows, goal row ----------------------
+    int es = -1, ee = -1;
+    if (RELABEL && flag) {
+      const float* rec = A.rec + s * (int64_t)A.rec_stride;
+      es = __float_as_int(__ldg(rec + A.col_ep_start));
+      ee = __float_as_int(__ldg(rec + A.col_ep_end));
+    }
+    float4 xh[HEAD][S], xalt[S];
+#pragma unroll
+    for (int t = 0; t < HEAD; ++t) {
+      int64_t row = s + t;
+      if (row >= g.len) row -= g.len;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        xh[t][k] = zero4;
+        if (t < T && (slot[k].meta & 15u) != SLOT_NONE) xh[t][k] = ldg4(slot[k].src + row * (int64_t)slot[k].sstride);
+      }
+    }
     if (RELABEL) {
-      if (__ldg(g.flags + b) != 0) {
-        const float* rec = A.rec + s * (int64_t)A.rec_stride;
-        const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
-        if (es >= 0) {
-          relabel = true;
-          ep_first = es;
-          tail_last = (int)(ee - s + (ee < s ? cap : 0));
-          grow = __ldg(g.goal_rows + b);
-        }
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const uint32_t kind = slot[k].meta & 15u;
+        xalt[k] = zero4;
+        if (flag && (kind == SLOT_DG4 || kind == SLOT_DGP))
+          xalt[k] = ldg4(AG.base + grow * (int64_t)AG.stride + 4 * ((slot[k].meta >> 4) & 255u));
       }
     }
 
+    bool relabel = false;
+    int tail_last = -1;
+    int64_t ep_first = 0;
+    if (RELABEL && flag && es >= 0) {
+      relabel = true;
+      ep_first = es;
+      tail_last = (int)(ee - s + (ee < s ? cap : 0));
+    }
+
+    // ---- hindsight scan over the episode tail (her.py:62-69 + nstep_return.py:69-72, quirk Q5) -----------------------
     int seg_first = -1, j0 = 0;
     if (RELABEL && relabel) {
-      const float4 gstar = load_goal_slice<LPR>(A, grow);
-      double carry = 0.0;
-      for (int jb = (tail_last >> 5) << 5; jb >= 0; jb -= 32) {
-        float Rg;
-        bool dn;
-        eval_chunk<LPR, false>(A, g.rs, s, jb, tail_last, gstar, Rg, dn);
-        const int j = jb + lane;
-        const bool valid = j <= tail_last;
-        float rnew = 0.f;
-        if (valid) rnew = (float)((double)__ldg(A.ga + ring_row(s, j, cap)) + (double)Rg);
-        double G = warp_suffix_scan(valid ? (double)rnew : 0.0, g.gamma, lane);
-        G = fma(wcar, carry, G);
-        carry = shfl_idx_f64(G, 0);
-        if (valid && j < T) {
-          sm_r[j] = rnew;
-          sm_g[j] = (float)G;
-          sm_d[j] = dn ? 1.f : 0.f;
-        }
-      }
       j0 = (int)(s - ep_first + (s < ep_first ? cap : 0));
-      if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
-        seg_first = 0;
-        for (int jb = ((j0 - 1) >> 5) << 5; jb >= 0 && j0 > 0; jb -= 32) {
+      double carry = 0.0;
+      if (MODE == 2) {
+        const float4 gsc = __ldg(A.scan + grow);
+        const int64_t gd = grow - s + (grow < s ? cap : 0);  // window-relative index of the goal row (may lie outside the tail)
+        for (int jb = (tail_last >> 7) << 7; jb >= 0; jb -= 128) {
+          float4 r4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = jb + 32 * u + lane;
+            r4[u] = j <= tail_last ? __ldg(A.scan + ring_row(s, j, cap)) : zero4;
+          }
+#pragma unroll
+          for (int u = 3; u >= 0; --u) {
+            const int jbu = jb + 32 * u;
+            if (jbu > tail_last) continue;
+            const int j = jbu + lane;
+            const bool valid = j <= tail_last;
+            bool m = valid && __float_as_uint(r4[u].x) == __float_as_uint(gsc.x) && __float_as_uint(r4[u].y) == __float_as_uint(gsc.y);
+            if (m) {  // hash match: the goal row itself is equal unless it holds a NaN; any other row is verified
+              if ((int64_t)j == gd) m = (__float_as_uint(r4[u].w) & 1u) == 0u;
+              else m = rows_equal(A, ring_row(s, j, cap), grow);
+            }
+            const float rnew = valid ? (float)((double)r4[u].z + (m ? 0.0 : -1.0)) : 0.f;
+            double G = warp_suffix_scan((double)rnew, g.gamma, lane);
+            G = fma(wcar, carry, G);
+            carry = shfl_idx_f64(G, 0);
+            if (valid && j < T) {
+              sm_r[j] = rnew;
+              sm_g[j] = (float)G;
+              sm_d[j] = m ? 1.f : 0.f;
+            }
+          }
+        }
+        if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+          seg_first = 0;
+          for (int jb = ((j0 - 1) >> 5) << 5; jb >= 0 && j0 > 0; jb -= 32) {
+            const int j = jb + lane;
+            const bool valid = j < j0;
+            const int64_t row = ring_row(ep_first, valid ? j : 0, cap);
+            const float4 r = valid ? __ldg(A.scan + row) : zero4;
+            bool m = valid && __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+            if (m) {
+              if (row == grow) m = (__float_as_uint(r.w) & 1u) == 0u;
+              else m = rows_equal(A, row, grow);
+            }
+            const unsigned bal = __ballot_sync(kFull, m);
+            if (bal) {
+              seg_first = jb + 32 - __clz(bal);
+              break;
+            }
+          }
+        }
+      } else {
+        const float4 gstar = load_goal_slice<LPR>(A, grow);
+        for (int jb = (tail_last >> 5) << 5; jb >= 0; jb -= 32) {
           float Rg;
           bool dn;
-          eval_chunk<LPR, false>(A, g.rs, ep_first, jb, j0 - 1, gstar, Rg, dn);
-          const unsigned bal = __ballot_sync(kFull, dn && (jb + lane) < j0);
-          if (bal) {
-            seg_first = jb + 32 - __clz(bal);
-            break;
+          eval_chunk<LPR, false>(A, g.rs, s, jb, tail_last, gstar, Rg, dn);
+          const int j = jb + lane;
+          const bool valid = j <= tail_last;
+          float rnew = 0.f;
+          if (valid) rnew = (float)((double)__ldg(reinterpret_cast<const float*>(A.scan + ring_row(s, j, cap)) + 2) + (double)Rg);
+          double G = warp_suffix_scan(valid ? (double)rnew : 0.0, g.gamma, lane);
+          G = fma(wcar, carry, G);
+          carry = shfl_idx_f64(G, 0);
+          if (valid && j < T) {
+            sm_r[j] = rnew;
+            sm_g[j] = (float)G;
+            sm_d[j] = dn ? 1.f : 0.f;
+          }
+        }
+        if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+          seg_first = 0;
+          for (int jb = ((j0 - 1) >> 5) << 5; jb >= 0 && j0 > 0; jb -= 32) {
+            float Rg;
+            bool dn;
+            eval_chunk<LPR, false>(A, g.rs, ep_first, jb, j0 - 1, gstar, Rg, dn);
+            const unsigned bal = __ballot_sync(kFull, dn && (jb + lane) < j0);
+            if (bal) {
+              seg_first = jb + 32 - __clz(bal);
+              break;
+            }
           }
         }
       }
@@ -513,33 +603,20 @@ __global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid
     }
 
     // ---- the rows: one 128-bit load + store per lane and slot -----------------------------------------------
-    const float* galt = nullptr;  // this lane's slice of the hindsight goal row (desired_goal slots)
-    if (RELABEL && relabel) galt = AG.base + grow * (int64_t)AG.stride;
-#pragma unroll 2
-    for (int t = 0; t < T; ++t) {
-      int64_t row = s + t;
-      if (row >= g.len) row -= g.len;
+    auto emit = [&](int t, const float4 (&x)[S]) {
       const bool in_ep = RELABEL && relabel && t <= tail_last;
-      float4 x[S];
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const uint32_t kind = slot[k].meta & 15u;
-        if (kind != SLOT_NONE) {
-          const float* src = slot[k].src + row * (int64_t)slot[k].sstride;
-          if (RELABEL && in_ep && (kind == SLOT_DG4 || kind == SLOT_DGP)) src = galt + 4 * ((slot[k].meta >> 4) & 255u);
-          x[k] = ldg4(src);
-        }
-      }
       const int64_t orow = (int64_t)t * g.n + b;
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         const uint32_t meta = slot[k].meta;
         const uint32_t kind = meta & 15u;
+        float4 v4 = x[k];
+        if (RELABEL && in_ep && (kind == SLOT_DG4 || kind == SLOT_DGP)) v4 = xalt[k];
         if (kind == SLOT_WIDE4 || kind == SLOT_DG4) {
-          st_stream4(slot[k].dst + orow * slot[k].dwidth, x[k]);
+          st_stream4(slot[k].dst + orow * slot[k].dwidth, v4);
         } else if (kind == SLOT_REC) {
           const int v = (meta >> 4) & 255u;
-          const float xs[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+          const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t code = (meta >> (16 + 3 * c)) & 7u;
@@ -555,18 +632,32 @@ __global__ void __launch_bounds__(256, 3) sample_gather_fast_kernel(const __grid
           }
         } else if (kind == SLOT_WIDEP || kind == SLOT_DGP) {
           const int m = (meta >> 12) & 15u;
-          const float xs[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+          const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
           float* dst = slot[k].dst + orow * slot[k].dwidth;
           for (int c = 0; c < m; ++c) st_stream1(dst + c, xs[c]);
         }
       }
+    };
+#pragma unroll
+    for (int t = 0; t < HEAD; ++t)
+      if (t < T) emit(t, xh[t]);
+    for (int t = HEAD; t < T; ++t) {
+      int64_t row = s + t;
+      if (row >= g.len) row -= g.len;
+      float4 x[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        x[k] = zero4;
+        if ((slot[k].meta & 15u) != SLOT_NONE) x[k] = ldg4(slot[k].src + row * (int64_t)slot[k].sstride);
+      }
+      emit(t, x);
     }
     __syncwarp();
   }
 }
 
-
-int g_force_generic_gather = 0;  // tests flip this to cover the descriptor-walking kernel
+int g_force_generic_gather = 0;       // tests flip this to cover the descriptor-walking kernel
+int g_force_full_vector_relabel = 0;  // ... and this to cover MODE 1 with the bitflip functor
 
 int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts, const uint8_t* flags,
                          const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host, int32_t n_params,
@@ -611,9 +702,9 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   const int slots = (row_vecs + 31) / 32;
   if (slots <= 4 && !g_force_generic_gather) {
     // persistent-style grid: as many blocks as stay resident, each warp strides over the windows
-#define FDQL_LAUNCH_FAST(SV, LPRV, REL)                                                                                \
+#define FDQL_LAUNCH_FAST(SV, LPRV, MODEV)                                                                              \
   do {                                                                                                                 \
-    auto kern = sample_gather_fast_kernel<SV, LPRV, REL>;                                                              \
+    auto kern = sample_gather_fast_kernel<SV, LPRV, MODEV>;                                                            \
     if (smem > 40 * 1024) FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 0;                                                                                                    \
     FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps_per_block * 32, smem));               \
@@ -621,22 +712,24 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     if (blocks > (int64_t)a->num_sms * per_sm) blocks = (int64_t)a->num_sms * per_sm;                                  \
     kern<<<(unsigned)blocks, warps_per_block * 32, smem, st>>>(g);                                                     \
   } while (0)
-#define FDQL_FAST_S(LPRV, REL)                                            \
-  do {                                                                    \
-    if (slots <= 1) FDQL_LAUNCH_FAST(1, LPRV, REL);                       \
-    else if (slots == 2) FDQL_LAUNCH_FAST(2, LPRV, REL);                  \
-    else FDQL_LAUNCH_FAST(4, LPRV, REL);                                  \
+#define FDQL_FAST_S(LPRV, MODEV)                                            \
+  do {                                                                      \
+    if (slots <= 1) FDQL_LAUNCH_FAST(1, LPRV, MODEV);                       \
+    else if (slots == 2) FDQL_LAUNCH_FAST(2, LPRV, MODEV);                  \
+    else FDQL_LAUNCH_FAST(4, LPRV, MODEV);                                  \
   } while (0)
     if (!relabel) {
-      FDQL_FAST_S(1, false);
+      FDQL_FAST_S(1, 0);
+    } else if (reward_op == FDQL_REWARD_BITFLIP && !g_force_full_vector_relabel) {
+      FDQL_FAST_S(1, 2);
     } else {
       switch (lpr) {
-        case 1: FDQL_FAST_S(1, true); break;
-        case 2: FDQL_FAST_S(2, true); break;
-        case 4: FDQL_FAST_S(4, true); break;
-        case 8: FDQL_FAST_S(8, true); break;
-        case 16: FDQL_FAST_S(16, true); break;
-        default: FDQL_FAST_S(32, true); break;
+        case 1: FDQL_FAST_S(1, 1); break;
+        case 2: FDQL_FAST_S(2, 1); break;
+        case 4: FDQL_FAST_S(4, 1); break;
+        case 8: FDQL_FAST_S(8, 1); break;
+        case 16: FDQL_FAST_S(16, 1); break;
+        default: FDQL_FAST_S(32, 1); break;
       }
     }
 #undef FDQL_FAST_S
@@ -677,8 +770,9 @@ using namespace fdql;
 extern "C" {
 
 int fdql_debug_force_generic_gather(int on) {
-  const int old = g_force_generic_gather;
-  g_force_generic_gather = on;
+  const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
+  g_force_generic_gather = on & 1;
+  g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }
 

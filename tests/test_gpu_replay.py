@@ -335,6 +335,50 @@ def test_descriptor_walking_gather_kernel(R, fdql, T, G, max_len):
         lib.fdql_debug_force_generic_gather(old)
 
 
+@pytest.mark.parametrize("T,G,max_len", [(2, 16, 130), (50, 64, 200), (5, 3, 70), (2, 100, 33)])
+def test_full_vector_relabel_scan_with_bitflip(R, fdql, T, G, max_len):
+    """The bitflip functor normally takes the hash-assisted scan (16 B scan record per tail row, hash matches verified on the
+    full vectors); force the full-vector scan that the other functors use and repeat the parity run."""
+    lib = fdql.lib()
+    old = lib.fdql_debug_force_generic_gather(2)
+    try:
+        test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len)
+    finally:
+        lib.fdql_debug_force_generic_gather(old)
+
+
+def test_hash_scan_verifies_matches_and_nans(R, fdql):
+    """Exactness of the hash-assisted scan does not rest on the hash: -0.0 == +0.0 must match, NaN never matches (not even the
+    goal row itself), and equal rows elsewhere in the tail are found."""
+    L = 40
+    ag = np.arange(L * 4, dtype=np.float32).reshape(L, 4)
+    ag[10] = [0.0, 1.0, 2.0, 3.0]
+    ag[20] = [-0.0, 1.0, 2.0, 3.0]      # equals row 10 as floats, differs in bits
+    ag[25] = [0.0, 1.0, 2.0, 3.0]
+    ag[30] = [np.nan, 1.0, 2.0, 3.0]    # a goal row holding NaN matches nothing, itself included
+    dg = np.tile(np.array([[9.0, 9.0, 9.0, 9.0]], np.float32), (L, 1))
+    step = np.arange(L, dtype=np.float32).reshape(-1, 1)
+    cols = {"achieved_goal": ag, "desired_goal": dg, "reward": np.full((L, 1), -1, np.float32), "task_done": np.zeros((L, 1), np.float32),
+            "episode_done": (step == L - 1).astype(np.float32), "episode_step": step, "mc_return": np.zeros((L, 1), np.float32)}
+    ring = R.ReplayMemory(64, 4, 1)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.9)
+    ring.add_rows(cols, episode_lengths=[L], with_returns=True)
+    starts = np.arange(L)
+    for goal in (10, 20, 30, 39):
+        got = ring.temporal_sample(starts=starts, flags=np.ones(L, np.uint8), goal_rows=np.full(L, goal), exact_episode_step=True, length=L)
+        with np.errstate(invalid="ignore"):
+            want = O.sample_time_relabel(cols, starts, 1, np.ones(L, bool), np.full(L, goal), np.zeros(L, int), np.full(L, L - 1),
+                                         O.reward_bitflip, 0.9)
+        for k in ("task_done", "episode_step", "reward"):
+            np.testing.assert_array_equal(npy(got[k]), want[k], err_msg=f"{k} goal={goal}")
+        np.testing.assert_allclose(npy(got["mc_return"]), want["mc_return"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(npy(got["desired_goal"]), want["desired_goal"])
+    d = npy(ring.temporal_sample(starts=starts, flags=np.ones(L, np.uint8), goal_rows=np.full(L, 20), length=L)["task_done"]).reshape(-1)
+    assert d[10] == 1 and d[20] == 1 and d[25] == 1 and d.sum() == 3
+    d = npy(ring.temporal_sample(starts=starts, flags=np.ones(L, np.uint8), goal_rows=np.full(L, 30), length=L)["task_done"]).reshape(-1)
+    assert d.sum() == 0
+
+
 def test_wide_rows_take_the_generic_kernel(R):
     rng = np.random.default_rng(2)
     N = 300
