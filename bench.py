@@ -36,12 +36,16 @@ ROW_BYTES = 4 * (OBS + ACT + 2 * GOAL) + 4 * 5  # 436 B, SURVEY.md section 8(d)
 
 # algorithmic bytes per transition (T=2), SURVEY.md section 8(d) / DESIGN.md:
 #   A gather: read 2 rows + 8 B start, write 2 rows                         = 4*436 + 8       = 1752
-#   B relabel: goal source row 4*G + goal_row(8) + flag(1)                  = 64 + 9          =   73   (x p)
-#   C return under relabel: n tail rows x (achieved_goal 4*G + goal-agnostic reward 4); mean tail of a uniform start in
-#     a 128-row episode = 64.5 rows                                         = 68 * 64.5       = 4386   (x p)
+#   B relabel: goal source row 4*G + its scan record 16 + goal_row(8) + flag(1) = 64 + 25      =   89   (x p)
+#   C return under relabel: n tail rows x one 16-byte scan record (64-bit goal hash, goal-agnostic reward, NaN flag);
+#     mean tail of a uniform start in a 128-row episode = 64.5 rows         = 16 * 64.5       = 1032   (x p)
+#     (SURVEY.md 8(d) counts 72*n B for this term, reading the goal vectors themselves: 4644 B.  The hash-assisted scan
+#      is exact -- hash matches are verified on the full vectors -- and moves 4.5x fewer bytes; the roofline below uses
+#      the bytes THIS algorithm needs, and `survey_bytes_per_transition` reports the SURVEY figure beside it.)
 #   D TQC: next_z + q_pred + grad_q (3 x 4*125) + 4 scalars in + loss out   = 1500 + 20       = 1520
 BYTES_GATHER = 4 * ROW_BYTES + 8
-BYTES_RELABEL = P_RELABEL * ((4 * GOAL + 9) + (4 * GOAL + 4) * (LEP + 1) / 2)
+BYTES_RELABEL = P_RELABEL * ((4 * GOAL + 25) + 16 * (LEP + 1) / 2)
+BYTES_RELABEL_SURVEY = P_RELABEL * ((4 * GOAL + 5) + 72 * (LEP + 1) / 2)
 BYTES_TQC = 3 * 4 * CQ + 20
 BYTES_STREAMS = 32 + 17  # read the start row's record sector, write start/flag/goal
 
@@ -314,6 +318,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["bytes_per_transition"] * M, "launch_ms": kernels[dom]["ms"],
+                "survey_bytes_per_transition": {"sample_gather_kernel": BYTES_GATHER + BYTES_RELABEL_SURVEY, "tqc_loss_kernel": BYTES_TQC},
                 "kernels": kernels,
                 "whole_step": {"bytes_per_transition": total_bytes, "achieved_gbs": total_bytes * M / (ms_step * 1e-3) / 1e9,
                                "frac": total_bytes * M / (ms_step * 1e-3) / 1e9 / peak}}

@@ -55,9 +55,9 @@ __device__ __forceinline__ void bitonic_step(float (&e)[VPL], int lane) {
         if constexpr (K < VPL) asc = (s & K) == 0;
         else if constexpr (K == N) asc = true;
         else asc = (lane & (K / VPL)) == 0;
-        const float lo = fminf(e[s], e[p]), hi = fmaxf(e[s], e[p]);
-        e[s] = asc ? lo : hi;
-        e[p] = asc ? hi : lo;
+        const float x = e[s], y = e[p];
+        e[s] = asc ? fminf(x, y) : fmaxf(x, y);
+        e[p] = asc ? fmaxf(x, y) : fminf(x, y);
       }
     }
   }
@@ -80,31 +80,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // count of sorted[0..N) strictly below x (LE=false) or <= x (LE=true); entries past the kept range hold +inf
+// `base` is the shared-window byte address of sorted[0]; the result is the byte offset 4*count, so that one step is
+// LDS [addr + imm], FSETP, predicated IADD and the prefix-sum tables are indexed by adding the same offset.
+template <int STEP, bool LE>
+__device__ __forceinline__ void search_steps(uint32_t& addr, float x) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(4 * (STEP - 1)));
+  const bool take = LE ? (v <= x) : (v < x);
+  if (take) addr += 4 * STEP;
+  if constexpr (STEP > 1) search_steps<STEP / 2, LE>(addr, x);
+}
 template <int N, bool LE>
-__device__ __forceinline__ int count_below(const float* __restrict__ sorted, float x) {
-  int lo = 0;
-#pragma unroll
-  for (int step = N / 2; step >= 1; step >>= 1) {
-    const float v = sorted[lo + step - 1];
-    const bool take = LE ? (v <= x) : (v < x);
-    lo = take ? lo + step : lo;
-  }
-  return lo;
+__device__ __forceinline__ uint32_t count_below_bytes(uint32_t base, float x) {
+  uint32_t addr = base;
+  search_steps<N / 2, LE>(addr, x);
+  return addr - base;
+}
+__device__ __forceinline__ float lds_at(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
 
 constexpr int kTqcWarps = 8;
 
 template <int VPL>
-__global__ void __launch_bounds__(kTqcWarps * 32) tqc_loss_kernel(const __grid_constant__ TqcArgs a) {
+__global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_kernel(const __grid_constant__ TqcArgs a) {
   constexpr int N = 32 * VPL;
   // per warp: sorted centred targets Y[N], exclusive prefix sums P1[N+1], P2[N+1]  (+pad to dodge bank aliasing)
-  constexpr int kStride = 3 * N + 8;
-  __shared__ float sm[kTqcWarps * kStride];
+  constexpr int kStride = 3 * N + 8;  // Y[N] | P1[N+4] | P2[N+4], each 16 B aligned
+  __shared__ __align__(16) float sm[kTqcWarps * kStride];
   __shared__ double sm_stats[3];
   const int lane = lane_id(), wib = threadIdx.x >> 5;
   float* Y = sm + wib * kStride;
   float* P1 = Y + N;
-  float* P2 = P1 + N + 1;
+  float* P2 = P1 + N + 4;
+  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aP1 = aY + 4 * N, aP2 = aP1 + 4 * (N + 4);
   const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
   const float inv_n = 1.f / (float)n;
   const float inv_nk = 1.f / ((float)n * (float)K);
@@ -171,20 +182,39 @@ __global__ void __launch_bounds__(kTqcWarps * 32) tqc_loss_kernel(const __grid_c
     float p1 = __shfl_up_sync(kFull, x1, 1), p2 = __shfl_up_sync(kFull, x2, 1);  // exclusive
     if (lane == 0) p1 = p2 = 0.f;
     __syncwarp();
+    {
+      float pa[VPL], pb[VPL];
 #pragma unroll
-    for (int s = 0; s < VPL; ++s) {
-      const int i = lane * VPL + s;
-      Y[i] = y[s];
-      P1[i] = p1;
-      P2[i] = p2;
-      if (i < K) {
-        p1 += y[s];
-        p2 = fmaf(y[s], y[s], p2);
+      for (int s = 0; s < VPL; ++s) {
+        const int i = lane * VPL + s;
+        pa[s] = p1;
+        pb[s] = p2;
+        if (i < K) {
+          p1 += y[s];
+          p2 = fmaf(y[s], y[s], p2);
+        }
       }
-    }
-    if (lane == 31) {
-      P1[N] = p1;
-      P2[N] = p2;
+      if constexpr (VPL % 4 == 0) {
+#pragma unroll
+        for (int s = 0; s < VPL; s += 4) {
+          const int i = lane * VPL + s;
+          *reinterpret_cast<float4*>(Y + i) = make_float4(y[s], y[s + 1], y[s + 2], y[s + 3]);
+          *reinterpret_cast<float4*>(P1 + i) = make_float4(pa[s], pa[s + 1], pa[s + 2], pa[s + 3]);
+          *reinterpret_cast<float4*>(P2 + i) = make_float4(pb[s], pb[s + 1], pb[s + 2], pb[s + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+          const int i = lane * VPL + s;
+          Y[i] = y[s];
+          P1[i] = pa[s];
+          P2[i] = pb[s];
+        }
+      }
+      if (lane == 31) {
+        P1[N] = p1;
+        P2[N] = p2;
+      }
     }
     __syncwarp();
     const float T1 = P1[K];
@@ -198,12 +228,13 @@ __global__ void __launch_bounds__(kTqcWarps * 32) tqc_loss_kernel(const __grid_c
     for (int s = 0; s < VPL; ++s) {
       const int j = lane + 32 * s;
       const float qc = q[s] - c0;
-      const int ia = count_below<N, false>(Y, qc - 1.f);
-      const int ib = count_below<N, false>(Y, qc);
-      const int ic = count_below<N, true>(Y, qc + 1.f);
+      const uint32_t oa = count_below_bytes<N, false>(aY, qc - 1.f);
+      const uint32_t ob = count_below_bytes<N, false>(aY, qc);
+      const uint32_t oc = count_below_bytes<N, true>(aY, qc + 1.f);
       const float tau = __fadd_rn(__fdiv_rn((float)j, (float)n), half_over_n);  // :98, tau over the pooled atoms
-      const float P1a = P1[ia], P1b = P1[ib], P1c = P1[ic];
-      const float P2a = P2[ia], P2b = P2[ib], P2c = P2[ic];
+      const float P1a = lds_at(aP1 + oa), P1b = lds_at(aP1 + ob), P1c = lds_at(aP1 + oc);
+      const float P2a = lds_at(aP2 + oa), P2b = lds_at(aP2 + ob), P2c = lds_at(aP2 + oc);
+      const int ia = oa >> 2, ib = ob >> 2, ic = oc >> 2;
       const float na = (float)ia, nab = (float)(ib - ia), nbc = (float)(ic - ib), nc = (float)(K - ic);
       const float d1ab = P1b - P1a, d1bc = P1c - P1b;
       // sum over a<=k<b of (y-q)^2 = dP2 - 2q dP1 + n q^2, same for b<=k<c

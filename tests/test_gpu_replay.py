@@ -374,7 +374,7 @@ def test_hash_scan_verifies_matches_and_nans(R, fdql):
         np.testing.assert_allclose(npy(got["mc_return"]), want["mc_return"], rtol=1e-5, atol=1e-6)
         np.testing.assert_array_equal(npy(got["desired_goal"]), want["desired_goal"])
     d = npy(ring.temporal_sample(starts=starts, flags=np.ones(L, np.uint8), goal_rows=np.full(L, 20), length=L)["task_done"]).reshape(-1)
-    assert d[10] == 1 and d[20] == 1 and d[25] == 1 and d.sum() == 3
+    assert d[0] == 1 and d[10] == 1 and d[20] == 1 and d[25] == 1 and d.sum() == 4  # row 0 is arange(4) = [0,1,2,3] too
     d = npy(ring.temporal_sample(starts=starts, flags=np.ones(L, np.uint8), goal_rows=np.full(L, 30), length=L)["task_done"]).reshape(-1)
     assert d.sum() == 0
 
