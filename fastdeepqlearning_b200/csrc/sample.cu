@@ -300,23 +300,31 @@ __global__ void __launch_bounds__(256) sample_gather_kernel(const __grid_constan
 //           and only hash matches are verified on the full vectors -> exact, at 16 B instead of 4*G+4 B per tail row.
 // The loads of the first two window rows are issued before the relabel scan, so their latency hides behind it.
 // =================================================================================================
-enum { SLOT_NONE = 0, SLOT_WIDE4 = 1, SLOT_WIDEP = 2, SLOT_DG4 = 3, SLOT_DGP = 4, SLOT_REC = 5 };
+enum { SLOT_NONE = 0, SLOT_WIDE4 = 1, SLOT_WIDEP = 2, SLOT_DG4 = 3, SLOT_DGP = 4, SLOT_SCAL = 5 };
 enum { RC_PLAIN = 0, RC_REWARD = 1, RC_TASK_DONE = 2, RC_EP_STEP = 3, RC_MC_RETURN = 4, RC_SKIP = 7 };
 
 struct Slot {
   const float* src;  // slab base + 4*v
-  float* dst;        // output base + 4*v (wide) ; unused for the record
+  float* dst;        // output base + 4*v (wide) or the scalar key's output
   uint32_t sstride;  // floats between rows of the slab
   uint32_t dwidth;   // floats between rows of the output
-  uint32_t meta;     // kind | v << 4 | valid floats << 12 | 4 x 3-bit record role codes << 16
+  uint32_t meta;     // kind | v << 4 | valid floats << 12 | record role code << 16
 };
+
+__device__ __forceinline__ float4 slot_load(const Slot& sl, int64_t row) {
+  const uint32_t kind = sl.meta & 15u;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* p = sl.src + row * (int64_t)sl.sstride;
+  if (kind == SLOT_SCAL) x.x = __ldg(p);
+  else if (kind != SLOT_NONE) x = ldg4(p);
+  return x;
+}
 
 template <int S, int LPR, int MODE>
 __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_kernel(const __grid_constant__ GatherArgs g) {
   constexpr bool RELABEL = MODE != 0;
   constexpr int HEAD = 2;  // window rows whose loads are issued ahead of the scan
   extern __shared__ float smem[];
-  __shared__ float* sm_scal_out[FDQL_MAX_KEYS + 4];
   const ArenaDev& A = g.A;
   const int lane = lane_id();
   const int wib = threadIdx.x >> 5;
@@ -329,10 +337,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   float* sm_c = sm_s + T;
   const int64_t cap = A.capacity;
   const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
-  const int rec_vecs = A.rec_stride >> 2;
-
-  if (threadIdx.x < FDQL_MAX_KEYS + 4)
-    sm_scal_out[threadIdx.x] = threadIdx.x < A.n_scal ? g.out.p[A.scal_key[threadIdx.x]] : nullptr;
 
   // ---- the lane's plan -------------------------------------------------------------------------
   Slot slot[S];
@@ -360,29 +364,20 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
       }
       i -= vecs;
     }
-    if (!found && i >= 0 && i < rec_vecs) {
-      uint32_t codes = 0;
-      bool any = false;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = 4 * i + c;
-        uint32_t code = RC_SKIP;
-        if (col < A.n_scal && g.out.p[A.scal_key[col]] != nullptr) {
-          any = true;
-          code = col == A.col_reward ? RC_REWARD : col == A.col_task_done ? RC_TASK_DONE : col == A.col_ep_step ? RC_EP_STEP
-                 : col == A.col_mc_return ? RC_MC_RETURN : RC_PLAIN;
-        }
-        codes |= code << (3 * c);
-      }
-      if (any) {
-        sl.src = A.rec + 4 * i;
+    if (!found && i >= 0 && i < A.n_scal) {  // one lane per scalar column of the record: 4-byte load, 4-byte store
+      float* o = g.out.p[A.scal_key[i]];
+      if (o != nullptr) {
+        const uint32_t code = i == A.col_reward ? RC_REWARD : i == A.col_task_done ? RC_TASK_DONE : i == A.col_ep_step ? RC_EP_STEP
+                              : i == A.col_mc_return ? RC_MC_RETURN : RC_PLAIN;
+        sl.src = A.rec + i;
+        sl.dst = o;
         sl.sstride = A.rec_stride;
-        sl.meta = SLOT_REC | (i << 4) | (codes << 16);
+        sl.dwidth = 1;
+        sl.meta = SLOT_SCAL | (code << 16);
       }
     }
     slot[k] = sl;
   }
-  __syncthreads();
 
   // gamma^(32-lane): weight of the carried return for this lane's row inside a 32-row pass
   double wcar = 1.0;
@@ -424,7 +419,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         xh[t][k] = zero4;
-        if (t < T && (slot[k].meta & 15u) != SLOT_NONE) xh[t][k] = ldg4(slot[k].src + row * (int64_t)slot[k].sstride);
+        if (t < T) xh[t][k] = slot_load(slot[k], row);
       }
     }
     if (RELABEL) {
@@ -614,22 +609,16 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
         if (RELABEL && in_ep && (kind == SLOT_DG4 || kind == SLOT_DGP)) v4 = xalt[k];
         if (kind == SLOT_WIDE4 || kind == SLOT_DG4) {
           st_stream4(slot[k].dst + orow * slot[k].dwidth, v4);
-        } else if (kind == SLOT_REC) {
-          const int v = (meta >> 4) & 255u;
-          const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t code = (meta >> (16 + 3 * c)) & 7u;
-            if (code == RC_SKIP) continue;
-            float val = xs[c];
-            if (RELABEL && relabel) {
-              if (code == RC_TASK_DONE) val = sm_d[t];
-              else if (code == RC_EP_STEP) val = sm_s[t];
-              else if (in_ep && code == RC_REWARD) val = sm_r[t];
-              else if (in_ep && code == RC_MC_RETURN) val = sm_g[t];
-            }
-            st_stream1(sm_scal_out[4 * v + c] + orow, val);
+        } else if (kind == SLOT_SCAL) {
+          const uint32_t code = meta >> 16;
+          float val = v4.x;
+          if (RELABEL && relabel) {
+            if (code == RC_TASK_DONE) val = sm_d[t];
+            if (code == RC_EP_STEP) val = sm_s[t];
+            if (in_ep && code == RC_REWARD) val = sm_r[t];
+            if (in_ep && code == RC_MC_RETURN) val = sm_g[t];
           }
+          st_stream1(slot[k].dst + orow, val);
         } else if (kind == SLOT_WIDEP || kind == SLOT_DGP) {
           const int m = (meta >> 12) & 15u;
           const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -647,8 +636,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
       float4 x[S];
 #pragma unroll
       for (int k = 0; k < S; ++k) {
-        x[k] = zero4;
-        if ((slot[k].meta & 15u) != SLOT_NONE) x[k] = ldg4(slot[k].src + row * (int64_t)slot[k].sstride);
+        x[k] = slot_load(slot[k], row);
       }
       emit(t, x);
     }
@@ -697,7 +685,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   FDQL_REQUIRE(smem <= 200 * 1024, "temporal_len %d too long for the per-warp window scratch", T);
   const int64_t want_blocks = (b_end - b_begin + warps_per_block - 1) / warps_per_block;
   int64_t blocks = want_blocks;
-  int row_vecs = a->dev.rec_stride / 4;
+  int row_vecs = a->dev.n_scal;  // one lane per float4 of a wide key + one lane per scalar column
   for (int w = 0; w < a->dev.n_wide; ++w) row_vecs += a->dev.wide[w].vecs;
   const int slots = (row_vecs + 31) / 32;
   if (slots <= 4 && !g_force_generic_gather) {

@@ -82,14 +82,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 // count of sorted[0..N) strictly below x (LE=false) or <= x (LE=true); entries past the kept range hold +inf
 // `base` is the shared-window byte address of sorted[0]; the result is the byte offset 4*count, so that one step is
 // LDS [addr + imm], FSETP, predicated IADD and the prefix-sum tables are indexed by adding the same offset.
+// Bank-conflict-free layout: logical index i lives at i + (i >> 5) (rows of 32 with a pitch of 33 floats), so the probes
+// of one search level -- logical indices that differ by multiples of 2*STEP -- fall into distinct banks.
+__host__ __device__ constexpr int skew(int i) { return i + (i >> 5); }
 template <int STEP, bool LE>
 __device__ __forceinline__ void search_steps(uint32_t& addr, float x) {
+  // lo is a multiple of 2*STEP; probe logical lo + STEP - 1, advance by STEP
+  constexpr int kProbe = STEP >= 32 ? 33 * (STEP / 32 - 1) + 31 : STEP - 1;
+  constexpr int kAdvance = STEP >= 32 ? STEP + STEP / 32 : STEP;
   float v;
-  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(4 * (STEP - 1)));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(4 * kProbe));
   const bool take = LE ? (v <= x) : (v < x);
-  if (take) addr += 4 * STEP;
+  if (take) addr += 4 * kAdvance;
   if constexpr (STEP > 1) search_steps<STEP / 2, LE>(addr, x);
 }
+// returns the byte offset of the skewed position of the count
 template <int N, bool LE>
 __device__ __forceinline__ uint32_t count_below_bytes(uint32_t base, float x) {
   uint32_t addr = base;
@@ -108,14 +115,15 @@ template <int VPL>
 __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_kernel(const __grid_constant__ TqcArgs a) {
   constexpr int N = 32 * VPL;
   // per warp: sorted centred targets Y[N], exclusive prefix sums P1[N+1], P2[N+1]  (+pad to dodge bank aliasing)
-  constexpr int kStride = 3 * N + 8;  // Y[N] | P1[N+4] | P2[N+4], each 16 B aligned
-  __shared__ __align__(16) float sm[kTqcWarps * kStride];
+  constexpr int kTab = skew(N) + 1;   // skewed table of N+1 entries
+  constexpr int kStride = 3 * kTab;   // Y | P1 | P2
+  __shared__ float sm[kTqcWarps * kStride];
   __shared__ double sm_stats[3];
   const int lane = lane_id(), wib = threadIdx.x >> 5;
   float* Y = sm + wib * kStride;
-  float* P1 = Y + N;
-  float* P2 = P1 + N + 4;
-  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aP1 = aY + 4 * N, aP2 = aP1 + 4 * (N + 4);
+  float* P1 = Y + kTab;
+  float* P2 = P1 + kTab;
+  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aP1 = aY + 4 * kTab, aP2 = aP1 + 4 * kTab;
   const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
   const float inv_n = 1.f / (float)n;
   const float inv_nk = 1.f / ((float)n * (float)K);
@@ -194,30 +202,20 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
           p2 = fmaf(y[s], y[s], p2);
         }
       }
-      if constexpr (VPL % 4 == 0) {
 #pragma unroll
-        for (int s = 0; s < VPL; s += 4) {
-          const int i = lane * VPL + s;
-          *reinterpret_cast<float4*>(Y + i) = make_float4(y[s], y[s + 1], y[s + 2], y[s + 3]);
-          *reinterpret_cast<float4*>(P1 + i) = make_float4(pa[s], pa[s + 1], pa[s + 2], pa[s + 3]);
-          *reinterpret_cast<float4*>(P2 + i) = make_float4(pb[s], pb[s + 1], pb[s + 2], pb[s + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) {
-          const int i = lane * VPL + s;
-          Y[i] = y[s];
-          P1[i] = pa[s];
-          P2[i] = pb[s];
-        }
+      for (int s = 0; s < VPL; ++s) {
+        const int i = skew(lane * VPL + s);
+        Y[i] = y[s];
+        P1[i] = pa[s];
+        P2[i] = pb[s];
       }
       if (lane == 31) {
-        P1[N] = p1;
-        P2[N] = p2;
+        P1[skew(N)] = p1;
+        P2[skew(N)] = p2;
       }
     }
     __syncwarp();
-    const float T1 = P1[K];
+    const float T1 = P1[skew(K)];
 
     // ---- per predicted atom: loss and gradient from the three split points ----------------------
     float acc = 0.f;  // this lane's share of the per-transition loss
@@ -234,7 +232,9 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       const float tau = __fadd_rn(__fdiv_rn((float)j, (float)n), half_over_n);  // :98, tau over the pooled atoms
       const float P1a = lds_at(aP1 + oa), P1b = lds_at(aP1 + ob), P1c = lds_at(aP1 + oc);
       const float P2a = lds_at(aP2 + oa), P2b = lds_at(aP2 + ob), P2c = lds_at(aP2 + oc);
-      const int ia = oa >> 2, ib = ob >> 2, ic = oc >> 2;
+      // skewed position p = i + i/32  ->  i = p - p/33
+      const int pa_ = oa >> 2, pb_ = ob >> 2, pc_ = oc >> 2;
+      const int ia = pa_ - pa_ / 33, ib = pb_ - pb_ / 33, ic = pc_ - pc_ / 33;
       const float na = (float)ia, nab = (float)(ib - ia), nbc = (float)(ic - ib), nc = (float)(K - ic);
       const float d1ab = P1b - P1a, d1bc = P1c - P1b;
       // sum over a<=k<b of (y-q)^2 = dP2 - 2q dP1 + n q^2, same for b<=k<c
