@@ -393,24 +393,68 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   const WideSlab AG = RELABEL ? A.wide[A.wide_ag] : A.wide[0];
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // ---- software pipeline over this warp's windows ------------------------------------------------------------------
+  // While window i is processed, the stream entries of window i+2 and the episode extents of window i+1 are in flight,
+  // and the rows / goal row / scan records of window i+1 are being pulled into L2 by prefetches, so that the loads of
+  // the next iteration find their lines on chip instead of paying a dependent chain of DRAM round trips.
+  struct Hdr {
+    int32_t s, grow;
+    bool flag;
+  };
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t b = g.b_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; b < g.b_end; b += nwarps) {
-    int64_t s = __ldg(g.starts + b);
-    bool flag = false;
-    int64_t grow = 0;
-    if (RELABEL) {
-      flag = __ldg(g.flags + b) != 0;
-      grow = __ldg(g.goal_rows + b);
+  const int64_t b_first = g.b_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  auto load_hdr = [&](int64_t bi) {
+    Hdr h;
+    h.s = 0; h.grow = 0; h.flag = false;
+    if (bi < g.b_end) {
+      int64_t s64 = __ldg(g.starts + bi);
+      if (s64 >= g.len) s64 %= g.len;
+      h.s = (int32_t)s64;
+      if (RELABEL) {
+        h.flag = __ldg(g.flags + bi) != 0;
+        h.grow = (int32_t)__ldg(g.goal_rows + bi);
+      }
     }
-    if (s >= g.len) s %= g.len;
+    return h;
+  };
+  auto load_ext = [&](const Hdr& h, int& es_, int& ee_) {
+    es_ = -1; ee_ = -1;
+    if (RELABEL && h.flag) {
+      const float* rec = A.rec + (int64_t)h.s * A.rec_stride;
+      es_ = __float_as_int(__ldg(rec + A.col_ep_start));
+      ee_ = __float_as_int(__ldg(rec + A.col_ep_end));
+    }
+  };
+  auto prefetch_rows = [&](const Hdr& h) {
+#pragma unroll
+    for (int t = 0; t < HEAD; ++t) {
+      int64_t row = (int64_t)h.s + t;
+      if (row >= g.len) row -= g.len;
+#pragma unroll
+      for (int k = 0; k < S; ++k)
+        if (t < T && (slot[k].meta & 15u) != SLOT_NONE) prefetch_l2(slot[k].src + row * (int64_t)slot[k].sstride);
+    }
+    if (RELABEL && h.flag) {
+      if (lane < AG.vecs) prefetch_l2(AG.base + (int64_t)h.grow * AG.stride + 4 * lane);
+      if (MODE == 2 && lane == 0) prefetch_l2(A.scan + h.grow);
+    }
+  };
+  auto prefetch_tail = [&](const Hdr& h, int es_, int ee_) {
+    if (MODE == 2 && h.flag && es_ >= 0) {
+      const int tl = (int)((int64_t)ee_ - h.s + (ee_ < h.s ? cap : 0));
+      for (int j = lane; j <= tl && j < 512; j += 32) prefetch_l2(A.scan + ring_row(h.s, j, cap));
+    }
+  };
+  Hdr cur = load_hdr(b_first), nxt = load_hdr(b_first + nwarps);
+  int es, ee, es_n = -1, ee_n = -1;
+  load_ext(cur, es, ee);
+  for (int64_t b = b_first; b < g.b_end; b += nwarps) {
+    const Hdr nn = load_hdr(b + 2 * nwarps);
+    load_ext(nxt, es_n, ee_n);
+    prefetch_rows(nxt);
+    const int64_t s = cur.s, grow = cur.grow;
+    const bool flag = cur.flag;
 
-    // ---- issue the loads that depend on the streams only: episode extents, head rows, goal row ----------------------
-    int es = -1, ee = -1;
-    if (RELABEL && flag) {
-      const float* rec = A.rec + s * (int64_t)A.rec_stride;
-      es = __float_as_int(__ldg(rec + A.col_ep_start));
-      ee = __float_as_int(__ldg(rec + A.col_ep_end));
-    }
     float4 xh[HEAD][S], xalt[S];
 #pragma unroll
     for (int t = 0; t < HEAD; ++t) {
@@ -640,6 +684,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
       }
       emit(t, x);
     }
+    prefetch_tail(nxt, es_n, ee_n);
+    cur = nxt;
+    es = es_n;
+    ee = ee_n;
+    nxt = nn;
     __syncwarp();
   }
 }

@@ -31,45 +31,58 @@ struct TqcArgs {
   double* stats;
 };
 
-// ---- warp-level bitonic sort of 32*VPL values; sorted position of (lane, slot) is lane*VPL + slot -----------
-template <int VPL, int K, int J>
-__device__ __forceinline__ void bitonic_step(float (&e)[VPL], int lane) {
-  constexpr int N = 32 * VPL;
+// ---- warp-level bitonic sort of 32*VPL values; sorted position of (lane, slot) is i = lane*VPL + slot ----------------
+// "Flip" formulation: phase K first compares i with i ^ (K-1), then i with i ^ J for J = K/4 ... 1, and every
+// compare-exchange is ascending (the lower index keeps the minimum).  So an in-lane stage needs no predicate at all and a
+// cross-lane stage needs one (am I the lower lane of the pair).
+template <int VPL, int K>
+__device__ __forceinline__ void bitonic_flip(float (&e)[VPL], int lane) {
+  if constexpr (K <= VPL) {
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      if ((s & (K >> 1)) == 0) {
+        const int p = s ^ (K - 1);
+        const float x = e[s], y = e[p];
+        e[s] = fminf(x, y);
+        e[p] = fmaxf(x, y);
+      }
+    }
+  } else {
+    constexpr int LM = K / VPL - 1;  // partner lane = lane ^ LM, partner slot = VPL-1-s
+    const bool lower = (lane & (K / 2 / VPL)) == 0;
+    float o[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) o[s] = __shfl_xor_sync(kFull, e[VPL - 1 - s], LM);
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) e[s] = lower ? fminf(e[s], o[s]) : fmaxf(e[s], o[s]);
+  }
+}
+template <int VPL, int J>
+__device__ __forceinline__ void bitonic_half(float (&e)[VPL], int lane) {
   if constexpr (J >= VPL) {
-    constexpr int LM = J / VPL;  // partner lane = lane ^ LM
-    // ascending block iff (i & K) == 0; i = lane*VPL + slot and K >= 2J >= 2*VPL, so only the lane decides
-    const bool asc = (K == N) ? true : ((lane & (K / VPL)) == 0);
+    constexpr int LM = J / VPL;
     const bool lower = (lane & LM) == 0;
-    const bool keep_min = (asc == lower);
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
       const float o = __shfl_xor_sync(kFull, e[s], LM);
-      e[s] = keep_min ? fminf(e[s], o) : fmaxf(e[s], o);
+      e[s] = lower ? fminf(e[s], o) : fmaxf(e[s], o);
     }
   } else {
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
       if ((s & J) == 0) {
-        const int p = s | J;
-        bool asc;
-        if constexpr (K < VPL) asc = (s & K) == 0;
-        else if constexpr (K == N) asc = true;
-        else asc = (lane & (K / VPL)) == 0;
-        const float x = e[s], y = e[p];
-        e[s] = asc ? fminf(x, y) : fmaxf(x, y);
-        e[p] = asc ? fmaxf(x, y) : fminf(x, y);
+        const float x = e[s], y = e[s | J];
+        e[s] = fminf(x, y);
+        e[s | J] = fmaxf(x, y);
       }
     }
   }
-}
-template <int VPL, int K, int J>
-__device__ __forceinline__ void bitonic_merge(float (&e)[VPL], int lane) {
-  bitonic_step<VPL, K, J>(e, lane);
-  if constexpr (J > 1) bitonic_merge<VPL, K, J / 2>(e, lane);
+  if constexpr (J > 1) bitonic_half<VPL, J / 2>(e, lane);
 }
 template <int VPL, int K>
 __device__ __forceinline__ void bitonic_sort_from(float (&e)[VPL], int lane) {
-  bitonic_merge<VPL, K, K / 2>(e, lane);
+  bitonic_flip<VPL, K>(e, lane);
+  if constexpr (K >= 4) bitonic_half<VPL, K / 4>(e, lane);
   if constexpr (K < 32 * VPL) bitonic_sort_from<VPL, K * 2>(e, lane);
 }
 
@@ -103,9 +116,9 @@ __device__ __forceinline__ uint32_t count_below_bytes(uint32_t base, float x) {
   search_steps<N / 2, LE>(addr, x);
   return addr - base;
 }
-__device__ __forceinline__ float lds_at(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+__device__ __forceinline__ float4 lds4_at(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 
@@ -115,15 +128,15 @@ template <int VPL>
 __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_kernel(const __grid_constant__ TqcArgs a) {
   constexpr int N = 32 * VPL;
   // per warp: sorted centred targets Y[N], exclusive prefix sums P1[N+1], P2[N+1]  (+pad to dodge bank aliasing)
-  constexpr int kTab = skew(N) + 1;   // skewed table of N+1 entries
-  constexpr int kStride = 3 * kTab;   // Y | P1 | P2
-  __shared__ float sm[kTqcWarps * kStride];
+  constexpr int kTab = skew(N) + 1;      // skewed table of N+1 entries
+  constexpr int kTabY = (kTab + 3) / 4 * 4;
+  constexpr int kStride = kTabY + 4 * kTab;  // Y | Q = float4 {prefix sum of y, prefix sum of y^2, count, -}
+  __shared__ __align__(16) float sm[kTqcWarps * kStride];
   __shared__ double sm_stats[3];
   const int lane = lane_id(), wib = threadIdx.x >> 5;
   float* Y = sm + wib * kStride;
-  float* P1 = Y + kTab;
-  float* P2 = P1 + kTab;
-  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aP1 = aY + 4 * kTab, aP2 = aP1 + 4 * kTab;
+  float4* Qt = reinterpret_cast<float4*>(Y + kTabY);
+  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aQ = aY + 4 * kTabY;
   const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
   const float inv_n = 1.f / (float)n;
   const float inv_nk = 1.f / ((float)n * (float)K);
@@ -131,6 +144,10 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
   if (a.stats && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
   if (a.stats) __syncthreads();
   double st_sum = 0.0, st_var = 0.0, st_viol = 0.0;
+  float taus[VPL];  // :98, tau over the pooled atoms: fl32(fl32(j / n) + fl32(1/2/n)), for this lane's atoms j = lane + 32 s
+#pragma unroll
+  for (int s = 0; s < VPL; ++s) taus[s] = __fadd_rn(__fdiv_rn((float)(lane + 32 * s), (float)n), half_over_n);
+  const float inv_nm1 = n > 1 ? 1.f / (float)(n - 1) : 0.f;
 
   const int64_t nwarps = (int64_t)gridDim.x * kTqcWarps;
   for (int64_t m = (int64_t)blockIdx.x * kTqcWarps + wib; m < a.M; m += nwarps) {
@@ -204,18 +221,14 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       }
 #pragma unroll
       for (int s = 0; s < VPL; ++s) {
-        const int i = skew(lane * VPL + s);
-        Y[i] = y[s];
-        P1[i] = pa[s];
-        P2[i] = pb[s];
+        const int i = lane * VPL + s;
+        Y[skew(i)] = y[s];
+        Qt[skew(i)] = make_float4(pa[s], pb[s], (float)i, 0.f);
       }
-      if (lane == 31) {
-        P1[skew(N)] = p1;
-        P2[skew(N)] = p2;
-      }
+      if (lane == 31) Qt[skew(N)] = make_float4(p1, p2, (float)N, 0.f);
     }
     __syncwarp();
-    const float T1 = P1[skew(K)];
+    const float T1 = Qt[skew(K)].x;
 
     // ---- per predicted atom: loss and gradient from the three split points ----------------------
     float acc = 0.f;  // this lane's share of the per-transition loss
@@ -229,13 +242,10 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       const uint32_t oa = count_below_bytes<N, false>(aY, qc - 1.f);
       const uint32_t ob = count_below_bytes<N, false>(aY, qc);
       const uint32_t oc = count_below_bytes<N, true>(aY, qc + 1.f);
-      const float tau = __fadd_rn(__fdiv_rn((float)j, (float)n), half_over_n);  // :98, tau over the pooled atoms
-      const float P1a = lds_at(aP1 + oa), P1b = lds_at(aP1 + ob), P1c = lds_at(aP1 + oc);
-      const float P2a = lds_at(aP2 + oa), P2b = lds_at(aP2 + ob), P2c = lds_at(aP2 + oc);
-      // skewed position p = i + i/32  ->  i = p - p/33
-      const int pa_ = oa >> 2, pb_ = ob >> 2, pc_ = oc >> 2;
-      const int ia = pa_ - pa_ / 33, ib = pb_ - pb_ / 33, ic = pc_ - pc_ / 33;
-      const float na = (float)ia, nab = (float)(ib - ia), nbc = (float)(ic - ib), nc = (float)(K - ic);
+      const float4 Qa = lds4_at(aQ + 4 * oa), Qb = lds4_at(aQ + 4 * ob), Qc = lds4_at(aQ + 4 * oc);
+      const float P1a = Qa.x, P1b = Qb.x, P1c = Qc.x, P2a = Qa.y, P2b = Qb.y, P2c = Qc.y;
+      const float na = Qa.z, nab = Qb.z - Qa.z, nbc = Qc.z - Qb.z, nc = (float)K - Qc.z;
+      const float tau = taus[s];
       const float d1ab = P1b - P1a, d1bc = P1c - P1b;
       // sum over a<=k<b of (y-q)^2 = dP2 - 2q dP1 + n q^2, same for b<=k<c
       const float sqab = fmaf(qc, fmaf(qc, nab, -2.f * d1ab), P2b - P2a);
@@ -250,15 +260,13 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       float lbj = 0.f;
       if (a.mc_return) {  // :76-79 lower bound relu(mc_return - q)
         lbj = fmaxf(G - q[s], 0.f);
-        if (lbj > 0.f) {
-          gj -= inv_n;
-          if (j < n) ++viol;
-        }
+        const bool on = lbj > 0.f;
+        gj -= on ? inv_n : 0.f;
+        viol += (on && j < n) ? 1 : 0;
       }
-      if (j < n) {
-        acc += fmaf(lj, inv_nk, lbj * inv_n);
-        qsum += q[s];
-      }
+      const float contrib = fmaf(lj, inv_nk, lbj * inv_n);
+      acc += j < n ? contrib : 0.f;
+      qsum += q[s];  // padded slots hold 0
       gout[s] = gj * gs;
     }
     if (a.grad_q) {
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       const int vsum = __reduce_add_sync(kFull, viol);
       if (lane == 0) {
         st_sum += (double)mean * n;
-        st_var += (double)dv / (double)(n - 1);
+        st_var += (double)(dv * inv_nm1);
         st_viol += (double)vsum;
       }
     }
