@@ -95,30 +95,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 // count of sorted[0..N) strictly below x (LE=false) or <= x (LE=true); entries past the kept range hold +inf
 // `base` is the shared-window byte address of sorted[0]; the result is the byte offset 4*count, so that one step is
 // LDS [addr + imm], FSETP, predicated IADD and the prefix-sum tables are indexed by adding the same offset.
-// Bank-conflict-free layout: logical index i lives at i + (i >> 5) (rows of 32 with a pitch of 33 floats), so the probes
-// of one search level -- logical indices that differ by multiples of 2*STEP -- fall into distinct banks.
-__host__ __device__ constexpr int skew(int i) { return i + (i >> 5); }
-template <int STEP, bool LE>
+// Bank-conflict-free layout: sorted index i = lane*VPL + slot lives at phys(i) = slot*33 + lane (VPL rows of 32 columns with
+// a pitch of 33).  Stores of one slot by 32 lanes are consecutive, and the probes of one search level -- logical indices
+// that differ by multiples of 2*STEP -- fall into distinct banks down to the last level.  Index 32*VPL (the "count = all"
+// entry of the prefix tables) lands in the pad column of row 0.
+template <int VPL>
+__host__ __device__ constexpr int phys(int i) { return (i % VPL) * 33 + i / VPL; }
+template <int VPL, int STEP, bool LE>
 __device__ __forceinline__ void search_steps(uint32_t& addr, float x) {
-  // lo is a multiple of 2*STEP; probe logical lo + STEP - 1, advance by STEP
-  constexpr int kProbe = STEP >= 32 ? 33 * (STEP / 32 - 1) + 31 : STEP - 1;
-  constexpr int kAdvance = STEP >= 32 ? STEP + STEP / 32 : STEP;
+  // lo is a multiple of 2*STEP; probe logical lo + STEP - 1, then advance lo by STEP
+  constexpr int kProbe = STEP >= VPL ? (VPL - 1) * 33 + STEP / VPL - 1 : (STEP - 1) * 33;
+  constexpr int kAdvance = STEP >= VPL ? STEP / VPL : STEP * 33;
   float v;
   asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(4 * kProbe));
   const bool take = LE ? (v <= x) : (v < x);
   if (take) addr += 4 * kAdvance;
-  if constexpr (STEP > 1) search_steps<STEP / 2, LE>(addr, x);
+  if constexpr (STEP > 1) search_steps<VPL, STEP / 2, LE>(addr, x);
 }
-// returns the byte offset of the skewed position of the count
-template <int N, bool LE>
+// returns 4 * phys(count)
+template <int VPL, bool LE>
 __device__ __forceinline__ uint32_t count_below_bytes(uint32_t base, float x) {
   uint32_t addr = base;
-  search_steps<N / 2, LE>(addr, x);
+  search_steps<VPL, 16 * VPL, LE>(addr, x);
   return addr - base;
 }
-__device__ __forceinline__ float4 lds4_at(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+__device__ __forceinline__ float2 lds2_at(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
 
@@ -128,15 +131,14 @@ template <int VPL>
 __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_kernel(const __grid_constant__ TqcArgs a) {
   constexpr int N = 32 * VPL;
   // per warp: sorted centred targets Y[N], exclusive prefix sums P1[N+1], P2[N+1]  (+pad to dodge bank aliasing)
-  constexpr int kTab = skew(N) + 1;      // skewed table of N+1 entries
-  constexpr int kTabY = (kTab + 3) / 4 * 4;
-  constexpr int kStride = kTabY + 4 * kTab;  // Y | Q = float4 {prefix sum of y, prefix sum of y^2, count, -}
+  constexpr int kTab = 33 * VPL + (VPL & 1);  // phys() table of N+1 entries, even length
+  constexpr int kStride = 3 * kTab;           // Y | Q = float2 {prefix sum of y, prefix sum of y^2}
   __shared__ __align__(16) float sm[kTqcWarps * kStride];
   __shared__ double sm_stats[3];
   const int lane = lane_id(), wib = threadIdx.x >> 5;
   float* Y = sm + wib * kStride;
-  float4* Qt = reinterpret_cast<float4*>(Y + kTabY);
-  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aQ = aY + 4 * kTabY;
+  float2* Qt = reinterpret_cast<float2*>(Y + kTab);
+  const uint32_t aY = (uint32_t)__cvta_generic_to_shared(Y), aQ = aY + 4 * kTab;
   const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
   const float inv_n = 1.f / (float)n;
   const float inv_nk = 1.f / ((float)n * (float)K);
@@ -221,14 +223,13 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       }
 #pragma unroll
       for (int s = 0; s < VPL; ++s) {
-        const int i = lane * VPL + s;
-        Y[skew(i)] = y[s];
-        Qt[skew(i)] = make_float4(pa[s], pb[s], (float)i, 0.f);
+        Y[s * 33 + lane] = y[s];
+        Qt[s * 33 + lane] = make_float2(pa[s], pb[s]);
       }
-      if (lane == 31) Qt[skew(N)] = make_float4(p1, p2, (float)N, 0.f);
+      if (lane == 31) Qt[phys<VPL>(N)] = make_float2(p1, p2);
     }
     __syncwarp();
-    const float T1 = Qt[skew(K)].x;
+    const float T1 = Qt[phys<VPL>(K)].x;
 
     // ---- per predicted atom: loss and gradient from the three split points ----------------------
     float acc = 0.f;  // this lane's share of the per-transition loss
@@ -239,12 +240,15 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
     for (int s = 0; s < VPL; ++s) {
       const int j = lane + 32 * s;
       const float qc = q[s] - c0;
-      const uint32_t oa = count_below_bytes<N, false>(aY, qc - 1.f);
-      const uint32_t ob = count_below_bytes<N, false>(aY, qc);
-      const uint32_t oc = count_below_bytes<N, true>(aY, qc + 1.f);
-      const float4 Qa = lds4_at(aQ + 4 * oa), Qb = lds4_at(aQ + 4 * ob), Qc = lds4_at(aQ + 4 * oc);
+      const uint32_t oa = count_below_bytes<VPL, false>(aY, qc - 1.f);
+      const uint32_t ob = count_below_bytes<VPL, false>(aY, qc);
+      const uint32_t oc = count_below_bytes<VPL, true>(aY, qc + 1.f);
+      const float2 Qa = lds2_at(aQ + 2 * oa), Qb = lds2_at(aQ + 2 * ob), Qc = lds2_at(aQ + 2 * oc);
       const float P1a = Qa.x, P1b = Qb.x, P1c = Qc.x, P2a = Qa.y, P2b = Qb.y, P2c = Qc.y;
-      const float na = Qa.z, nab = Qb.z - Qa.z, nbc = Qc.z - Qb.z, nc = (float)K - Qc.z;
+      // phys p = slot*33 + lane  ->  count = lane*VPL + slot
+      const int pa_ = oa >> 2, pb_ = ob >> 2, pc_ = oc >> 2;
+      const int ia = (pa_ % 33) * VPL + pa_ / 33, ib = (pb_ % 33) * VPL + pb_ / 33, ic = (pc_ % 33) * VPL + pc_ / 33;
+      const float na = (float)ia, nab = (float)(ib - ia), nbc = (float)(ic - ib), nc = (float)(K - ic);
       const float tau = taus[s];
       const float d1ab = P1b - P1a, d1bc = P1c - P1b;
       // sum over a<=k<b of (y-q)^2 = dP2 - 2q dP1 + n q^2, same for b<=k<c
