@@ -1,0 +1,123 @@
+"""Mirror of franQ/Agent/components/soft_actor_critic.py: SoftActorCritic with the same members (critic, critic_target,
+critic_frozen, actor, actor_target, log_alpha, curr_alpha), `q_loss`, `actor_loss`, `update_target`.
+
+`q_loss(curr_xp, next_xp) -> (q_loss [T-1,B,1], None, summaries)` keeps the reference signature; everything after the
+critics' forward passes (entropy term, min over atoms, TD target, smooth-L1, lower bound, summaries and the gradient
+w.r.t. q_pred) is ONE launch of fdql_sac_min_target_loss instead of a dozen torch ops."""
+import math
+
+import torch
+from torch import nn
+
+from . import models
+from ... import ops
+
+
+def make_actor(conf, input_dim):
+    if getattr(conf, "discrete", False):
+        raise NotImplementedError("discrete (Gumbel-softmax) policies stay franQ's own torch module; plug it in via actor_factory")
+    return models.GaussianPolicy(input_dim, conf.action_space.shape[0], conf.pi_hidden_dims)
+
+
+def make_critic(conf, input_dim):
+    act = conf.action_space.n if getattr(conf, "discrete", False) else conf.action_space.shape[-1]
+    return models.MLPEnsemble(input_dim + act, conf.num_q_predictions, conf.critic_hidden_dims, ensemble_size=conf.num_critics)
+
+
+def _summaries_from_stats(stats, n_atoms, with_violations):
+    """q_pred mean, mean unbiased row variance, constraint violations (soft_actor_critic.py:86-87,95-97) from the
+    kernel's 4 accumulators {sum q, sum row-var, #violations, M}; stays on the device (no sync)."""
+    m = stats[3].clamp(min=1)
+    out = {"q_pred_mu": (stats[0] / (m * n_atoms)).float(), "q_pred_var": (stats[1] / m).float()}
+    if with_violations:
+        out["mc_constraint_violations"] = (stats[2] / (m * n_atoms)).float()
+    return out
+
+
+class _LossWithStats(torch.autograd.Function):
+    """Differentiable wrapper: forward launches the fused kernel once (loss, d loss/d q_pred, stats), backward scales."""
+
+    @staticmethod
+    def forward(ctx, q_pred, fn):
+        r = fn(q_pred)
+        ctx.save_for_backward(r["grad"])
+        ctx.mark_non_differentiable(r["stats"])
+        return r["loss"], r["stats"]
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss, None
+
+
+class SoftActorCritic(nn.Module):
+    def __init__(self, conf, input_dim, actor_factory=make_actor, critic_factory=make_critic):
+        super().__init__()
+        self.conf = conf
+        self.critic = critic_factory(conf, input_dim)
+        self.critic_target = critic_factory(conf, input_dim)
+        self.critic_frozen = critic_factory(conf, input_dim)  # used for updating the actor (soft_actor_critic.py:33)
+        self.critic_target.load_state_dict(self.critic.state_dict())
+        self.actor = actor_factory(conf, input_dim)
+        self.actor_target = actor_factory(conf, input_dim)
+        self.actor_target.load_state_dict(self.actor.state_dict())
+        self.log_alpha = nn.Parameter(torch.tensor(float(conf.init_log_alpha), dtype=torch.float32))
+        self.curr_alpha = math.exp(float(conf.init_log_alpha))
+        self.target_entropy = -float(conf.action_space.n if getattr(conf, "discrete", False)
+                                     else math.prod(conf.action_space.shape))
+        for p in list(self.critic_target.parameters()) + list(self.critic_frozen.parameters()) + list(self.actor_target.parameters()):
+            p.requires_grad_(False)
+        self.param_dict = {"actor": list(self.actor.parameters()), "critic": list(self.critic.parameters()),
+                           "log_alpha": [self.log_alpha]}
+        self._fast_params = sum(self.param_dict.values(), start=[])
+
+    def parameters(self, *args, **kwargs):  # trainable parameters only, like the reference (:50-51)
+        return self._fast_params
+
+    @torch.no_grad()
+    def update_target(self):
+        pairs = [(self.actor_target, self.actor), (self.critic_target, self.critic)]
+        for tgt, src in pairs:
+            t, s = list(tgt.parameters()), list(src.parameters())
+            if getattr(self.conf, "use_hard_updates", False):
+                torch._foreach_copy_(t, s)
+            else:
+                torch._foreach_lerp_(t, s, float(self.conf.tau))  # t*(1-tau) + s*tau (utils/common.py:10-13)
+
+    # ---- shared front half of q_loss: the MLP forward passes (ordinary torch) --------------------------------------
+    def _critic_io(self, curr_xp, next_xp):
+        with torch.no_grad():
+            next_action, next_log_pi, _ = self.actor_target(next_xp["state"])
+            next_z = self.critic_target(torch.cat((next_xp["state"], next_action), dim=-1))
+        action = curr_xp["action_onehot"] if getattr(self.conf, "discrete", False) else curr_xp["action"]
+        q_pred = self.critic(torch.cat((curr_xp["state"], action), dim=-1))
+        return q_pred, next_z, next_log_pi
+
+    def _alpha(self):
+        a = self.curr_alpha
+        return float(a) if not torch.is_tensor(a) else float(a.item()) if a.device.type == "cpu" else a
+
+    def q_loss(self, curr_xp, next_xp):
+        conf = self.conf
+        if getattr(conf, "use_bootstrap_minibatch_nstep", False):
+            raise NotImplementedError("use_bootstrap_minibatch_nstep (soft_actor_critic.py:102-132) is outside the hot path")
+        q_pred, next_z, next_log_pi = self._critic_io(curr_xp, next_xp)
+        lb = next_xp["mc_return"] if conf.use_nStep_lowerbounds else None
+        lp = next_log_pi if conf.use_max_entropy_q else None
+        alpha = float(self.curr_alpha)
+
+        def fused(q):
+            return ops.sac_min_target_loss(q, next_z, lp, next_xp["reward"], next_xp["mask"], lb, alpha, conf.gamma, want_stats=True)
+        loss, stats = _LossWithStats.apply(q_pred, fused)
+        return loss, None, _summaries_from_stats(stats, q_pred.shape[-1], lb is not None)
+
+    def actor_loss(self, xp):
+        """soft_actor_critic.py:136-154 (ordinary torch: it differentiates through the critic MLP)."""
+        pi, log_pi, _ = self.actor(xp["state"])
+        entropy = -log_pi
+        self.critic_frozen.load_state_dict(self.critic.state_dict())
+        qpi = self.critic_frozen(torch.cat((xp["state"].detach(), pi), dim=-1)).mean(-1, keepdim=True)
+        policy_loss = -(self.curr_alpha * entropy) - qpi
+        alpha_loss = -(self.log_alpha * (self.target_entropy - entropy).detach())
+        self.curr_alpha = float(torch.exp(self.log_alpha).detach())
+        return policy_loss.mean(-1, keepdim=True), alpha_loss, {"curr_alpha": self.curr_alpha}

@@ -1,0 +1,118 @@
+"""Learner: mirror of the training half of franQ/Agent/deepQlearning.py (`get_losses` :198-249, `train_step` :105-127,
+`_temporal_difference_shift` :251-258) over the device replay and the fused loss kernels.
+
+One `train_step()` consumes one batch from every local replay shard (the reference's loop over `self.replays`).  Under
+torch.distributed each rank owns its shards and only gradients cross GPUs: one flat bucket, one NCCL all-reduce per
+optimizer step.  The encoder is the reference's default for 1-D observations -- concatenation of
+the obs keys -- so `state` is a view-free torch.cat; MLP encoders stay user torch modules (`encoder=` argument)."""
+import types
+
+import torch
+from torch import nn
+
+from .components.distributional_soft_actor_critic import DistributionalSoftActorCritic
+from .components.soft_actor_critic import SoftActorCritic
+
+
+class LearnerConf(types.SimpleNamespace):
+    """The hot-path knobs of franQ/Agent/conf.py:8-76 with the reference's names and defaults."""
+
+    def __init__(self, **kw):
+        d = dict(batch_size=256, replay_size=int(5e4), temporal_len=50, use_nStep_lowerbounds=True, nStep_return_steps=1000,
+                 gamma=0.99, tau=5e-3, use_hard_updates=False, use_HER=False, her_mode="final", num_critics=5,
+                 num_q_predictions=10, top_quantiles_to_drop=0.2, use_max_entropy_q=True, use_distributional_sac=True,
+                 use_squashed_rewards=False, num_instances=1, training_device="cuda:0", dtype=torch.float32,
+                 init_log_alpha=0.0, learning_rate=3e-4, pi_hidden_dims=(256,), critic_hidden_dims=(256, 256), discrete=False,
+                 obs_keys=("obs_1d", "achieved_goal", "desired_goal"), use_bootstrap_minibatch_nstep=False, clip_grad_norm=None)
+        d.update(kw)
+        super().__init__(**d)
+
+
+class ConcatEncoder(nn.Module):
+    """encoder.py:52-58 for 1-D observation spaces without a joiner: state = cat(obs keys)."""
+
+    def __init__(self, keys):
+        super().__init__()
+        self.keys = tuple(keys)
+
+    def forward_train(self, xp):
+        return torch.cat([xp[k] for k in self.keys if k in xp], dim=-1)
+
+
+class Learner:
+    def __init__(self, conf, replays=None, encoder=None, state_dim=None):
+        self.conf = conf
+        self.device = torch.device(conf.training_device)
+        self.encoder = encoder or ConcatEncoder(conf.obs_keys)
+        if state_dim is None:
+            state_dim = sum(conf.obs_space[k] for k in conf.obs_keys if k in conf.obs_space)
+        ac_cls = DistributionalSoftActorCritic if conf.use_distributional_sac else SoftActorCritic
+        self.actor_critic = ac_cls(conf, state_dim).to(self.device)
+        params = list(self.actor_critic.parameters()) + [p for p in self.encoder.parameters() if p.requires_grad]
+        self.params = params
+        self.optimizer = torch.optim.Adam(params, lr=conf.learning_rate)
+        self.replays = list(replays or [])
+        self.train_steps = 0
+        self._flat = None
+        self.last_summaries = {}
+
+    def enable_training(self, replays):
+        """deepQlearning.py:64-71,96-103: register the read heads (already device loaders)."""
+        self.replays = list(replays)
+
+    @staticmethod
+    def _temporal_difference_shift(xp):
+        curr, nxt = {}, {}
+        for k, v in xp.items():
+            curr[k], nxt[k] = v[:-1], v[1:]
+        return curr, nxt
+
+    def get_losses(self, xp):
+        """deepQlearning.py:198-249.  `xp` is a sampled [T, B, .] dict; it is mutated like in the reference (mask,
+        is_contiguous, state).  When the gather kernel already emitted mask / is_contiguous (aux=True) they are used as is."""
+        conf = self.conf
+        if "mask" not in xp:
+            xp["mask"] = torch.logical_not(xp["task_done"] != 0).to(xp["task_done"].dtype)
+        if "is_contiguous" not in xp:
+            step = xp["episode_step"]
+            xp["is_contiguous"] = ((step[1:] == step[:-1] + 1) & (xp["mask"][:-1] != 0)).to(step.dtype)
+        is_contiguous = xp.pop("is_contiguous")
+        xp.pop("loss_weight", None)
+        xp["state"] = self.encoder.forward_train(xp)
+        curr, nxt = self._temporal_difference_shift(xp)
+        q_loss, _, summ = self.actor_critic.q_loss(curr, nxt)
+        pi_loss, alpha_loss, asumm = self.actor_critic.actor_loss(curr)
+        loss = ((q_loss + pi_loss + alpha_loss) * is_contiguous).sum(0) / (is_contiguous.sum(0) + 1e-4)   # :222-225
+        self.last_summaries = {**summ, **asumm, "Valid_Portion": is_contiguous.mean()}
+        return loss.mean() / conf.temporal_len                                                         # :249
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        grads = [p.grad for p in self.params if p.grad is not None]
+        n = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
+        flat = self._flat
+        torch._foreach_copy_(list(flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+        torch._foreach_copy_([g.reshape(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
+
+    def train_step(self):
+        """deepQlearning.py:105-127: for each local shard: sample -> loss -> backward -> (all-reduce) -> Adam -> targets."""
+        last = None
+        for replay in self.replays:
+            xp = replay.temporal_sample()
+            loss = self.get_losses(xp)
+            self.optimizer.zero_grad(set_to_none=False)
+            loss.backward()
+            self._allreduce_grads()
+            if self.conf.clip_grad_norm:
+                torch.nn.utils.clip_grad_norm_(self.params, self.conf.clip_grad_norm)
+            self.optimizer.step()
+            self.actor_critic.update_target()
+            self.train_steps += 1
+            last = loss.detach()
+        return last

@@ -204,6 +204,18 @@ class ReplayMemory:
                                                 _stream_ptr(self.device)))
         return dst
 
+    def reserve_rows(self, n):
+        """Advance the cursor by n rows whose content a device kernel will produce; returns the first reserved row."""
+        self.flush()
+        first = C.c_int64()
+        check(self._lib.fdql_arena_reserve(self._h, int(n), C.byref(first)))
+        self._advance(int(n))
+        return first.value
+
+    def q3_duplicate(self, src_row, n_step, dst_row, gamma):
+        """quirk Q3: the oldest row of an episode longer than n_step, stored once more with the n-step-truncated return."""
+        check(self._lib.fdql_q3_duplicate(self._h, int(src_row), int(n_step), int(dst_row), float(gamma), _stream_ptr(self.device)))
+
     # ------------------------------------------------------------------ read side (replay_memory.py:48-70)
     def __len__(self):
         return self._curr_len

@@ -47,9 +47,30 @@ class NStepReturn(ReplayMemoryWrapper):
         return self.replay_buffer.add_rows(cols, episode_lengths=lens, with_returns=True, gamma=self.discount)
 
     def _add_rows_q3(self, cols, lens):
-        raise NotImplementedError("episodes longer than nStep_return_steps (quirk Q3 duplicate row) are not supported yet")
+        """Episode by episode: an episode longer than n_step is preceded by the duplicate of its oldest row (the reference
+        emits it while the episode is still running, so it lands in the ring before the episode's own rows)."""
+        n = next(iter(cols.values())).shape[0]
+        cols = dict(cols)
+        if self.return_name not in cols:
+            cols[self.return_name] = np.zeros((n, 1), np.float32)
+        first, off = None, 0
+        for L in lens:
+            sub = {k: v[off:off + L] for k, v in cols.items()}
+            dup = self.replay_buffer.reserve_rows(1) if L > self.n_step else None
+            begin = self.replay_buffer.add_rows(sub, episode_lengths=[L], with_returns=True, gamma=self.discount)
+            if dup is not None:
+                self.replay_buffer.q3_duplicate(begin, self.n_step, dup, self.discount)
+            first = (dup if dup is not None else begin) if first is None else first
+            off += L
+        return first
 
     def add_hindsight_rows(self, src_begins, lens, goal_rows, **kw):
-        if any(int(L) > self.n_step for L in lens):
-            raise NotImplementedError("episodes longer than nStep_return_steps (quirk Q3 duplicate row) are not supported yet")
-        return self.replay_buffer.add_hindsight_rows(src_begins, lens, goal_rows, with_returns=True, gamma=self.discount)
+        out = []
+        for src, L, goal in zip(src_begins, lens, goal_rows):
+            L = int(L)
+            dup = self.replay_buffer.reserve_rows(1) if L > self.n_step else None
+            dst = self.replay_buffer.add_hindsight_rows([src], [L], [goal], with_returns=True, gamma=self.discount)
+            if dup is not None:
+                self.replay_buffer.q3_duplicate(int(dst[0]), self.n_step, dup, self.discount)
+            out.append(int(dst[0]))
+        return out

@@ -226,6 +226,38 @@ her_flush_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ src_begi
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// quirk Q3 (nstep_return.py:33-34,50-57): when the episode buffer reaches n_step rows the reference stores the oldest row
+// once more, with the return truncated after n_step rewards, and never removes it.  One warp: copy row src -> dst, then
+// run the exact recurrence over the rewards of rows src .. src+n_step-1.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) q3_duplicate_kernel(ArenaDev A, int64_t src, int32_t n_step, int64_t dst, double gamma) {
+  const int lane = lane_id();
+  for (int w = 0; w < A.n_wide; ++w) {
+    const WideSlab W = A.wide[w];
+    for (int v = lane; v < W.vecs; v += 32)
+      *reinterpret_cast<float4*>(W.base + dst * (int64_t)W.stride + 4 * v) = ldg4(W.base + src * (int64_t)W.stride + 4 * v);
+  }
+  for (int c = lane; c < A.rec_stride; c += 32) {
+    float v = A.rec[src * (int64_t)A.rec_stride + c];
+    if (c == A.col_ep_start || c == A.col_ep_end) v = __int_as_float(-1);  // a lone row: never relabelled at sample time
+    A.rec[dst * (int64_t)A.rec_stride + c] = v;
+  }
+  if (lane == 0) A.scan[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (A.col_mc_return < 0 || A.col_reward < 0) return;
+  float acc = 0.f, g0 = 0.f;
+  bool first = true;
+  for (int jb = ((n_step - 1) / 32) * 32; jb >= 0; jb -= 32) {
+    const int j = jb + lane;
+    const bool valid = j < n_step;
+    const float r = valid ? A.rec[ring_row(src, valid ? j : 0, A.capacity) * (int64_t)A.rec_stride + A.col_reward] : 0.f;
+    const float g = exact_return_chunk(r, jb, n_step, gamma, acc, first);
+    if (jb == 0) g0 = g;
+  }
+  __syncwarp();
+  if (lane == 0) A.rec[dst * (int64_t)A.rec_stride + A.col_mc_return] = g0;
+}
+
 static void advance_cursor(Arena* a, int64_t n) {
   const int64_t cap = a->dev.capacity, top = a->top;
   int64_t mx;
@@ -431,6 +463,15 @@ int fdql_arena_append_host(fdql_arena* a, int64_t n_rows, const float* const* sr
     off += (b + 255) / 256 * 256;
   }
   return fdql_arena_append(a, n_rows, dev_ptrs, stream);
+}
+
+int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t dst_row, double gamma, void* stream) {
+  FDQL_REQUIRE(a != nullptr, "null arena");
+  FDQL_REQUIRE(src_row >= 0 && src_row < a->dev.capacity && dst_row >= 0 && dst_row < a->dev.capacity, "row out of range");
+  FDQL_REQUIRE(n_step >= 1 && n_step <= a->dev.capacity, "bad n_step");
+  q3_duplicate_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->dev, src_row, n_step, dst_row, gamma);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
 }
 
 int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row) {

@@ -108,6 +108,11 @@ int fdql_her_flush_episodes(fdql_arena* a, int32_t n_eps, const int64_t* src_beg
 /* advance the cursor by n rows without writing them (their content is produced by fdql_her_flush_episodes) */
 int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row);
 
+/* quirk Q3 (nstep_return.py:33-34,50-57): NStepReturn._pop stores the oldest buffered row a second time, with the return
+ * truncated after n_step rewards.  Copies row src_row to dst_row (reserved by the caller) and sets its mc_return to the
+ * recurrence over the rewards of rows src_row .. src_row+n_step-1. */
+int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t dst_row, double gamma, void* stream);
+
 /* np.random.randint(0, len-T, B) (replay_memory.py:59) + HER goal choice (her.py:48-53), drawn on the device with a
  * counter-based generator.  Parity runs inject the streams instead.  flags[b]=1 with probability relabel_prob. */
 int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,

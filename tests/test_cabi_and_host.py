@@ -1,0 +1,118 @@
+"""CPU-only checks (no CUDA calls): the C-ABI library loads and exports every symbol include/fdql.h declares, the ctypes
+table matches the header, the host mirrors refuse to run without CUDA (no silent fallback), and the host-side cursor /
+episode bookkeeping follows the reference arithmetic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fdql.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdql_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()  # nvcc cross-compiles for sm_100a without a GPU
+    import fastdeepqlearning_b200 as pkg
+    return pkg
+
+
+def test_library_exports_every_declared_symbol(built):
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    h = ctypes.CDLL(built.LIB_PATH)
+    for s in syms:
+        assert hasattr(h, s), f"{s} is declared in include/fdql.h but not exported by libfdql.so"
+    assert sorted(built.EXPORTS) == syms, "ctypes signature table and header disagree"
+    assert built.lib().fdql_version() >= 100
+    assert built.lib().fdql_last_error() is not None
+
+
+def test_library_is_sm100a_only(built):
+    out = subprocess.run(["cuobjdump", "-lelf", built.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_validation_needs_no_gpu(built):
+    L = built.lib()
+    # n_drop == 0 is the reference's empty-target quirk (Q8): refused before any launch
+    rc = L.fdql_tqc_loss(4, 125, 0, 1, 1, None, 1, 1, None, None, 1.0, 0.99, None, None, None, None, None)
+    assert rc == -1 and b"n_drop" in L.fdql_last_error()
+    assert L.fdql_tqc_loss(0, 125, 10, None, None, None, None, None, None, None, 1.0, 0.99, None, None, None, None, None) == 0
+    assert L.fdql_sample_gather(None, 1, 2, 10, None, None, None, 0, None, 0, 0.99, 0, 0, None, None, None, None, None) == -1
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    from fastdeepqlearning_b200 import Replay, ops
+    with pytest.raises(built.FdqlError):
+        Replay.ReplayMemory(100, 4, 2, device="cpu")
+    with pytest.raises(built.FdqlError):
+        ops.tqc_loss(torch.zeros(2, 125), torch.zeros(2, 125), None, torch.zeros(2, 1), torch.ones(2, 1), None, 1.0, 0.99, 10)
+    with pytest.raises(TypeError):
+        built.RewardOp.coerce(lambda ag, dg: (0.0, False))  # arbitrary Python reward callables are refused, not run on the host
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "fastdeepqlearning_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "/root/reference" in txt:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_host_cursor_matches_reference_arithmetic():
+    """ReplayMemory._advance (batched) == n single steps of replay_memory.py:45-46, incl. quirk Q1 (len saturates at maxlen-1)."""
+    from fastdeepqlearning_b200.Replay.replay_memory import ReplayMemory
+    rng = np.random.default_rng(0)
+    for cap in (2, 3, 7, 64):
+        m = ReplayMemory.__new__(ReplayMemory)
+        m._maxlen, m._top, m._curr_len = cap, 0, 0
+        top = ln = 0
+        for _ in range(200):
+            n = int(rng.integers(0, 2 * cap))
+            for _ in range(n):
+                top = (top + 1) % cap
+                ln = max(top, ln)
+            m._advance(n)
+            assert (m._top, m._curr_len) == (top, ln), (cap, n)
+        assert ln == cap - 1
+
+
+def test_pohlen_transform_matches_golden():
+    from conftest import load_golden
+    from fastdeepqlearning_b200.Replay.wrappers.squash_rewards import _pohlen_transform
+    g = load_golden("get_losses")
+    got = np.array([_pohlen_transform(x) for x in g["pohlen_in"]])
+    np.testing.assert_allclose(got, g["pohlen_out"], rtol=1e-12, atol=1e-15)
+
+
+def test_hindsight_goal_pick_indexing():
+    """her.py:48-53: 'final' is the newest row; 'random' uses random.choice over the newest-first deque, i.e. chronological
+    index L-1-i; the pick is injectable by seeding Python's `random` like the golden generator does."""
+    import random
+    from fastdeepqlearning_b200.Replay.wrappers.her import HindsightNStepReplay
+    w = HindsightNStepReplay.__new__(HindsightNStepReplay)
+    w._mode = "final"
+    assert w._select_virtual_goal(9) == 8
+    w._mode = "random"
+    random.seed(3)
+    picks = [w._select_virtual_goal(9) for _ in range(50)]
+    random.seed(3)
+    want = [9 - 1 - random.choice(range(9)) for _ in range(50)]
+    assert picks == want and set(picks) <= set(range(9))

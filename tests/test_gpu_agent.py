@@ -1,0 +1,121 @@
+"""GPU parity of the Agent mirror: q_loss of DistributionalSoftActorCritic / SoftActorCritic (fused kernels) vs the
+reference's operator sequence (oracle.tqc_q_loss_torch / sac restatement) on the same MLP outputs, forward and backward,
+and one Learner.train_step end to end."""
+import types
+
+import numpy as np
+import pytest
+
+from oracle import cpu_restatement as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_conf(Agent, **kw):
+    d = dict(training_device="cuda:0", obs_space={"obs_1d": 64, "achieved_goal": 16, "desired_goal": 16},
+             action_space=types.SimpleNamespace(shape=(8,)), num_critics=5, num_q_predictions=25, top_quantiles_to_drop=0.08,
+             batch_size=64, temporal_len=3, pi_hidden_dims=(32,), critic_hidden_dims=(32, 32))
+    d.update(kw)
+    return Agent.LearnerConf(**d)
+
+
+def random_xp(torch, T, B, dev="cuda"):
+    g = torch.Generator(device=dev).manual_seed(0)
+    r = lambda *s: torch.randn(*s, device=dev, generator=g)
+    step = torch.arange(T, device=dev).float().view(T, 1, 1).expand(T, B, 1).clone()
+    step[:, ::7] = 0  # some non-contiguous windows
+    done = (torch.rand(T, B, 1, device=dev, generator=g) < 0.1).float()
+    return {"obs_1d": r(T, B, 64), "achieved_goal": r(T, B, 16), "desired_goal": r(T, B, 16), "action": torch.tanh(r(T, B, 8)),
+            "reward": r(T, B, 1), "task_done": done, "episode_step": step, "mc_return": r(T, B, 1) * 3}
+
+
+@pytest.mark.parametrize("distributional", [True, False])
+def test_q_loss_matches_reference_operator_sequence(fdql, distributional):
+    import torch
+    from fastdeepqlearning_b200 import Agent
+    torch.manual_seed(0)
+    conf = make_conf(Agent, use_distributional_sac=distributional)
+    L = Agent.Learner(conf)
+    ac = L.actor_critic
+    xp = random_xp(torch, 3, 64)
+    xp["mask"] = 1 - xp["task_done"]
+    xp["state"] = L.encoder.forward_train(xp)
+    curr, nxt = L._temporal_difference_shift(xp)
+    captured = {}
+    orig = ac._critic_io
+
+    def spy(c, n):
+        out = orig(c, n)
+        captured["io"] = out
+        return out
+    ac._critic_io = spy
+    q_loss, extra, summ = ac.q_loss(curr, nxt)
+    assert extra is None and tuple(q_loss.shape) == (2, 64, 1)
+    q_pred, next_z, next_log_pi = captured["io"]
+    w = torch.rand_like(q_loss)
+    (gq,) = torch.autograd.grad((q_loss * w).sum(), q_pred)
+    c = lambda t: t.detach().cpu()
+    qp = c(q_pred).clone().requires_grad_(True)
+    if distributional:
+        ref = O.tqc_q_loss_torch(qp, c(next_z), c(next_log_pi), c(nxt["reward"]), c(nxt["mask"]), c(nxt["mc_return"]),
+                                 float(ac.curr_alpha), conf.gamma, int(0.08 * 125))
+    else:
+        lo, gr, _ = O.sac_min_target_loss(c(q_pred).numpy(), c(next_z).numpy(), c(next_log_pi).numpy(), c(nxt["reward"]).numpy(),
+                                          c(nxt["mask"]).numpy(), c(nxt["mc_return"]).numpy(), float(ac.curr_alpha), conf.gamma)
+        np.testing.assert_allclose(c(q_loss).numpy(), lo, rtol=1e-5, atol=1e-6)
+        want = gr * c(w).numpy()
+        np.testing.assert_allclose(c(gq).numpy(), want, rtol=1e-4, atol=1e-5 * np.abs(want).max())
+        return
+    np.testing.assert_allclose(c(q_loss).numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    (gref,) = torch.autograd.grad((ref * c(w)).sum(), qp)
+    np.testing.assert_allclose(c(gq).numpy(), gref.numpy(), rtol=1e-4, atol=1e-5 * float(gref.abs().max()))
+    np.testing.assert_allclose(float(summ["q_pred_mu"]), float(q_pred.mean()), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(float(summ["q_pred_var"]), float(q_pred.var(-1).mean()), rtol=1e-4)
+    lb = (nxt["mc_return"] - q_pred).relu()
+    np.testing.assert_allclose(float(summ["mc_constraint_violations"]), float((lb > 0).float().mean()), rtol=1e-5)
+
+
+def test_get_losses_uses_kernel_aux_and_matches_torch_preprocessing(fdql):
+    """mask / is_contiguous emitted by the gather kernel == the torch formulas of deepQlearning.py:201-203."""
+    import torch
+    from fastdeepqlearning_b200 import Agent
+    torch.manual_seed(1)
+    conf = make_conf(Agent)
+    xp = random_xp(torch, 3, 64)
+    a, b = dict(xp), dict(xp)
+    mask = 1 - xp["task_done"]
+    b["mask"] = mask
+    b["is_contiguous"] = ((xp["episode_step"][1:] == xp["episode_step"][:-1] + 1) & (mask[:-1] != 0)).float()
+    L = Agent.Learner(conf)
+    st = torch.cuda.get_rng_state()
+    la = L.get_losses(a)
+    torch.cuda.set_rng_state(st)
+    lb = L.get_losses(b)
+    assert torch.allclose(la, lb, rtol=1e-6)
+    assert "state" in a and "mask" in a  # the sampled dict is mutated like in the reference
+
+
+def test_train_step_end_to_end(fdql):
+    import torch
+    from fastdeepqlearning_b200 import Agent, Replay
+    torch.manual_seed(0)
+    conf = make_conf(Agent, replay_size=20000, use_HER=True, her_mode="future", num_instances=1, temporal_len=2, batch_size=256)
+    read, write = Replay.make(conf, compute_reward=fdql.RewardOp.bitflip())
+    rng = np.random.default_rng(0)
+    Lep, n_eps = 32, 200
+    N = Lep * n_eps
+    ag = rng.integers(0, 2, (N, 16)).astype(np.float32)
+    dg = np.repeat(rng.integers(0, 2, (n_eps, 16)).astype(np.float32), Lep, 0)
+    hit = (ag == dg).all(-1, keepdims=True).astype(np.float32)
+    step = (np.arange(N) % Lep).astype(np.float32).reshape(-1, 1)
+    write[0].add_rows({"obs_1d": rng.standard_normal((N, 64)).astype(np.float32), "action": rng.uniform(-1, 1, (N, 8)).astype(np.float32),
+                       "achieved_goal": ag, "desired_goal": dg, "reward": hit - 1, "task_done": hit,
+                       "episode_done": (step == Lep - 1).astype(np.float32), "episode_step": step}, episode_lengths=[Lep] * n_eps)
+    learner = Agent.Learner(conf, read)
+    before = [p.detach().clone() for p in learner.params]
+    tgt_before = [p.detach().clone() for p in learner.actor_critic.critic_target.parameters()]
+    losses = [float(learner.train_step()) for _ in range(5)]
+    assert all(np.isfinite(losses))
+    assert any(not torch.equal(a, b) for a, b in zip(before, learner.params))
+    assert any(not torch.equal(a, b) for a, b in zip(tgt_before, learner.actor_critic.critic_target.parameters()))
+    assert learner.train_steps == 5
