@@ -161,9 +161,7 @@ class ReplayMemory:
         are whole episodes laid end to end and are committed (extents, optional returns) in the same call."""
         first = next(iter(cols.values()))
         n = int(first.shape[0])
-        if self._h is None:
-            self._jit_initialize({k: int(np.prod(v.shape[1:])) if len(v.shape) > 1 else 1 for k, v in cols.items()},
-                                 {k: tuple(v.shape[1:]) or (1,) for k, v in cols.items()})
+        self.ensure_schema(cols)
         self.flush()
         dev = []
         for k, w in zip(self._keys, self._widths):
@@ -203,6 +201,12 @@ class ReplayMemory:
                                                 float(self.gamma if gamma is None else gamma), int(bool(with_returns)),
                                                 _stream_ptr(self.device)))
         return dst
+
+    def ensure_schema(self, cols):
+        """Allocate the arena from a column dict if no row has been added yet (replay_memory.py:23-35)."""
+        if self._h is None:
+            self._jit_initialize({k: int(np.prod(v.shape[1:])) if len(v.shape) > 1 else 1 for k, v in cols.items()},
+                                 {k: tuple(v.shape[1:]) or (1,) for k, v in cols.items()})
 
     def reserve_rows(self, n):
         """Advance the cursor by n rows whose content a device kernel will produce; returns the first reserved row."""

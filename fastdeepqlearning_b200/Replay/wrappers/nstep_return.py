@@ -53,6 +53,7 @@ class NStepReturn(ReplayMemoryWrapper):
         cols = dict(cols)
         if self.return_name not in cols:
             cols[self.return_name] = np.zeros((n, 1), np.float32)
+        self.replay_buffer.ensure_schema(cols)
         first, off = None, 0
         for L in lens:
             sub = {k: v[off:off + L] for k, v in cols.items()}
