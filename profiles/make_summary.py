@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Turn an ncu report (--set full) into the tracked summary files:  python profiles/make_summary.py gpurun_out/prof_r1.ncu-rep r1
+writes profiles/<tag>_ncu_summary.md and profiles/traffic.json (dram bytes per launch per kernel, read by bench.py)."""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+rep, tag = sys.argv[1], sys.argv[2]
+HERE = os.path.dirname(os.path.abspath(__file__))
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct"]
+ik = hdr.index("Kernel Name")
+SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0, "second": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}
+out, traffic = [f"# ncu --set full summary ({tag}); source report: {os.path.basename(rep)} (scratch, not tracked)\n"], {}
+for r in data:
+    name = r[ik].split("(")[0].replace("void ", "").strip()
+    out.append(f"\n## {r[ik][:110]}\n\n| metric | value | unit |\n|---|---|---|")
+    vals = {}
+    for m in want:
+        if m in hdr:
+            i = hdr.index(m)
+            out.append(f"| {m} | {r[i]} | {units[i]} |")
+            try:
+                vals[m] = float(r[i].replace(",", "")) * SCALE.get(units[i], 1.0)
+            except ValueError:
+                pass
+    if "dram__bytes_read.sum" in vals:
+        tot = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+        key = "sample_gather_kernel" if "sample_gather" in name else name.split("<")[0]
+        traffic[key] = tot
+        dur = vals.get("gpu__time_duration.sum")
+        out.append(f"| dram bytes read+write per launch | {tot:.4g} | byte |")
+        if dur:
+            out.append(f"| dram GB/s under ncu (cold-cache replay) | {tot / dur / 1e9:.1f} | GB/s |")
+open(os.path.join(HERE, f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
+print("\n".join(out))
