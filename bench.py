@@ -53,8 +53,8 @@ BYTES_STREAMS = 32 + 17  # read the start row's record sector, write start/flag/
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring-rows", type=int, default=10_000_000)
     ap.add_argument("--batches-per-step", type=int, default=64)
@@ -158,6 +158,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the one JSON line: NCCL's version / debug lines go to a file unless the caller chose one
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fdql_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=device)
     lib = pkg.lib()
     D = args.batches_per_step

@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(256) sample_gather_kernel(const __grid_constan
 //           and only hash matches are verified on the full vectors -> exact, at 16 B instead of 4*G+4 B per tail row.
 // The loads of the first two window rows are issued before the relabel scan, so their latency hides behind it.
 // =================================================================================================
-enum { SLOT_NONE = 0, SLOT_WIDE4 = 1, SLOT_WIDEP = 2, SLOT_DG4 = 3, SLOT_DGP = 4, SLOT_SCAL = 5 };
+// slot kind flags: how the lane's row vector is stored, and whether it is the desired_goal (replaced by the hindsight goal)
+enum { SLOT_NONE = 0, SLOT_V4 = 1, SLOT_SCAL = 2, SLOT_PART = 4, SLOT_DG = 8 };
 enum { RC_PLAIN = 0, RC_REWARD = 1, RC_TASK_DONE = 2, RC_EP_STEP = 3, RC_MC_RETURN = 4, RC_SKIP = 7 };
 
 struct Slot {
@@ -308,15 +309,17 @@ struct Slot {
   float* dst;        // output base + 4*v (wide) or the scalar key's output
   uint32_t sstride;  // floats between rows of the slab
   uint32_t dwidth;   // floats between rows of the output
-  uint32_t meta;     // kind | v << 4 | valid floats << 12 | record role code << 16
+  uint32_t meta;     // kind flags | v << 4 | valid floats << 12
+  uint32_t ovr;      // scalar columns with a role: shared-window address of the per-row override array | 1 if always applied
 };
 
-__device__ __forceinline__ float4 slot_load(const Slot& sl, int64_t row) {
-  const uint32_t kind = sl.meta & 15u;
+// `galt` (may be null): the hindsight goal row, read instead of the stored desired_goal by the lanes that own it
+__device__ __forceinline__ float4 slot_load(const Slot& sl, int64_t row, const float* galt) {
   float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* p = sl.src + row * (int64_t)sl.sstride;
-  if (kind == SLOT_SCAL) x.x = __ldg(p);
-  else if (kind != SLOT_NONE) x = ldg4(p);
+  if (galt != nullptr && (sl.meta & SLOT_DG)) p = galt + 4 * ((sl.meta >> 4) & 255u);
+  if (sl.meta & SLOT_SCAL) x.x = __ldg(p);
+  else if (sl.meta & (SLOT_V4 | SLOT_PART)) x = ldg4(p);
   return x;
 }
 
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   for (int k = 0; k < S; ++k) {
     int i = lane + 32 * k;
     Slot sl;
-    sl.src = nullptr; sl.dst = nullptr; sl.sstride = 0; sl.dwidth = 0; sl.meta = SLOT_NONE;
+    sl.src = nullptr; sl.dst = nullptr; sl.sstride = 0; sl.dwidth = 0; sl.meta = SLOT_NONE; sl.ovr = 0;
     bool found = false;
     for (int w = 0; w < A.n_wide; ++w) {
       const int vecs = A.wide[w].vecs;
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
           sl.dst = o + 4 * i;
           sl.sstride = A.wide[w].stride;
           sl.dwidth = width;
-          sl.meta = (dg ? (v4 ? SLOT_DG4 : SLOT_DGP) : (v4 ? SLOT_WIDE4 : SLOT_WIDEP)) | (i << 4) | (min(4, width - 4 * i) << 12);
+          sl.meta = (v4 ? SLOT_V4 : SLOT_PART) | (dg ? SLOT_DG : 0) | (i << 4) | (min(4, width - 4 * i) << 12);
         }
       }
       i -= vecs;
@@ -367,13 +370,17 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
     if (!found && i >= 0 && i < A.n_scal) {  // one lane per scalar column of the record: 4-byte load, 4-byte store
       float* o = g.out.p[A.scal_key[i]];
       if (o != nullptr) {
-        const uint32_t code = i == A.col_reward ? RC_REWARD : i == A.col_task_done ? RC_TASK_DONE : i == A.col_ep_step ? RC_EP_STEP
-                              : i == A.col_mc_return ? RC_MC_RETURN : RC_PLAIN;
         sl.src = A.rec + i;
         sl.dst = o;
         sl.sstride = A.rec_stride;
         sl.dwidth = 1;
-        sl.meta = SLOT_SCAL | (code << 16);
+        sl.meta = SLOT_SCAL;
+        if (RELABEL) {  // task_done / episode_step are final for every row of a relabelled window, reward / return inside the episode
+          if (i == A.col_task_done) sl.ovr = (uint32_t)__cvta_generic_to_shared(sm_d) | 1u;
+          if (i == A.col_ep_step) sl.ovr = (uint32_t)__cvta_generic_to_shared(sm_s) | 1u;
+          if (i == A.col_reward) sl.ovr = (uint32_t)__cvta_generic_to_shared(sm_r);
+          if (i == A.col_mc_return) sl.ovr = (uint32_t)__cvta_generic_to_shared(sm_g);
+        }
       }
     }
     slot[k] = sl;
@@ -455,27 +462,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
     const int64_t s = cur.s, grow = cur.grow;
     const bool flag = cur.flag;
 
-    float4 xh[HEAD][S], xalt[S];
-#pragma unroll
-    for (int t = 0; t < HEAD; ++t) {
-      int64_t row = s + t;
-      if (row >= g.len) row -= g.len;
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        xh[t][k] = zero4;
-        if (t < T) xh[t][k] = slot_load(slot[k], row);
-      }
-    }
-    if (RELABEL) {
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const uint32_t kind = slot[k].meta & 15u;
-        xalt[k] = zero4;
-        if (flag && (kind == SLOT_DG4 || kind == SLOT_DGP))
-          xalt[k] = ldg4(AG.base + grow * (int64_t)AG.stride + 4 * ((slot[k].meta >> 4) & 255u));
-      }
-    }
-
     bool relabel = false;
     int tail_last = -1;
     int64_t ep_first = 0;
@@ -483,6 +469,20 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
       relabel = true;
       ep_first = es;
       tail_last = (int)(ee - s + (ee < s ? cap : 0));
+    }
+    const float* galt = (RELABEL && relabel) ? AG.base + grow * (int64_t)AG.stride : nullptr;
+
+    // ---- issue the loads of the head rows before the scan ------------------------------------------------------------
+    float4 xh[HEAD][S];
+#pragma unroll
+    for (int t = 0; t < HEAD; ++t) {
+      int64_t row = s + t;
+      if (row >= g.len) row -= g.len;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        xh[t][k] = zero4;
+        if (t < T) xh[t][k] = slot_load(slot[k], row, t <= tail_last ? galt : nullptr);
+      }
     }
 
     // ---- hindsight scan over the episode tail (her.py:62-69 + nstep_return.py:69-72, quirk Q5) -----------------------
@@ -579,6 +579,46 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
 
     // ---- lane <-> window row: final task_done / episode_step of every row, learner aux --------------------
     if ((RELABEL && relabel) || want_aux) {
+      if (T <= 32) {  // the whole window fits one pass: no carries between passes, no staging of the contiguity bits
+        const int t = lane;
+        const bool valid = t < T;
+        int64_t row = s + (valid ? t : 0);
+        if (row >= g.len) row -= g.len;
+        const float* rec = A.rec + row * (int64_t)A.rec_stride;
+        float v_step = 0.f, v_done = 0.f;
+        if (A.col_ep_step >= 0) v_step = __ldg(rec + A.col_ep_step);
+        if (A.col_task_done >= 0) v_done = __ldg(rec + A.col_task_done);
+        if (RELABEL && relabel) {
+          const bool in_ep = valid && t <= tail_last;
+          const bool dn = in_ep && sm_d[t] != 0.f;
+          const unsigned bal = __ballot_sync(kFull, dn);
+          if (in_ep) {
+            v_done = dn ? 1.f : 0.f;
+            const unsigned below = bal & ((1u << lane) - 1u);
+            const int f = below ? (j0 + 32 - __clz(below)) : seg_first;
+            if (f >= 0 && A.col_ep_step >= 0)
+              v_step = v_step - __ldg(A.rec + ring_row(ep_first, f, cap) * (int64_t)A.rec_stride + A.col_ep_step);
+          }
+          if (valid) {
+            sm_d[t] = v_done;
+            sm_s[t] = v_step;
+          }
+        }
+        if (want_aux) {
+          const float v_mask = v_done != 0.f ? 0.f : 1.f;
+          if (valid && g.aux_mask) st_stream1(g.aux_mask + (int64_t)t * g.n + b, v_mask);
+          const float nxt = __shfl_down_sync(kFull, v_step, 1);
+          const float c = (t + 1 < T && nxt == v_step + 1.f && v_mask != 0.f) ? 1.f : 0.f;
+          float csum = c;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+          if (t + 1 < T) {
+            if (g.aux_contig) st_stream1(g.aux_contig + (int64_t)t * g.n + b, c);
+            if (g.aux_weight) st_stream1(g.aux_weight + (int64_t)t * g.n + b, (c / (csum + 1e-4f)) * g.inv_bt);
+          }
+        }
+        __syncwarp();
+      } else {
       float contig_sum = 0.f, carry_step = 0.f, carry_mask = 0.f;
       for (int tb = 0; tb < T; tb += 32) {
         const int t = tb + lane;
@@ -639,6 +679,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
         }
       }
       __syncwarp();
+      }
     }
 
     // ---- the rows: one 128-bit load + store per lane and slot -----------------------------------------------
@@ -648,24 +689,16 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         const uint32_t meta = slot[k].meta;
-        const uint32_t kind = meta & 15u;
-        float4 v4 = x[k];
-        if (RELABEL && in_ep && (kind == SLOT_DG4 || kind == SLOT_DGP)) v4 = xalt[k];
-        if (kind == SLOT_WIDE4 || kind == SLOT_DG4) {
-          st_stream4(slot[k].dst + orow * slot[k].dwidth, v4);
-        } else if (kind == SLOT_SCAL) {
-          const uint32_t code = meta >> 16;
-          float val = v4.x;
-          if (RELABEL && relabel) {
-            if (code == RC_TASK_DONE) val = sm_d[t];
-            if (code == RC_EP_STEP) val = sm_s[t];
-            if (in_ep && code == RC_REWARD) val = sm_r[t];
-            if (in_ep && code == RC_MC_RETURN) val = sm_g[t];
-          }
+        if (meta & SLOT_V4) st_stream4(slot[k].dst + orow * slot[k].dwidth, x[k]);
+        if (meta & SLOT_SCAL) {
+          float val = x[k].x;
+          const uint32_t ovr = slot[k].ovr;
+          if (RELABEL && relabel && ovr != 0u && ((ovr & 1u) || in_ep)) val = lds_f32((ovr & ~3u) + 4u * (uint32_t)t);
           st_stream1(slot[k].dst + orow, val);
-        } else if (kind == SLOT_WIDEP || kind == SLOT_DGP) {
+        }
+        if (meta & SLOT_PART) {
           const int m = (meta >> 12) & 15u;
-          const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
+          const float xs[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
           float* dst = slot[k].dst + orow * slot[k].dwidth;
           for (int c = 0; c < m; ++c) st_stream1(dst + c, xs[c]);
         }
@@ -679,9 +712,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
       if (row >= g.len) row -= g.len;
       float4 x[S];
 #pragma unroll
-      for (int k = 0; k < S; ++k) {
-        x[k] = slot_load(slot[k], row);
-      }
+      for (int k = 0; k < S; ++k) x[k] = slot_load(slot[k], row, t <= tail_last ? galt : nullptr);
       emit(t, x);
     }
     prefetch_tail(nxt, es_n, ee_n);
