@@ -774,9 +774,14 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   do {                                                                                                                 \
     auto kern = sample_gather_fast_kernel<SV, LPRV, MODEV>;                                                            \
     if (smem > 40 * 1024) FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    int per_sm = 0;                                                                                                    \
-    FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps_per_block * 32, smem));               \
-    if (per_sm < 1) per_sm = 1;                                                                                        \
+    static int per_sm_cached = 0;                                                                                      \
+    static size_t smem_cached = ~(size_t)0;                                                                            \
+    if (per_sm_cached == 0 || smem_cached != smem) {                                                                   \
+      FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, kern, warps_per_block * 32, smem));      \
+      if (per_sm_cached < 1) per_sm_cached = 1;                                                                        \
+      smem_cached = smem;                                                                                              \
+    }                                                                                                                  \
+    const int per_sm = per_sm_cached;                                                                                  \
     if (blocks > (int64_t)a->num_sms * per_sm) blocks = (int64_t)a->num_sms * per_sm;                                  \
     kern<<<(unsigned)blocks, warps_per_block * 32, smem, st>>>(g);                                                     \
   } while (0)
