@@ -323,9 +323,16 @@ __device__ __forceinline__ float4 slot_load(const Slot& sl, int64_t row, const f
   return x;
 }
 
+__device__ __forceinline__ int ring_row32(int base, int off, int cap) {  // capacity < 2^31 (fdql_arena_create)
+  const unsigned r = (unsigned)base + (unsigned)off;
+  return (int)(r >= (unsigned)cap ? r - (unsigned)cap : r);
+}
+
 template <int S, int LPR, int MODE>
 __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_kernel(const __grid_constant__ GatherArgs g) {
   constexpr bool RELABEL = MODE != 0;
+  constexpr bool HASH = MODE >= 2;     // equality reward: 16-byte scan records + verified hash matches
+  constexpr bool HORNER = MODE == 3;   // ... with the scan-free return recompute (host picks it when T <= 32 and gamma^-(T-1) is harmless)
   constexpr int HEAD = 2;  // window rows whose loads are issued ahead of the scan
   extern __shared__ float smem[];
   const ArenaDev& A = g.A;
@@ -397,8 +404,23 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
       e >>= 1;
     }
   }
+  // MODE 2 return recompute without a scan per pass: every lane folds its rows j = lane, lane+32, ... with Horner in
+  // gamma^32, one weighted warp reduction gives G_0, and G_j = gamma^-j (G_0 - sum_{i<j} gamma^i r'_i) for the window rows.
+  // Used when the window fits one pass and gamma^-(T-1) is harmless in fp64; otherwise the per-pass suffix scan runs.
+  double w_lane = 1.0, gamma32 = 1.0;
+  if (HORNER) {
+    double p = g.gamma;
+    for (int e = lane; e; e >>= 1) {
+      if (e & 1) w_lane *= p;
+      p *= p;
+    }
+    double q = g.gamma;
+    for (int e = 0; e < 5; ++e) q *= q;
+    gamma32 = q;
+  }
   const WideSlab AG = RELABEL ? A.wide[A.wide_ag] : A.wide[0];
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cap32 = (int)A.capacity, len32 = (int)g.len;
 
   // ---- software pipeline over this warp's windows ------------------------------------------------------------------
   // While window i is processed, the stream entries of window i+2 and the episode extents of window i+1 are in flight,
@@ -435,21 +457,20 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   auto prefetch_rows = [&](const Hdr& h) {
 #pragma unroll
     for (int t = 0; t < HEAD; ++t) {
-      int64_t row = (int64_t)h.s + t;
-      if (row >= g.len) row -= g.len;
+      const int row = ring_row32(h.s, t, len32);
 #pragma unroll
       for (int k = 0; k < S; ++k)
-        if (t < T && (slot[k].meta & 15u) != SLOT_NONE) prefetch_l2(slot[k].src + row * (int64_t)slot[k].sstride);
+        if (t < T && (slot[k].meta & 15u) != SLOT_NONE) prefetch_l2(slot[k].src + (int64_t)row * slot[k].sstride);
     }
     if (RELABEL && h.flag) {
       if (lane < AG.vecs) prefetch_l2(AG.base + (int64_t)h.grow * AG.stride + 4 * lane);
-      if (MODE == 2 && lane == 0) prefetch_l2(A.scan + h.grow);
+      if (HASH && lane == 0) prefetch_l2(A.scan + h.grow);
     }
   };
   auto prefetch_tail = [&](const Hdr& h, int es_, int ee_) {
-    if (MODE == 2 && h.flag && es_ >= 0) {
-      const int tl = (int)((int64_t)ee_ - h.s + (ee_ < h.s ? cap : 0));
-      for (int j = lane; j <= tl && j < 512; j += 32) prefetch_l2(A.scan + ring_row(h.s, j, cap));
+    if (HASH && h.flag && es_ >= 0) {
+      const int tl = ee_ - h.s + (ee_ < h.s ? cap32 : 0);
+      for (int j = lane; j <= tl && j < 512; j += 32) prefetch_l2(A.scan + ring_row32(h.s, j, cap32));
     }
   };
   Hdr cur = load_hdr(b_first), nxt = load_hdr(b_first + nwarps);
@@ -459,25 +480,24 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
     const Hdr nn = load_hdr(b + 2 * nwarps);
     load_ext(nxt, es_n, ee_n);
     prefetch_rows(nxt);
-    const int64_t s = cur.s, grow = cur.grow;
+    const int s = cur.s, grow = cur.grow;
     const bool flag = cur.flag;
 
     bool relabel = false;
     int tail_last = -1;
-    int64_t ep_first = 0;
+    int ep_first = 0;
     if (RELABEL && flag && es >= 0) {
       relabel = true;
       ep_first = es;
-      tail_last = (int)(ee - s + (ee < s ? cap : 0));
+      tail_last = ee - s + (ee < s ? cap32 : 0);
     }
-    const float* galt = (RELABEL && relabel) ? AG.base + grow * (int64_t)AG.stride : nullptr;
+    const float* galt = (RELABEL && relabel) ? AG.base + (int64_t)grow * AG.stride : nullptr;
 
     // ---- issue the loads of the head rows before the scan ------------------------------------------------------------
     float4 xh[HEAD][S];
 #pragma unroll
     for (int t = 0; t < HEAD; ++t) {
-      int64_t row = s + t;
-      if (row >= g.len) row -= g.len;
+      const int row = ring_row32(s, t, len32);
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         xh[t][k] = zero4;
@@ -488,17 +508,18 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
     // ---- hindsight scan over the episode tail (her.py:62-69 + nstep_return.py:69-72, quirk Q5) -----------------------
     int seg_first = -1, j0 = 0;
     if (RELABEL && relabel) {
-      j0 = (int)(s - ep_first + (s < ep_first ? cap : 0));
+      j0 = s - ep_first + (s < ep_first ? cap32 : 0);
       double carry = 0.0;
-      if (MODE == 2) {
+      if (HASH) {
         const float4 gsc = __ldg(A.scan + grow);
-        const int64_t gd = grow - s + (grow < s ? cap : 0);  // window-relative index of the goal row (may lie outside the tail)
+        const int gd = grow - s + (grow < s ? cap32 : 0);  // window-relative index of the goal row (may lie outside the tail)
+        double acc = 0.0;  // Horner accumulator of this lane's rows
         for (int jb = (tail_last >> 7) << 7; jb >= 0; jb -= 128) {
           float4 r4[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int j = jb + 32 * u + lane;
-            r4[u] = j <= tail_last ? __ldg(A.scan + ring_row(s, j, cap)) : zero4;
+            r4[u] = j <= tail_last ? __ldg(A.scan + ring_row32(s, j, cap32)) : zero4;
           }
 #pragma unroll
           for (int u = 3; u >= 0; --u) {
@@ -508,26 +529,55 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
             const bool valid = j <= tail_last;
             bool m = valid && __float_as_uint(r4[u].x) == __float_as_uint(gsc.x) && __float_as_uint(r4[u].y) == __float_as_uint(gsc.y);
             if (m) {  // hash match: the goal row itself is equal unless it holds a NaN; any other row is verified
-              if ((int64_t)j == gd) m = (__float_as_uint(r4[u].w) & 1u) == 0u;
-              else m = rows_equal(A, ring_row(s, j, cap), grow);
+              if (j == gd) m = (__float_as_uint(r4[u].w) & 1u) == 0u;
+              else m = rows_equal(A, ring_row32(s, j, cap32), grow);
             }
             const float rnew = valid ? (float)((double)r4[u].z + (m ? 0.0 : -1.0)) : 0.f;
-            double G = warp_suffix_scan((double)rnew, g.gamma, lane);
-            G = fma(wcar, carry, G);
-            carry = shfl_idx_f64(G, 0);
-            if (valid && j < T) {
-              sm_r[j] = rnew;
-              sm_g[j] = (float)G;
-              sm_d[j] = m ? 1.f : 0.f;
+            if (HORNER) {
+              acc = fma(acc, gamma32, (double)rnew);
+              if (valid && j < T) {
+                sm_r[j] = rnew;
+                sm_d[j] = m ? 1.f : 0.f;
+              }
+            } else {
+              double G = warp_suffix_scan((double)rnew, g.gamma, lane);
+              G = fma(wcar, carry, G);
+              carry = shfl_idx_f64(G, 0);
+              if (valid && j < T) {
+                sm_r[j] = rnew;
+                sm_g[j] = (float)G;
+                sm_d[j] = m ? 1.f : 0.f;
+              }
             }
           }
+        }
+        if (HORNER) {
+          // G_0 = sum_l gamma^l acc_l ; window row j: G_j = (G_0 - sum_{i<j} gamma^i r'_i) / gamma^j
+          double tot = acc * w_lane;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) tot += shfl_xor_f64(tot, d);
+          __syncwarp();
+          double pre = 0.0;  // exclusive prefix of gamma^i r'_i over the window rows
+          if (T == 2) {
+            pre = lane == 1 ? (double)sm_r[0] : 0.0;
+          } else if (T > 2) {
+            double v = (lane < T && lane <= tail_last) ? w_lane * (double)sm_r[lane] : 0.0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const double o = shfl_up_f64(v, d);
+              if (lane >= d) v += o;
+            }
+            pre = shfl_up_f64(v, 1);
+            if (lane == 0) pre = 0.0;
+          }
+          if (lane < T && lane <= tail_last) sm_g[lane] = (float)((tot - pre) / w_lane);
         }
         if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
           seg_first = 0;
           for (int jb = ((j0 - 1) >> 5) << 5; jb >= 0 && j0 > 0; jb -= 32) {
             const int j = jb + lane;
             const bool valid = j < j0;
-            const int64_t row = ring_row(ep_first, valid ? j : 0, cap);
+            const int row = ring_row32(ep_first, valid ? j : 0, cap32);
             const float4 r = valid ? __ldg(A.scan + row) : zero4;
             bool m = valid && __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
             if (m) {
@@ -768,7 +818,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   int row_vecs = a->dev.n_scal;  // one lane per float4 of a wide key + one lane per scalar column
   for (int w = 0; w < a->dev.n_wide; ++w) row_vecs += a->dev.wide[w].vecs;
   const int slots = (row_vecs + 31) / 32;
-  if (slots <= 4 && !g_force_generic_gather) {
+  if (slots <= 4 && !(g_force_generic_gather & 1)) {
     // persistent-style grid: as many blocks as stay resident, each warp strides over the windows
 #define FDQL_LAUNCH_FAST(SV, LPRV, MODEV)                                                                              \
   do {                                                                                                                 \
@@ -794,7 +844,9 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     if (!relabel) {
       FDQL_FAST_S(1, 0);
     } else if (reward_op == FDQL_REWARD_BITFLIP && !g_force_full_vector_relabel) {
-      FDQL_FAST_S(1, 2);
+      // scan-free return recompute when the window fits one pass and gamma^-(T-1) stays harmless in fp64
+      if (T <= 32 && gamma > 0.0 && pow(gamma, (double)(T - 1)) > 1e-9 && !(g_force_generic_gather & 4)) FDQL_FAST_S(1, 3);
+      else FDQL_FAST_S(1, 2);
     } else {
       switch (lpr) {
         case 1: FDQL_FAST_S(1, 1); break;
@@ -844,7 +896,7 @@ extern "C" {
 
 int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
-  g_force_generic_gather = on & 1;
+  g_force_generic_gather = on & 5;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner
   g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }

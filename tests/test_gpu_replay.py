@@ -347,6 +347,18 @@ def test_full_vector_relabel_scan_with_bitflip(R, fdql, T, G, max_len):
         lib.fdql_debug_force_generic_gather(old)
 
 
+@pytest.mark.parametrize("T,G,max_len", [(2, 16, 130), (5, 3, 70), (33, 8, 90)])
+def test_hash_scan_with_per_pass_suffix_scan(R, fdql, T, G, max_len):
+    """The hash-assisted scan has two return recomputes (scan-free Horner form for T <= 32, per-pass suffix scan otherwise);
+    force the second on small windows too."""
+    lib = fdql.lib()
+    old = lib.fdql_debug_force_generic_gather(4)
+    try:
+        test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len)
+    finally:
+        lib.fdql_debug_force_generic_gather(old)
+
+
 def test_hash_scan_verifies_matches_and_nans(R, fdql):
     """Exactness of the hash-assisted scan does not rest on the hash: -0.0 == +0.0 must match, NaN never matches (not even the
     goal row itself), and equal rows elsewhere in the tail are found."""
