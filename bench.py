@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--no-updates", action="store_true")
     ap.add_argument("--exact-episode-step", action="store_true")
     return ap.parse_args()
 
@@ -194,7 +195,7 @@ def run_ours(args):
     def step(ev=None):
         if ev:
             ev[0].record(stream)
-        L.check(lib.fdql_sample_streams(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], p(starts), p(flags), p(goals), sp))
+        L.check(lib.fdql_sample_streams(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], None, p(starts), p(flags), p(goals), sp))
         counter[0] += 1
         if ev:
             ev[1].record(stream)
@@ -242,7 +243,7 @@ def run_ours(args):
     # ---- single-batch launches (B=4096 windows per launch): latency-bound figure, reported beside the headline ----
     def small_step(i):
         o = (i % D) * B
-        L.check(lib.fdql_sample_streams(h, B, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, 10_000 + i, p(starts[o:]), p(flags[o:]),
+        L.check(lib.fdql_sample_streams(h, B, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, 10_000 + i, None, p(starts[o:]), p(flags[o:]),
                                         p(goals[o:]), sp))
         outs = L.ptr_array([out[k].data_ptr() for k in keys])
         # outputs of a B-window launch are laid out [T, B, w] inside the first T*B rows of the big buffers
@@ -305,6 +306,39 @@ def run_ours(args):
                "ms_per_step": ms_e2e, "api": "fdql_hotpath_step_host (pinned host streams + critic outputs in, loss + dloss/dq out)",
                "loss_mean": float(hloss.mean())}
 
+    # ---- second metric of BASELINE.json: TQC updates/s = full learner steps (sample+relabel on this ring, PyTorch MLP
+    #      forward/backward for 5x25 critics + actor, fused TQC loss, Adam, soft target update; gradient all-reduce if N>1)
+    updates = None
+    if not args.no_updates:
+        import types
+        from fastdeepqlearning_b200 import Agent
+        from fastdeepqlearning_b200.Replay.wrappers import SampleTimeHindsight
+        torch.manual_seed(0)
+        lconf = Agent.LearnerConf(training_device=str(device), obs_space={"obs_1d": OBS, "achieved_goal": GOAL, "desired_goal": GOAL},
+                                  action_space=types.SimpleNamespace(shape=(ACT,)), num_critics=C_CRIT, num_q_predictions=Q_ATOMS,
+                                  top_quantiles_to_drop=N_DROP / CQ + 1e-9, batch_size=B, temporal_len=T, gamma=GAMMA)
+        learner = Agent.Learner(lconf, [SampleTimeHindsight(ring, relabel_prob=P_RELABEL)])
+        for _ in range(5):
+            learner.train_step()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        n_upd = 30
+        e0.record(stream)
+        for _ in range(n_upd):
+            last = learner.train_step()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        ms_upd = e0.elapsed_time(e1) / n_upd
+        if dist:
+            tm = torch.tensor([ms_upd], device=device)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms_upd = float(tm.item())
+        updates = {"value": 1e3 / ms_upd, "unit": "updates/s (each rank steps on its own 4096-window batch, gradients averaged)",
+                   "ms_per_update": ms_upd, "transitions_per_s": world * B * (T - 1) * 1e3 / ms_upd,
+                   "params": int(sum(p.numel() for p in learner.params)), "loss": float(last),
+                   "note": "policy/critic MLPs are ordinary PyTorch modules (eager); only sample/relabel/target/loss are CUDA kernels of this repo"}
+
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()
     kernels = {
@@ -349,6 +383,8 @@ def run_ours(args):
                        "violations": float(stats[2] / max(float(stats[3]), 1) / CQ)}}
     if e2e:
         line["e2e"] = e2e
+    if updates:
+        line["tqc_updates"] = updates
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(args, steps=3, warmup=1, quiet=True)["cpu_baseline"]
     if rank == 0:

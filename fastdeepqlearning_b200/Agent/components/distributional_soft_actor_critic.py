@@ -25,7 +25,7 @@ class DistributionalSoftActorCritic(SoftActorCritic):
         q_pred, next_z, next_log_pi = self._critic_io(curr_xp, next_xp)
         lb = next_xp["mc_return"] if conf.use_nStep_lowerbounds else None
         lp = next_log_pi if conf.use_max_entropy_q else None
-        alpha, n_drop = float(self.curr_alpha), self.n_drop(q_pred.shape[-1])
+        alpha, n_drop = self.curr_alpha, self.n_drop(q_pred.shape[-1])  # alpha stays on the device
 
         def fused(q):
             return ops.tqc_loss(q, next_z, lp, next_xp["reward"], next_xp["mask"], lb, alpha, conf.gamma, n_drop,

@@ -62,7 +62,9 @@ class SoftActorCritic(nn.Module):
         self.actor_target = actor_factory(conf, input_dim)
         self.actor_target.load_state_dict(self.actor.state_dict())
         self.log_alpha = nn.Parameter(torch.tensor(float(conf.init_log_alpha), dtype=torch.float32))
-        self.curr_alpha = math.exp(float(conf.init_log_alpha))
+        # curr_alpha = exp(log_alpha) (soft_actor_critic.py:40,151), kept as a 1-element device tensor: the loss kernel reads it
+        # from device memory, so no step of the learner needs a host sync (and the step can be captured in a CUDA graph)
+        self.register_buffer("curr_alpha", torch.tensor([math.exp(float(conf.init_log_alpha))], dtype=torch.float32))
         self.target_entropy = -float(conf.action_space.n if getattr(conf, "discrete", False)
                                      else math.prod(conf.action_space.shape))
         for p in list(self.critic_target.parameters()) + list(self.critic_frozen.parameters()) + list(self.actor_target.parameters()):
@@ -93,10 +95,6 @@ class SoftActorCritic(nn.Module):
         q_pred = self.critic(torch.cat((curr_xp["state"], action), dim=-1))
         return q_pred, next_z, next_log_pi
 
-    def _alpha(self):
-        a = self.curr_alpha
-        return float(a) if not torch.is_tensor(a) else float(a.item()) if a.device.type == "cpu" else a
-
     def q_loss(self, curr_xp, next_xp):
         conf = self.conf
         if getattr(conf, "use_bootstrap_minibatch_nstep", False):
@@ -104,7 +102,7 @@ class SoftActorCritic(nn.Module):
         q_pred, next_z, next_log_pi = self._critic_io(curr_xp, next_xp)
         lb = next_xp["mc_return"] if conf.use_nStep_lowerbounds else None
         lp = next_log_pi if conf.use_max_entropy_q else None
-        alpha = float(self.curr_alpha)
+        alpha = float(self.curr_alpha)  # (host read: the non-distributional kernel takes alpha by value)
 
         def fused(q):
             return ops.sac_min_target_loss(q, next_z, lp, next_xp["reward"], next_xp["mask"], lb, alpha, conf.gamma, want_stats=True)
@@ -115,9 +113,11 @@ class SoftActorCritic(nn.Module):
         """soft_actor_critic.py:136-154 (ordinary torch: it differentiates through the critic MLP)."""
         pi, log_pi, _ = self.actor(xp["state"])
         entropy = -log_pi
-        self.critic_frozen.load_state_dict(self.critic.state_dict())
+        with torch.no_grad():  # hard_update(critic_frozen, critic) (soft_actor_critic.py:142) as one multi-tensor copy
+            torch._foreach_copy_(list(self.critic_frozen.parameters()), list(self.critic.parameters()))
         qpi = self.critic_frozen(torch.cat((xp["state"].detach(), pi), dim=-1)).mean(-1, keepdim=True)
         policy_loss = -(self.curr_alpha * entropy) - qpi
         alpha_loss = -(self.log_alpha * (self.target_entropy - entropy).detach())
-        self.curr_alpha = float(torch.exp(self.log_alpha).detach())
+        with torch.no_grad():
+            self.curr_alpha.copy_(torch.exp(self.log_alpha).reshape(1))
         return policy_loss.mean(-1, keepdim=True), alpha_loss, {"curr_alpha": self.curr_alpha}

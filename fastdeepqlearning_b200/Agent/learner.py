@@ -50,7 +50,9 @@ class Learner:
         self.actor_critic = ac_cls(conf, state_dim).to(self.device)
         params = list(self.actor_critic.parameters()) + [p for p in self.encoder.parameters() if p.requires_grad]
         self.params = params
-        self.optimizer = torch.optim.Adam(params, lr=conf.learning_rate)
+        on_gpu = self.device.type == "cuda"
+        self.optimizer = torch.optim.Adam(params, lr=conf.learning_rate, fused=on_gpu, capturable=on_gpu)
+        self._graphs = {}  # replay index -> (CUDAGraph, static loss, ring length at capture)
         self.replays = list(replays or [])
         self.train_steps = 0
         self._flat = None
@@ -100,19 +102,62 @@ class Learner:
         flat.div_(dist.get_world_size())
         torch._foreach_copy_([g.reshape(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
 
+    def _one_update(self, replay, **sample_kw):
+        xp = replay.temporal_sample(**sample_kw)
+        loss = self.get_losses(xp)
+        loss.backward()
+        self._allreduce_grads()
+        if self.conf.clip_grad_norm:
+            torch.nn.utils.clip_grad_norm_(self.params, self.conf.clip_grad_norm)
+        self.optimizer.step()
+        self.actor_critic.update_target()
+        return loss.detach()
+
     def train_step(self):
         """deepQlearning.py:105-127: for each local shard: sample -> loss -> backward -> (all-reduce) -> Adam -> targets."""
         last = None
-        for replay in self.replays:
-            xp = replay.temporal_sample()
-            loss = self.get_losses(xp)
-            self.optimizer.zero_grad(set_to_none=False)
-            loss.backward()
-            self._allreduce_grads()
-            if self.conf.clip_grad_norm:
-                torch.nn.utils.clip_grad_norm_(self.params, self.conf.clip_grad_norm)
-            self.optimizer.step()
-            self.actor_critic.update_target()
+        for i, replay in enumerate(self.replays):
+            if getattr(self.conf, "use_cuda_graph", False):
+                last = self._graphed_update(i, replay)
+            else:
+                self.optimizer.zero_grad(set_to_none=False)
+                last = self._one_update(replay)
             self.train_steps += 1
-            last = loss.detach()
         return last
+
+    # ---- whole-step CUDA graph (SURVEY.md section 8f rank 2): sample/relabel kernel, MLP forward/backward, fused loss, Adam and
+    #      the target update are captured once and replayed; the draw counter and the temperature live in device memory.
+    def _graphed_update(self, i, replay):
+        ring = replay
+        while hasattr(ring, "replay_buffer") or (hasattr(ring, "replay") and not hasattr(ring, "flush")):
+            ring = getattr(ring, "replay_buffer", None) or ring.replay
+        ring = getattr(ring, "replay", ring)
+        ring.flush()
+        n_now = len(ring)
+        entry = self._graphs.get(i)
+        if entry is not None and abs(n_now - entry[2]) > 0.05 * entry[2]:
+            entry = None  # the sampling range is baked into the captured launch: refresh it when the ring has grown
+        if entry is None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not getattr(self.conf, "graph_allreduce", False):
+                raise RuntimeError("use_cuda_graph with world_size > 1 needs conf.graph_allreduce=True (NCCL capture)")
+            if self.conf.clip_grad_norm:
+                raise RuntimeError("clip_grad_norm is not capturable")
+            ring.device_counter = True
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm-up on a side stream (allocator, autograd buffers, Adam state)
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._one_update(replay, reuse_outputs=True)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_loss = self._one_update(replay, reuse_outputs=True)
+            entry = (graph, static_loss, n_now)
+            self._graphs[i] = entry
+        entry[0].replay()
+        return entry[1]

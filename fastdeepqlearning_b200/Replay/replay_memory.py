@@ -58,6 +58,8 @@ class ReplayMemory:
         self.gamma = 0.99
         self._rng_seed = int(kwargs.get("seed", 0x5EED))
         self._rng_counter = 0
+        self._rng_counter_dev = None
+        self.device_counter = False  # True: the draw counter lives in device memory (CUDA-graph capture of the learner step)
         self._out_cache: T.Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ allocation (replay_memory.py:23-35)
@@ -288,13 +290,17 @@ class ReplayMemory:
             flags = torch.empty(n, dtype=torch.uint8, device=self.device)
             goals = torch.empty(n, dtype=torch.int64, device=self.device)
         self._sync_cursor()
+        if self._rng_counter_dev is None:  # {draw counter, block ticket}: lets a captured graph draw fresh streams per replay
+            self._rng_counter_dev = torch.zeros(2, dtype=torch.int64, device=self.device)
         check(self._lib.fdql_sample_streams(self._h, n, Tn, L.GOAL_FUTURE if goal_mode is None else int(goal_mode),
                                             float(relabel_prob), self._rng_seed, self._rng_counter,
+                                            C.c_void_p(self._rng_counter_dev.data_ptr()) if self.device_counter else None,
                                             C.c_void_p(starts.data_ptr()),
                                             C.c_void_p(flags.data_ptr()) if flags is not None else None,
                                             C.c_void_p(goals.data_ptr()) if goals is not None else None,
                                             _stream_ptr(self.device)))
-        self._rng_counter += 1
+        if not self.device_counter:
+            self._rng_counter += 1
         return starts, flags, goals
 
     def _sync_cursor(self):

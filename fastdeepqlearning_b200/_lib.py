@@ -54,12 +54,13 @@ _SIGNATURES = {
     "fdql_her_flush_episodes": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _i32, _p]),
     "fdql_q3_duplicate": (C.c_int, [_p, _i64, _i32, _i64, _f64, _p]),
     "fdql_arena_reserve": (C.c_int, [_p, _i64, C.POINTER(_i64)]),
-    "fdql_sample_streams": (C.c_int, [_p, _i64, _i32, _i32, _f32, _u64, _u64, _p, _p, _p, _p]),
+    "fdql_sample_streams": (C.c_int, [_p, _i64, _i32, _i32, _f32, _u64, _u64, _p, _p, _p, _p, _p]),
     "fdql_gather_rows": (C.c_int, [_p, _i64, _p, _pp, _p]),
     "fdql_sample_gather": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _u32, _i32, _pp,
                                      _p, _p, _p, _p]),
     "fdql_debug_force_generic_gather": (C.c_int, [C.c_int]),
     "fdql_tqc_loss": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p]),
+    "fdql_tqc_loss_dev_alpha": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "fdql_quantile_huber": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "fdql_sac_min_target_loss": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p]),
     "fdql_hotpath_step_host": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _u32, _pp,

@@ -37,7 +37,26 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr_lo, uint64_t ctr_hi, ui
 // over the committed extents of the start row's episode (her.py:48-53).  Uncommitted rows are never relabelled.
 __global__ void __launch_bounds__(256)
 sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int goal_mode, float relabel_prob, uint64_t seed, uint64_t counter,
-                      int64_t* __restrict__ starts, uint8_t* __restrict__ flags, int64_t* __restrict__ goal_rows) {
+                      unsigned long long* counter_dev, int64_t* __restrict__ starts, uint8_t* __restrict__ flags,
+                      int64_t* __restrict__ goal_rows) {
+  // counter_dev (optional): {draw counter, block ticket} in device memory, so that a captured CUDA graph draws fresh streams at
+  // every replay.  Every block reads the counter before it takes its ticket; the last block to finish advances it.
+  __shared__ unsigned long long sh_ctr;
+  if (counter_dev != nullptr) {
+    if (threadIdx.x == 0) sh_ctr = *reinterpret_cast<volatile unsigned long long*>(counter_dev);
+    __syncthreads();
+    counter += sh_ctr;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long ticket = atomicAdd(counter_dev + 1, 1ull);
+      if (ticket == (unsigned long long)gridDim.x - 1) {
+        counter_dev[1] = 0ull;
+        counter_dev[0] = sh_ctr + 1ull;
+        __threadfence();
+      }
+    }
+  }
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   const uint4 x = philox4x32((uint64_t)b, counter, seed);
@@ -902,7 +921,8 @@ int fdql_debug_force_generic_gather(int on) {
 }
 
 int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
-                        uint64_t counter, int64_t* starts, uint8_t* flags, int64_t* goal_rows, void* stream) {
+                        uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows,
+                        void* stream) {
   FDQL_REQUIRE(a != nullptr && starts != nullptr, "null argument");
   FDQL_REQUIRE(n >= 0 && T >= 0, "bad sizes");
   FDQL_REQUIRE(goal_mode >= FDQL_GOAL_FINAL && goal_mode <= FDQL_GOAL_FUTURE, "bad goal mode");
@@ -916,7 +936,9 @@ int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_
   const int64_t range = a->len - T;  // T==0: flat sample() over [0, len)
   FDQL_REQUIRE(range > 0, "empty start range");
   sample_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->dev, n, range, goal_mode, relabel_prob,
-                                                                                       seed, counter, starts, flags, goal_rows);
+                                                                                       seed, counter,
+                                                                                       reinterpret_cast<unsigned long long*>(counter_dev),
+                                                                                       starts, flags, goal_rows);
   FDQL_CUDA(cudaGetLastError());
   return FDQL_OK;
 }

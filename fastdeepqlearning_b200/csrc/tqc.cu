@@ -29,6 +29,7 @@ struct TqcArgs {
   float* grad_q;
   float* td_target;
   double* stats;
+  const float* alpha_dev;  // when set, overrides alpha
 };
 
 // ---- warp-level bitonic sort of 32*VPL values; sorted position of (lane, slot) is i = lane*VPL + slot ----------------
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       q[s] = j < n ? ld_stream1(qrow + j) : 0.f;
     }
     const float rew = a.reward ? __ldg(a.reward + m) : 0.f, msk = a.mask ? __ldg(a.mask + m) : 1.f;
-    const float ent = a.next_log_pi ? __fmul_rn(a.alpha, -__ldg(a.next_log_pi + m)) : 0.f;
+    const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
+    const float ent = a.next_log_pi ? __fmul_rn(alpha, -__ldg(a.next_log_pi + m)) : 0.f;
     const float G = a.mc_return ? __ldg(a.mc_return + m) : 0.f;
     const float gs = a.grad_scale ? __ldg(a.grad_scale + m) : 1.f;
     const float mg = __fmul_rn(msk, a.gamma);
@@ -449,7 +451,22 @@ int fdql_tqc_loss(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_
   if (M == 0) return FDQL_OK;
   FDQL_REQUIRE(next_z && q_pred && reward && mask, "null input");
   TqcArgs a{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q,
-            td_target, stats};
+            td_target, stats, nullptr};
+  return launch_tqc(a, (cudaStream_t)stream);
+}
+
+int fdql_tqc_loss_dev_alpha(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_z, const float* q_pred,
+                            const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,
+                            const float* grad_scale, const float* alpha_dev, float gamma, float* loss, float* grad_q,
+                            float* td_target, double* stats, void* stream) {
+  FDQL_REQUIRE(M >= 0, "negative M");
+  FDQL_REQUIRE(n_atoms >= 2 && n_atoms <= 256, "n_atoms must be in [2, 256], got %d", n_atoms);
+  FDQL_REQUIRE(n_drop >= 1 && n_drop < n_atoms, "n_drop must be in [1, n_atoms) (reference: int(top_quantiles_to_drop*CQ)); got %d",
+               n_drop);
+  if (M == 0) return FDQL_OK;
+  FDQL_REQUIRE(next_z && q_pred && reward && mask && alpha_dev, "null input");
+  TqcArgs a{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, 0.f, gamma, loss, grad_q,
+            td_target, stats, alpha_dev};
   return launch_tqc(a, (cudaStream_t)stream);
 }
 
@@ -461,7 +478,7 @@ int fdql_quantile_huber(int64_t M, int32_t n_quantiles, int32_t n_samples, const
   if (M == 0) return FDQL_OK;
   FDQL_REQUIRE(quantiles && samples, "null input");
   TqcArgs a{M, n_quantiles, n_samples, 0, samples, quantiles, nullptr, nullptr, nullptr, nullptr, grad_scale, 1.f, 1.f,
-            loss, grad_q, nullptr, nullptr};
+            loss, grad_q, nullptr, nullptr, nullptr};
   return launch_tqc(a, (cudaStream_t)stream);
 }
 

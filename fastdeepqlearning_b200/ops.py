@@ -50,9 +50,15 @@ def tqc_loss(q_pred, next_z, next_log_pi, reward, mask, mc_return, alpha, gamma,
         K = n - int(n_drop)
         td = torch.empty((M, max(K, 0)), dtype=torch.float32, device=q.device) if want_target else None
         stats = torch.zeros(4, dtype=torch.float64, device=q.device) if want_stats else None
-        L.check(L.lib().fdql_tqc_loss(M, n, int(n_drop), _p(z), _p(q), _p(_flat(next_log_pi)), _p(_flat(reward)),
-                                      _p(_flat(mask)), _p(_flat(mc_return)), _p(_flat(grad_scale)), float(alpha), float(gamma),
-                                      _p(loss), _p(grad), _p(td), _p(stats), _stream(q)))
+        if torch.is_tensor(alpha):  # temperature kept on the device (no host sync; CUDA-graph safe)
+            a_dev = alpha.detach().to(device=q.device, dtype=torch.float32).reshape(-1)
+            L.check(L.lib().fdql_tqc_loss_dev_alpha(M, n, int(n_drop), _p(z), _p(q), _p(_flat(next_log_pi)), _p(_flat(reward)),
+                                                    _p(_flat(mask)), _p(_flat(mc_return)), _p(_flat(grad_scale)), _p(a_dev),
+                                                    float(gamma), _p(loss), _p(grad), _p(td), _p(stats), _stream(q)))
+        else:
+            L.check(L.lib().fdql_tqc_loss(M, n, int(n_drop), _p(z), _p(q), _p(_flat(next_log_pi)), _p(_flat(reward)),
+                                          _p(_flat(mask)), _p(_flat(mc_return)), _p(_flat(grad_scale)), float(alpha), float(gamma),
+                                          _p(loss), _p(grad), _p(td), _p(stats), _stream(q)))
     out = {"loss": loss.reshape(lead + (1,))}
     if want_grad:
         out["grad"] = grad.reshape(lead + (n,))

@@ -114,9 +114,12 @@ int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row);
 int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t dst_row, double gamma, void* stream);
 
 /* np.random.randint(0, len-T, B) (replay_memory.py:59) + HER goal choice (her.py:48-53), drawn on the device with a
- * counter-based generator.  Parity runs inject the streams instead.  flags[b]=1 with probability relabel_prob. */
+ * counter-based generator.  Parity runs inject the streams instead.  flags[b]=1 with probability relabel_prob.
+ * counter_dev (may be NULL): two uint64 in device memory {draw counter, 0}; when given, the draw uses counter + *counter_dev and
+ * the kernel advances it, so a captured CUDA graph draws fresh streams at every replay. */
 int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
-                        uint64_t counter, int64_t* starts, uint8_t* flags, int64_t* goal_rows, void* stream);
+                        uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows,
+                        void* stream);
 
 /* ReplayMemory.__getitem__ / sample (replay_memory.py:48-52,68-70): out[k] is [n, width_k]. */
 int fdql_gather_rows(const fdql_arena* a, int64_t n, const int64_t* idx, float* const* out, void* stream);
@@ -150,6 +153,12 @@ int fdql_tqc_loss(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_
                   const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,
                   const float* grad_scale, float alpha, float gamma, float* loss, float* grad_q, float* td_target,
                   double* stats, void* stream);
+/* same, with the entropy temperature read from device memory (alpha_dev[0]) at kernel time: for callers that keep
+ * curr_alpha = exp(log_alpha) on the device (soft_actor_critic.py:151) and for CUDA-graph capture of the learner step */
+int fdql_tqc_loss_dev_alpha(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_z, const float* q_pred,
+                            const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,
+                            const float* grad_scale, const float* alpha_dev, float gamma, float* loss, float* grad_q,
+                            float* td_target, double* stats, void* stream);
 
 /* quantile_huber_loss_f(quantiles [M, n_quantiles], samples [M, n_samples]) -> loss [M] and d loss / d quantiles
  * (distributional_soft_actor_critic.py:90-103) for callers that built the target themselves. */

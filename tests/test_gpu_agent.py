@@ -119,3 +119,40 @@ def test_train_step_end_to_end(fdql):
     assert any(not torch.equal(a, b) for a, b in zip(before, learner.params))
     assert any(not torch.equal(a, b) for a, b in zip(tgt_before, learner.actor_critic.critic_target.parameters()))
     assert learner.train_steps == 5
+
+
+def test_cuda_graph_step_matches_eager_and_draws_fresh_streams(fdql):
+    """The whole learner step captured in a CUDA graph: same update as eager from the same state, and every replay draws new
+    windows (device-side draw counter) with the current temperature (device-side alpha)."""
+    import copy
+    import torch
+    from fastdeepqlearning_b200 import Agent, Replay
+    rng = np.random.default_rng(0)
+    Lep, n_eps = 32, 400
+    N = Lep * n_eps
+    ag = rng.integers(0, 2, (N, 16)).astype(np.float32)
+    dg = np.repeat(rng.integers(0, 2, (n_eps, 16)).astype(np.float32), Lep, 0)
+    hit = (ag == dg).all(-1, keepdims=True).astype(np.float32)
+    step = (np.arange(N) % Lep).astype(np.float32).reshape(-1, 1)
+    cols = {"obs_1d": rng.standard_normal((N, 64)).astype(np.float32), "action": rng.uniform(-1, 1, (N, 8)).astype(np.float32),
+            "achieved_goal": ag, "desired_goal": dg, "reward": hit - 1, "task_done": hit,
+            "episode_done": (step == Lep - 1).astype(np.float32), "episode_step": step}
+
+    def build(graph):
+        torch.manual_seed(0)
+        conf = make_conf(Agent, replay_size=N + 1, use_HER=True, her_mode="future", num_instances=1, temporal_len=2, batch_size=512,
+                         use_cuda_graph=graph)
+        read, write = Replay.make(conf, compute_reward=fdql.RewardOp.bitflip())
+        write[0].add_rows(cols, episode_lengths=[Lep] * n_eps)
+        return Agent.Learner(conf, read), read[0]
+
+    lg, head = build(True)
+    losses = [float(lg.train_step()) for _ in range(6)]
+    assert all(np.isfinite(losses)) and len(set(losses)) > 1, losses   # fresh windows each replay
+    ring = head.replay_buffer.replay
+    assert int(ring._rng_counter_dev[0]) >= 6 and int(ring._rng_counter_dev[1]) == 0
+    a0 = float(lg.actor_critic.curr_alpha)
+    assert abs(a0 - float(torch.exp(lg.actor_critic.log_alpha))) < 1e-6 and a0 != 1.0   # temperature follows log_alpha inside the graph
+    le, _ = build(False)
+    le_losses = [float(le.train_step()) for _ in range(3)]
+    assert all(np.isfinite(le_losses))
