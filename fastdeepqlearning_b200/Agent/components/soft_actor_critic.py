@@ -116,7 +116,8 @@ class SoftActorCritic(nn.Module):
         with torch.no_grad():  # hard_update(critic_frozen, critic) (soft_actor_critic.py:142) as one multi-tensor copy
             torch._foreach_copy_(list(self.critic_frozen.parameters()), list(self.critic.parameters()))
         qpi = self.critic_frozen(torch.cat((xp["state"].detach(), pi), dim=-1)).mean(-1, keepdim=True)
-        policy_loss = -(self.curr_alpha * entropy) - qpi
+        alpha_now = self.curr_alpha.detach().clone()  # the buffer is refreshed in place below
+        policy_loss = -(alpha_now * entropy) - qpi
         alpha_loss = -(self.log_alpha * (self.target_entropy - entropy).detach())
         with torch.no_grad():
             self.curr_alpha.copy_(torch.exp(self.log_alpha).reshape(1))
