@@ -45,8 +45,11 @@ class GaussianPolicy(SkipHeadMLP):
     def forward(self, state):
         mean, log_std = torch.chunk(super().forward(state), 2, dim=-1)
         log_std = log_std.clamp(self.log_sig_min, self.log_sig_max)
-        normal = torch.distributions.Normal(mean, log_std.exp())
-        x = normal.rsample()
+        # reparameterised sample and its log-density written out (torch.distributions validates its arguments with a
+        # host-side .all(), which would put a sync in every step and cannot be captured in a CUDA graph)
+        eps = torch.randn_like(mean)
+        x = mean + log_std.exp() * eps
         action = torch.tanh(x)
-        log_prob = (normal.log_prob(x) - torch.log((1 - action.pow(2)) + self.epsilon)).sum(-1, keepdim=True)
+        normal_log_prob = -0.5 * eps.pow(2) - log_std - 0.9189385332046727  # log(sqrt(2*pi))
+        log_prob = (normal_log_prob - torch.log((1 - action.pow(2)) + self.epsilon)).sum(-1, keepdim=True)
         return action, log_prob, torch.tanh(mean)
