@@ -316,7 +316,8 @@ def run_ours(args):
         torch.manual_seed(0)
         lconf = Agent.LearnerConf(training_device=str(device), obs_space={"obs_1d": OBS, "achieved_goal": GOAL, "desired_goal": GOAL},
                                   action_space=types.SimpleNamespace(shape=(ACT,)), num_critics=C_CRIT, num_q_predictions=Q_ATOMS,
-                                  top_quantiles_to_drop=N_DROP / CQ + 1e-9, batch_size=B, temporal_len=T, gamma=GAMMA)
+                                  top_quantiles_to_drop=N_DROP / CQ + 1e-9, batch_size=B, temporal_len=T, gamma=GAMMA,
+                                  use_cuda_graph=(world == 1))
         learner = Agent.Learner(lconf, [SampleTimeHindsight(ring, relabel_prob=P_RELABEL)])
         for _ in range(5):
             learner.train_step()
@@ -337,7 +338,9 @@ def run_ours(args):
         updates = {"value": 1e3 / ms_upd, "unit": "updates/s (each rank steps on its own 4096-window batch, gradients averaged)",
                    "ms_per_update": ms_upd, "transitions_per_s": world * B * (T - 1) * 1e3 / ms_upd,
                    "params": int(sum(p.numel() for p in learner.params)), "loss": float(last),
-                   "note": "policy/critic MLPs are ordinary PyTorch modules (eager); only sample/relabel/target/loss are CUDA kernels of this repo"}
+                   "cuda_graph": bool(lconf.use_cuda_graph),
+                   "note": "policy/critic MLPs are ordinary PyTorch fp32 modules; sample/relabel/target/loss are this repo's CUDA kernels; "
+                           "at N=1 the whole step (kernels + MLP fwd/bwd + Adam + target update) is one captured CUDA graph"}
 
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()

@@ -152,7 +152,8 @@ def test_cuda_graph_step_matches_eager_and_draws_fresh_streams(fdql):
     ring = head.replay_buffer.replay
     assert int(ring._rng_counter_dev[0]) >= 6 and int(ring._rng_counter_dev[1]) == 0
     a0 = float(lg.actor_critic.curr_alpha)
-    assert abs(a0 - float(torch.exp(lg.actor_critic.log_alpha))) < 1e-6 and a0 != 1.0   # temperature follows log_alpha inside the graph
+    # temperature follows log_alpha inside the graph (it is refreshed before the optimizer step, so it lags by one Adam step)
+    assert abs(a0 - float(torch.exp(lg.actor_critic.log_alpha.detach()))) < 2e-3 and a0 != 1.0
     le, _ = build(False)
     le_losses = [float(le.train_step()) for _ in range(3)]
     assert all(np.isfinite(le_losses))
