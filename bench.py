@@ -265,6 +265,54 @@ def run_ours(args):
         torch.cuda.synchronize(device)
         small_ms = e0.elapsed_time(e1) / n_small
 
+    # ---- the same per-batch launches as a CUDA graph of G batches round-robin over four streams (the learner's prefetch
+    #      pattern: later batches are sampled/relabelled while earlier ones are targeted).  Draw counters live in device memory.
+    graph_ms = float("nan")
+    if not args.no_small:
+        G = 16
+        slots = []
+        for i in range(G):
+            so = {k: torch.empty((T, B, w), device=device) for k, w in zip(keys, ring._widths)}
+            slots.append({"out": so, "outp": L.ptr_array([so[k].data_ptr() for k in keys]), "mask": torch.empty(T, B, device=device),
+                          "contig": torch.empty(T - 1, B, device=device), "weight": torch.empty(T - 1, B, device=device),
+                          "ctr": torch.zeros(2, dtype=torch.int64, device=device)})
+
+        def graph_batch(i, st):
+            sl, o, spx = slots[i], i * B, C.c_void_p(st.cuda_stream)
+            L.check(lib.fdql_sample_streams(h, B, T, L.GOAL_FUTURE, P_RELABEL, 1000 + 97 * rank + i, 0, p(sl["ctr"]), p(starts[o:]),
+                                            p(flags[o:]), p(goals[o:]), spx))
+            L.check(lib.fdql_sample_gather(h, B, T, rlen, p(starts[o:]), p(flags[o:]), p(goals[o:]), ring.reward_op.op, params,
+                                           n_params, GAMMA, opts, B, sl["outp"], p(sl["mask"]), p(sl["contig"]), p(sl["weight"]), spx))
+            L.check(lib.fdql_tqc_loss(B, CQ, N_DROP, p(z[o:]), p(q[o:]), p(lp[o:]), p(sl["out"]["reward"][1:]), p(sl["mask"][1:]),
+                                      p(sl["out"]["mc_return"][1:]), p(sl["weight"]), ALPHA, GAMMA, p(loss[o:]), p(grad[o:]), None,
+                                      None, spx))
+        NS = 4
+        side = [torch.cuda.Stream(device) for _ in range(NS)]
+        for i in range(G):  # warm-up outside capture
+            graph_batch(i, stream)
+        torch.cuda.synchronize(device)
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            cs = torch.cuda.current_stream(device)
+            for st_ in side:
+                st_.wait_stream(cs)
+            for i in range(G):
+                graph_batch(i, side[i % NS])
+            for st_ in side:
+                cs.wait_stream(st_)
+        for _ in range(3):
+            cg.replay()
+        torch.cuda.synchronize(device)
+        reps = 20
+        first = starts[:B].clone()
+        e0.record(stream)
+        for _ in range(reps):
+            cg.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        assert not torch.equal(first, starts[:B]), "graph replays must draw fresh windows"
+        graph_ms = e0.elapsed_time(e1) / (reps * G)
+
     # ---- e2e: the host-buffer C-ABI call, pinned host inputs, host outputs ---------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -381,7 +429,9 @@ def run_ours(args):
                        "exact_episode_step": bool(args.exact_episode_step), "parallelism": f"replay shards x{world}, no data-path collective"},
             "roofline": roofline, "gpu_launches": 3 * K, "clocks": clk,
             "single_batch_launches": {"windows_per_launch": B, "ms_per_batch": small_ms, "transitions_per_s": world * B / (small_ms * 1e-3),
-                                      "note": "3 launches per 4096-window batch, launch-latency bound"},
+                                      "note": "3 launches per 4096-window batch from Python, launch-latency bound",
+                                      "cuda_graph_4_streams": {"ms_per_batch": graph_ms, "transitions_per_s": world * B / (graph_ms * 1e-3),
+                                                               "note": "16 batches x 3 launches captured once, round-robin over four streams"}},
             "checks": {"loss_mean": float(loss.mean()), "relabel_frac": float(flags.float().mean()),
                        "violations": float(stats[2] / max(float(stats[3]), 1) / CQ)}}
     if e2e:

@@ -120,6 +120,11 @@ __device__ __forceinline__ uint32_t count_below_bytes(uint32_t base, float x) {
   search_steps<VPL, 16 * VPL, LE>(addr, x);
   return addr - base;
 }
+template <int VPL>
+__device__ __forceinline__ float count_from_offset(uint32_t o) {
+  const uint32_t slot = (o * 993u) >> 17;
+  return (float)(int)((VPL * o >> 2) - (33u * VPL - 1u) * slot);
+}
 __device__ __forceinline__ float2 lds2_at(uint32_t addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -247,10 +252,10 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
       const uint32_t oc = count_below_bytes<VPL, true>(aY, qc + 1.f);
       const float2 Qa = lds2_at(aQ + 2 * oa), Qb = lds2_at(aQ + 2 * ob), Qc = lds2_at(aQ + 2 * oc);
       const float P1a = Qa.x, P1b = Qb.x, P1c = Qc.x, P2a = Qa.y, P2b = Qb.y, P2c = Qc.y;
-      // phys p = slot*33 + lane  ->  count = lane*VPL + slot
-      const int pa_ = oa >> 2, pb_ = ob >> 2, pc_ = oc >> 2;
-      const int ia = (pa_ % 33) * VPL + pa_ / 33, ib = (pb_ % 33) * VPL + pb_ / 33, ic = (pc_ % 33) * VPL + pc_ / 33;
-      const float na = (float)ia, nab = (float)(ib - ia), nbc = (float)(ic - ib), nc = (float)(K - ic);
+      // byte offset o = 4*phys, phys = slot*33 + lane  ->  count = lane*VPL + slot = VPL*phys - (33*VPL-1)*slot with
+      // slot = phys/33 = (o*993) >> 17 (exact for phys < 2^13)
+      const float fa = count_from_offset<VPL>(oa), fb = count_from_offset<VPL>(ob), fc = count_from_offset<VPL>(oc);
+      const float na = fa, nab = fb - fa, nbc = fc - fb, nc = (float)K - fc;
       const float tau = taus[s];
       const float d1ab = P1b - P1a, d1bc = P1c - P1b;
       // sum over a<=k<b of (y-q)^2 = dP2 - 2q dP1 + n q^2, same for b<=k<c
