@@ -793,6 +793,251 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   }
 }
 
+// =================================================================================================
+// Tile kernel (plain gather and equality-reward hindsight): a block owns a tile of 256 sampled windows.
+//   phase 1, one THREAD per window -- everything scalar: index / goal streams, episode extents, the hindsight scan over
+//     the tail's 16-byte scan records (hash match -> verified), the return recurrence in the reference's own order
+//     (fp64 step, fp32 store: bit-exact mc_return), task_done / episode_step re-basing, every scalar key of the row and
+//     the learner aux.  All 32 lanes of a warp work on different windows, stores are coalesced over the batch index.
+//   phase 2, one WARP per window -- the wide keys: each lane owns <= S float4 of a row (row plan in registers), loads of four
+//     windows are in flight before their stores; the desired_goal lanes read the hindsight goal row instead.
+// The two phases meet in 12 bytes of shared memory per window (start row, goal row, last in-episode window row).
+// =================================================================================================
+constexpr int kTileWindows = 256;
+
+template <int S, bool HASH>
+__global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(const __grid_constant__ GatherArgs g) {
+  __shared__ int sm_s[kTileWindows], sm_grow[kTileWindows], sm_tail[kTileWindows];
+  const ArenaDev& A = g.A;
+  const int lane = lane_id();
+  const int wib = threadIdx.x >> 5;
+  const int T = g.T;
+  const int cap32 = (int)A.capacity, len32 = (int)g.len;
+  const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // ---- the lane's plan for phase 2: wide keys only ---------------------------------------------------------------
+  Slot slot[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    int i = lane + 32 * k;
+    Slot sl;
+    sl.src = nullptr; sl.dst = nullptr; sl.sstride = 0; sl.dwidth = 0; sl.meta = SLOT_NONE; sl.ovr = 0;
+    bool found = false;
+    for (int w = 0; w < A.n_wide; ++w) {
+      const int vecs = A.wide[w].vecs;
+      if (!found && i >= 0 && i < vecs) {
+        found = true;
+        float* o = g.out.p[A.wide[w].key];
+        if (o != nullptr) {
+          const int width = A.wide[w].width;
+          const bool v4 = (width & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+          sl.src = A.wide[w].base + 4 * i;
+          sl.dst = o + 4 * i;
+          sl.sstride = A.wide[w].stride;
+          sl.dwidth = width;
+          sl.meta = (v4 ? SLOT_V4 : SLOT_PART) | ((HASH && w == A.wide_dg) ? SLOT_DG : 0) | (i << 4) | (min(4, width - 4 * i) << 12);
+        }
+      }
+      i -= vecs;
+    }
+    slot[k] = sl;
+  }
+  const WideSlab AG = HASH ? A.wide[A.wide_ag] : A.wide[0];
+
+  const int64_t n_tiles = (g.b_end - g.b_begin + kTileWindows - 1) / kTileWindows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b0 = g.b_begin + tile * kTileWindows;
+    const int n_here = (int)min((int64_t)kTileWindows, g.b_end - b0);
+
+    // ================= phase 1: thread <-> window =================
+    if ((int)threadIdx.x < n_here) {
+      const int64_t b = b0 + threadIdx.x;
+      int64_t s64 = __ldg(g.starts + b);
+      if (s64 >= g.len) s64 %= g.len;
+      const int s = (int)s64;
+      bool relabel = false;
+      int tail_last = -1, ep_first = 0, grow = 0;
+      if (HASH && g.flags != nullptr && __ldg(g.flags + b) != 0) {
+        const float* rec = A.rec + (int64_t)s * A.rec_stride;
+        const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
+        if (es >= 0) {
+          relabel = true;
+          ep_first = es;
+          tail_last = ee - s + (ee < s ? cap32 : 0);
+          grow = (int)__ldg(g.goal_rows + b);
+        }
+      }
+      sm_s[threadIdx.x] = s;
+      sm_grow[threadIdx.x] = grow;
+      sm_tail[threadIdx.x] = tail_last;
+
+      float4 gsc = zero4;
+      int gd = -1;
+      // the hindsight predicate of one tail row: R(ag_j, g*) == 0  <=>  achieved_goal[row] == achieved_goal[goal_row]
+      auto matches = [&](int j, const float4& r) {
+        bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+        if (m) {  // hash match: the goal row itself is equal unless it holds a NaN; any other row is verified
+          if (j == gd) m = (__float_as_uint(r.w) & 1u) == 0u;
+          else m = rows_equal(A, ring_row32(s, j, cap32), grow);
+        }
+        return m;
+      };
+      if (HASH && relabel) {
+        gsc = __ldg(A.scan + grow);
+        gd = grow - s + (grow < s ? cap32 : 0);
+        // return-to-go over the whole real episode with relabelled rewards (quirk Q5), newest row first, each step in fp64
+        // and rounded to fp32 on store exactly like nstep_return.py:69-72
+        float acc = 0.f;
+        bool first = true;
+        for (int j = tail_last; j >= 0; --j) {
+          const float4 r = __ldg(A.scan + ring_row32(s, j, cap32));
+          const bool m = matches(j, r);
+          const float rnew = (float)((double)r.z + (m ? 0.0 : -1.0));
+          acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
+          first = false;
+          if (j < T && A.col_mc_return >= 0) {
+            float* o = g.out.p[A.scal_key[A.col_mc_return]];
+            if (o != nullptr) st_stream1(o + (int64_t)j * g.n + b, acc);
+          }
+        }
+      }
+      // first row of the synthetic episode the window starts in (exact mode scans the episode prefix, her.py:72-83)
+      int seg_first = -1;
+      int j0 = 0;
+      if (HASH && relabel) {
+        j0 = s - ep_first + (s < ep_first ? cap32 : 0);
+        if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+          seg_first = 0;
+          for (int j = j0 - 1; j >= 0; --j) {
+            const int row = ring_row32(ep_first, j, cap32);
+            const float4 r = __ldg(A.scan + row);
+            bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+            if (m) {
+              if (row == grow) m = (__float_as_uint(r.w) & 1u) == 0u;
+              else m = rows_equal(A, row, grow);
+            }
+            if (m) {
+              seg_first = j + 1;
+              break;
+            }
+          }
+        }
+      }
+      // forward over the window rows: scalar keys (with the hindsight overrides) and the learner aux
+      float prev_step = 0.f, prev_mask = 0.f, csum = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const int row = ring_row32(s, t, len32);
+        const float* rec = A.rec + (int64_t)row * A.rec_stride;
+        const bool in_ep = HASH && relabel && t <= tail_last;
+        float v_step = A.col_ep_step >= 0 ? __ldg(rec + A.col_ep_step) : 0.f;
+        float v_done = A.col_task_done >= 0 ? __ldg(rec + A.col_task_done) : 0.f;
+        float v_rew = 0.f;
+        if (in_ep) {
+          const float4 r = __ldg(A.scan + ring_row32(s, t, cap32));
+          const bool m = matches(t, r);
+          v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
+          v_done = m ? 1.f : 0.f;
+          if (seg_first >= 0 && A.col_ep_step >= 0)
+            v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + A.col_ep_step);
+          if (m) seg_first = j0 + t + 1;
+        }
+        for (int c = 0; c < A.n_scal; ++c) {
+          float* o = g.out.p[A.scal_key[c]];
+          if (o == nullptr) continue;
+          float val;
+          if (c == A.col_ep_step) val = v_step;
+          else if (c == A.col_task_done) val = v_done;
+          else if (in_ep && c == A.col_reward) val = v_rew;
+          else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
+          else val = __ldg(rec + c);
+          st_stream1(o + (int64_t)t * g.n + b, val);
+        }
+        if (want_aux) {
+          // mask = !task_done (deepQlearning.py:201); is_contiguous[t-1] = (step[t]==step[t-1]+1) & mask[t-1] (:202-203)
+          const float v_mask = v_done != 0.f ? 0.f : 1.f;
+          if (g.aux_mask) st_stream1(g.aux_mask + (int64_t)t * g.n + b, v_mask);
+          if (t > 0) {
+            const float c = (v_step == prev_step + 1.f && prev_mask != 0.f) ? 1.f : 0.f;
+            csum += c;
+            if (g.aux_contig) st_stream1(g.aux_contig + (int64_t)(t - 1) * g.n + b, c);
+            if (g.aux_weight && T > 2) g.aux_weight[(int64_t)(t - 1) * g.n + b] = c;  // parked, rescaled below
+          }
+          prev_step = v_step;
+          prev_mask = v_mask;
+        }
+      }
+      if (want_aux && g.aux_weight && T >= 2) {
+        // upstream weight of q_loss[t,b]: contig / ((sum_t contig + 1e-4) * B * T)  (deepQlearning.py:222-225,249)
+        const float scale = g.inv_bt / (csum + 1e-4f);
+        if (T == 2) {
+          st_stream1(g.aux_weight + b, csum * scale);
+        } else {
+          for (int t = 0; t < T - 1; ++t) {
+            float* w = g.aux_weight + (int64_t)t * g.n + b;
+            *w = *w * scale;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ================= phase 2: warp <-> window, wide keys =================
+    constexpr int UW = 4;  // windows whose loads are in flight together
+    for (int w0 = wib * 32; w0 < wib * 32 + 32 && w0 < n_here; w0 += UW) {
+      float4 x[UW][2][S];
+      int sv[UW], tl[UW];
+      const float* ga[UW];
+#pragma unroll
+      for (int u = 0; u < UW; ++u) {
+        const int wi = min(w0 + u, n_here - 1);
+        sv[u] = sm_s[wi];
+        tl[u] = sm_tail[wi];
+        ga[u] = (HASH && tl[u] >= 0) ? AG.base + (int64_t)sm_grow[wi] * AG.stride : nullptr;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int row = ring_row32(sv[u], t, len32);
+#pragma unroll
+          for (int k = 0; k < S; ++k) {
+            x[u][t][k] = zero4;
+            if (t < T && w0 + u < n_here) x[u][t][k] = slot_load(slot[k], row, t <= tl[u] ? ga[u] : nullptr);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UW; ++u) {
+        if (w0 + u >= n_here) continue;
+        const int64_t b = b0 + w0 + u;
+        auto put = [&](int t, const float4 (&v)[S]) {
+          const int64_t orow = (int64_t)t * g.n + b;
+#pragma unroll
+          for (int k = 0; k < S; ++k) {
+            const uint32_t meta = slot[k].meta;
+            if (meta & SLOT_V4) st_stream4(slot[k].dst + orow * slot[k].dwidth, v[k]);
+            if (meta & SLOT_PART) {
+              const int m = (meta >> 12) & 15u;
+              const float xs[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+              float* dst = slot[k].dst + orow * slot[k].dwidth;
+              for (int c = 0; c < m; ++c) st_stream1(dst + c, xs[c]);
+            }
+          }
+        };
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          if (t < T) put(t, x[u][t]);
+        for (int t = 2; t < T; ++t) {
+          const int row = ring_row32(sv[u], t, len32);
+          float4 v[S];
+#pragma unroll
+          for (int k = 0; k < S; ++k) v[k] = slot_load(slot[k], row, t <= tl[u] ? ga[u] : nullptr);
+          put(t, v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int g_force_generic_gather = 0;       // tests flip this to cover the descriptor-walking kernel
 int g_force_full_vector_relabel = 0;  // ... and this to cover MODE 1 with the bitflip functor
 
@@ -837,6 +1082,36 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   int row_vecs = a->dev.n_scal;  // one lane per float4 of a wide key + one lane per scalar column
   for (int w = 0; w < a->dev.n_wide; ++w) row_vecs += a->dev.wide[w].vecs;
   const int slots = (row_vecs + 31) / 32;
+  int wide_vecs = 0;
+  for (int w = 0; w < a->dev.n_wide; ++w) wide_vecs += a->dev.wide[w].vecs;
+  const int wslots = (wide_vecs + 31) / 32;
+  const bool hash_ok = relabel && reward_op == FDQL_REWARD_BITFLIP && !g_force_full_vector_relabel;
+  if (wslots <= 4 && (!relabel || hash_ok) && !(g_force_generic_gather & (1 | 8))) {
+    int64_t tiles = (b_end - b_begin + kTileWindows - 1) / kTileWindows;
+#define FDQL_LAUNCH_TILE(SV, HASHV)                                                                              \
+  do {                                                                                                           \
+    auto kern = sample_gather_tile_kernel<SV, HASHV>;                                                            \
+    static int per_sm_cached = 0;                                                                                \
+    if (per_sm_cached == 0) {                                                                                    \
+      FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, kern, kTileWindows, 0));           \
+      if (per_sm_cached < 1) per_sm_cached = 1;                                                                  \
+    }                                                                                                            \
+    if (tiles > (int64_t)a->num_sms * per_sm_cached) tiles = (int64_t)a->num_sms * per_sm_cached;                \
+    kern<<<(unsigned)tiles, kTileWindows, 0, st>>>(g);                                                           \
+  } while (0)
+#define FDQL_TILE_S(HASHV)                                   \
+  do {                                                       \
+    if (wslots <= 1) FDQL_LAUNCH_TILE(1, HASHV);             \
+    else if (wslots == 2) FDQL_LAUNCH_TILE(2, HASHV);        \
+    else FDQL_LAUNCH_TILE(4, HASHV);                         \
+  } while (0)
+    if (hash_ok) FDQL_TILE_S(true);
+    else FDQL_TILE_S(false);
+#undef FDQL_TILE_S
+#undef FDQL_LAUNCH_TILE
+    FDQL_CUDA(cudaGetLastError());
+    return FDQL_OK;
+  }
   if (slots <= 4 && !(g_force_generic_gather & 1)) {
     // persistent-style grid: as many blocks as stay resident, each warp strides over the windows
 #define FDQL_LAUNCH_FAST(SV, LPRV, MODEV)                                                                              \
@@ -915,7 +1190,8 @@ extern "C" {
 
 int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
-  g_force_generic_gather = on & 5;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner
+  g_force_generic_gather = on & 13;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
+                                     // bit 3: warp-per-window kernels instead of the tile kernel
   g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }

@@ -138,7 +138,8 @@ int fdql_sample_gather(const fdql_arena* a, int64_t n_windows, int32_t T, int64_
 /* test hook (returns the previous setting): bit 0 routes fdql_sample_gather / fdql_gather_rows through the
  * descriptor-walking kernel that serves rows wider than 128 float4; bit 1 makes the bitflip functor take the full-vector
  * relabel scan instead of the hash-assisted one; bit 2 makes the hash-assisted scan use the per-pass suffix scan for the
- * returns instead of the scan-free (Horner + one reduction) form */
+ * returns instead of the scan-free (Horner + one reduction) form; bit 3 routes plain and bitflip gathers through the
+ * warp-per-window kernels instead of the tile kernel */
 int fdql_debug_force_generic_gather(int on);
 
 /* DistributionalSoftActorCritic.q_loss from the MLP outputs onward + quantile_huber_loss_f, forward and backward

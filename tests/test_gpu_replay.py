@@ -352,9 +352,24 @@ def test_hash_scan_with_per_pass_suffix_scan(R, fdql, T, G, max_len):
     """The hash-assisted scan has two return recomputes (scan-free Horner form for T <= 32, per-pass suffix scan otherwise);
     force the second on small windows too."""
     lib = fdql.lib()
-    old = lib.fdql_debug_force_generic_gather(4)
+    old = lib.fdql_debug_force_generic_gather(8 | 4)
     try:
         test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len)
+        test_hash_scan_verifies_matches_and_nans(R, fdql)
+    finally:
+        lib.fdql_debug_force_generic_gather(old)
+
+
+@pytest.mark.parametrize("T,G,max_len", [(1, 16, 40), (2, 16, 130), (5, 3, 70), (50, 64, 200)])
+def test_warp_per_window_kernels(R, fdql, T, G, max_len):
+    """Plain and bitflip gathers normally take the tile kernel (thread-per-window scalars + warp-per-window wide keys); route
+    them through the warp-per-window kernels (scan-free Horner returns for T <= 32) and repeat the parity runs."""
+    lib = fdql.lib()
+    old = lib.fdql_debug_force_generic_gather(8)
+    try:
+        test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len)
+        test_hash_scan_verifies_matches_and_nans(R, fdql)
+        test_ring_cursor_and_gather_golden(R)
     finally:
         lib.fdql_debug_force_generic_gather(old)
 
