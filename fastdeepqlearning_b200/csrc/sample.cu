@@ -102,6 +102,7 @@ struct GatherArgs {
   float* aux_mask;
   float* aux_contig;
   float* aux_weight;
+  int32_t tile;  // tile kernel: windows per block iteration (32..256)
 };
 
 __device__ __forceinline__ double warp_suffix_scan(double v, double g, int lane) {
@@ -804,6 +805,12 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
 // The two phases meet in 12 bytes of shared memory per window (start row, goal row, last in-episode window row).
 // =================================================================================================
 constexpr int kTileWindows = 256;
+#ifndef TAIL_UNROLL
+#define TAIL_UNROLL 4
+#endif
+#ifndef WIN_UNROLL
+#define WIN_UNROLL 4
+#endif
 
 template <int S, bool HASH>
 __global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(const __grid_constant__ GatherArgs g) {
@@ -845,10 +852,11 @@ __global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(con
   }
   const WideSlab AG = HASH ? A.wide[A.wide_ag] : A.wide[0];
 
-  const int64_t n_tiles = (g.b_end - g.b_begin + kTileWindows - 1) / kTileWindows;
+  const int tile_w = g.tile;  // small launches use small tiles so that every SM gets work
+  const int64_t n_tiles = (g.b_end - g.b_begin + tile_w - 1) / tile_w;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t b0 = g.b_begin + tile * kTileWindows;
-    const int n_here = (int)min((int64_t)kTileWindows, g.b_end - b0);
+    const int64_t b0 = g.b_begin + tile * tile_w;
+    const int n_here = (int)min((int64_t)tile_w, g.b_end - b0);
 
     // ================= phase 1: thread <-> window =================
     if ((int)threadIdx.x < n_here) {
@@ -871,6 +879,7 @@ __global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(con
       sm_s[threadIdx.x] = s;
       sm_grow[threadIdx.x] = grow;
       sm_tail[threadIdx.x] = tail_last;
+      float* o_ret = A.col_mc_return >= 0 ? g.out.p[A.scal_key[A.col_mc_return]] : nullptr;
 
       float4 gsc = zero4;
       int gd = -1;
@@ -890,15 +899,20 @@ __global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(con
         // and rounded to fp32 on store exactly like nstep_return.py:69-72
         float acc = 0.f;
         bool first = true;
-        for (int j = tail_last; j >= 0; --j) {
-          const float4 r = __ldg(A.scan + ring_row32(s, j, cap32));
-          const bool m = matches(j, r);
-          const float rnew = (float)((double)r.z + (m ? 0.0 : -1.0));
-          acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
-          first = false;
-          if (j < T && A.col_mc_return >= 0) {
-            float* o = g.out.p[A.scal_key[A.col_mc_return]];
-            if (o != nullptr) st_stream1(o + (int64_t)j * g.n + b, acc);
+        constexpr int UR = TAIL_UNROLL;  // scan records in flight per thread (per-thread L2 prefetches were measured slower)
+        for (int jt = tail_last; jt >= 0; jt -= UR) {
+          float4 r4[UR];
+#pragma unroll
+          for (int u = 0; u < UR; ++u) r4[u] = jt - u >= 0 ? __ldg(A.scan + ring_row32(s, jt - u, cap32)) : zero4;
+#pragma unroll
+          for (int u = 0; u < UR; ++u) {
+            const int j = jt - u;
+            if (j < 0) break;
+            const bool m = matches(j, r4[u]);
+            const float rnew = (float)((double)r4[u].z + (m ? 0.0 : -1.0));
+            acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
+            first = false;
+            if (j < T && o_ret != nullptr) st_stream1(o_ret + (int64_t)j * g.n + b, acc);
           }
         }
       }
@@ -983,8 +997,8 @@ __global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(con
     __syncthreads();
 
     // ================= phase 2: warp <-> window, wide keys =================
-    constexpr int UW = 4;  // windows whose loads are in flight together
-    for (int w0 = wib * 32; w0 < wib * 32 + 32 && w0 < n_here; w0 += UW) {
+    constexpr int UW = WIN_UNROLL;  // windows whose loads are in flight together
+    for (int w0 = wib * UW; w0 < n_here; w0 += UW * (kTileWindows / 32)) {
       float4 x[UW][2][S];
       int sv[UW], tl[UW];
       const float* ga[UW];
@@ -1038,6 +1052,7 @@ __global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(con
   }
 }
 
+int g_tile_override = 0;
 int g_force_generic_gather = 0;       // tests flip this to cover the descriptor-walking kernel
 int g_force_full_vector_relabel = 0;  // ... and this to cover MODE 1 with the bitflip functor
 
@@ -1086,8 +1101,16 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   for (int w = 0; w < a->dev.n_wide; ++w) wide_vecs += a->dev.wide[w].vecs;
   const int wslots = (wide_vecs + 31) / 32;
   const bool hash_ok = relabel && reward_op == FDQL_REWARD_BITFLIP && !g_force_full_vector_relabel;
-  if (wslots <= 4 && (!relabel || hash_ok) && !(g_force_generic_gather & (1 | 8))) {
-    int64_t tiles = (b_end - b_begin + kTileWindows - 1) / kTileWindows;
+  // small launches are latency-bound and run faster with one warp per window (measured: 4096 windows 20 us vs 29 us);
+  // from ~48K windows on, the tile kernel's lower instruction count wins (262144 windows: 209 us vs 261 us)
+  const bool big = (b_end - b_begin) >= 49152 || g_tile_override != 0;
+  if (wslots <= 4 && (!relabel || hash_ok) && big && !(g_force_generic_gather & (1 | 8))) {
+    // tile size: 256 windows when there is enough work to fill the machine, down to 32 for small batches
+    int tile_w = kTileWindows;
+    while (tile_w > 64 && (b_end - b_begin + tile_w - 1) / tile_w < (int64_t)a->num_sms * 3) tile_w >>= 1;
+    if (g_tile_override) tile_w = g_tile_override;
+    g.tile = tile_w;
+    int64_t tiles = (b_end - b_begin + tile_w - 1) / tile_w;
 #define FDQL_LAUNCH_TILE(SV, HASHV)                                                                              \
   do {                                                                                                           \
     auto kern = sample_gather_tile_kernel<SV, HASHV>;                                                            \
@@ -1190,6 +1213,7 @@ extern "C" {
 
 int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
+  g_tile_override = (on >> 8) & 0x1ff;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
   g_force_generic_gather = on & 13;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
                                      // bit 3: warp-per-window kernels instead of the tile kernel
   g_force_full_vector_relabel = (on >> 1) & 1;
