@@ -805,15 +805,18 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
 // The two phases meet in 12 bytes of shared memory per window (start row, goal row, last in-episode window row).
 // =================================================================================================
 constexpr int kTileWindows = 256;
+#ifndef TILE_MINB
+#define TILE_MINB 4
+#endif
 #ifndef TAIL_UNROLL
 #define TAIL_UNROLL 4
 #endif
 #ifndef WIN_UNROLL
-#define WIN_UNROLL 4
+#define WIN_UNROLL 2
 #endif
 
 template <int S, bool HASH>
-__global__ void __launch_bounds__(kTileWindows, 3) sample_gather_tile_kernel(const __grid_constant__ GatherArgs g) {
+__global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_kernel(const __grid_constant__ GatherArgs g) {
   __shared__ int sm_s[kTileWindows], sm_grow[kTileWindows], sm_tail[kTileWindows];
   const ArenaDev& A = g.A;
   const int lane = lane_id();
