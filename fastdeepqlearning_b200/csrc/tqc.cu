@@ -321,6 +321,388 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
   }
 }
 
+// =================================================================================================
+// Group kernel (n_atoms, n_z <= 128): a warp owns G = 32/LPT transitions per round and works in two layouts.
+//   phase A, LPT lanes per transition, E = 16 values per lane: the pooled target atoms come out of a shared-memory staging
+//     copy (filled one round ahead with 16-byte cp.async), are sorted by a bitonic network that is in registers except for
+//     log2(LPT) partner exchanges per merge phase, turned into the soft target, centred, prefix-summed (serial walk per lane +
+//     a log2(LPT)-step scan) and written as G search tables.
+//   phase B, the whole warp per transition: lane l handles predicted atoms l, l+32, ...; all 32 lanes search the SAME table,
+//     whose layout makes every search level bank-conflict free, and read {-P1, P2} at the three split points.
+// Against the warp-per-transition kernel above this removes most of the cross-lane sort traffic (6 instead of 15 exchange
+// stages of 128 values), all scans/reductions/bounds checks that were paid per transition by 32 lanes, and the global-load
+// address arithmetic (rows arrive by cp.async).
+//   table layout: sorted index i lives at phys(i) = (i % R) * 32 + i / R, R = NT / 32 rows, table pitch NT + 1 entries so
+//   that the G tables of a warp start one bank apart (phase A stores are conflict free, too).
+// =================================================================================================
+constexpr int kGrpE = 16;
+constexpr int kGrpWarps = 4;
+
+template <int NT>
+struct GrpCfg {
+  static constexpr int E = kGrpE;
+  static constexpr int LPT = NT / E;    // lanes per transition in phase A
+  static constexpr int G = 32 / LPT;    // transitions per warp and round
+  static constexpr int R = NT / 32;     // table rows = predicted atoms per lane in phase B
+  static constexpr int TP = NT + 1;     // table pitch in entries
+  static constexpr int kZY = G * TP;    // floats: staged rows of next_z, later the G sorted tables (two buffers)
+  static constexpr int kSc = 8;         // per-transition scalars
+  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars |
+  static constexpr int kRed = 3 * G * 33 + (4 - (3 * G * 33) % 4) % 4;  // per-lane partial sums, [3*G][33]
+  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | red |
+  static constexpr int kWarpFloats = 2 * kZY + 2 * kZY + G * NT + kSc * G + kRed;
+  static_assert(kZY % 4 == 0 && kWarpFloats % 4 == 0, "16-byte alignment of the staging buffers");
+};
+
+template <int E, int NT, int K>
+__device__ __forceinline__ void grp_flip(float (&e)[E], int sl) {
+  if constexpr (K <= E) {
+#pragma unroll
+    for (int s = 0; s < E; ++s)
+      if ((s & (K >> 1)) == 0) {
+        const int p = s ^ (K - 1);
+        const float x = e[s], y = e[p];
+        e[s] = fminf(x, y);
+        e[p] = fmaxf(x, y);
+      }
+  } else {
+    constexpr int LM = K / E - 1;
+    const bool lower = (sl & (K / 2 / E)) == 0;
+    float o[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) o[s] = __shfl_xor_sync(kFull, e[E - 1 - s], LM);
+#pragma unroll
+    for (int s = 0; s < E; ++s) e[s] = lower ? fminf(e[s], o[s]) : fmaxf(e[s], o[s]);
+  }
+}
+template <int E, int J>
+__device__ __forceinline__ void grp_half(float (&e)[E], int sl) {
+  if constexpr (J >= E) {
+    constexpr int LM = J / E;
+    const bool lower = (sl & LM) == 0;
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const float o = __shfl_xor_sync(kFull, e[s], LM);
+      e[s] = lower ? fminf(e[s], o) : fmaxf(e[s], o);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < E; ++s)
+      if ((s & J) == 0) {
+        const float x = e[s], y = e[s | J];
+        e[s] = fminf(x, y);
+        e[s | J] = fmaxf(x, y);
+      }
+  }
+  if constexpr (J > 1) grp_half<E, J / 2>(e, sl);
+}
+template <int E, int NT, int K>
+__device__ __forceinline__ void grp_sort_from(float (&e)[E], int sl) {
+  grp_flip<E, NT, K>(e, sl);
+  if constexpr (K >= 4) grp_half<E, K / 4>(e, sl);
+  if constexpr (K < NT) grp_sort_from<E, NT, K * 2>(e, sl);
+}
+
+// one level of the branch-free search in the pitch-32 layout: lo is a multiple of 2*STEP, probe logical lo + STEP - 1.
+// The conditional advance is issued as a predicated IMAD (addr = one * imm + addr with an opaque register holding 1): the
+// sort and the compares already load the ALU pipe, IMAD goes down the FMA pipe.
+template <int R, int STEP, bool LE>
+__device__ __forceinline__ void grp_search_steps(uint32_t& addr, float x, uint32_t one) {
+  constexpr int kProbe = STEP >= R ? (R - 1) * 32 + STEP / R - 1 : (STEP - 1) * 32;
+  constexpr int kAdvance = STEP >= R ? STEP / R : STEP * 32;
+  if constexpr (LE)
+    asm volatile("{\n .reg .pred p;\n .reg .f32 v;\n ld.shared.f32 v, [%0+%3];\n setp.le.f32 p, v, %1;\n @p mad.lo.u32 %0, %2, %4, %0;\n}"
+                 : "+r"(addr)
+                 : "f"(x), "r"(one), "n"(4 * kProbe), "n"(4 * kAdvance));
+  else
+    asm volatile("{\n .reg .pred p;\n .reg .f32 v;\n ld.shared.f32 v, [%0+%3];\n setp.lt.f32 p, v, %1;\n @p mad.lo.u32 %0, %2, %4, %0;\n}"
+                 : "+r"(addr)
+                 : "f"(x), "r"(one), "n"(4 * kProbe), "n"(4 * kAdvance));
+  if constexpr (STEP > 1) grp_search_steps<R, STEP / 2, LE>(addr, x, one);
+}
+// byte offset 4*phys -> sorted index: phys = row * 32 + col, i = col * R + row
+template <int R>
+__device__ __forceinline__ float grp_count(uint32_t o) {
+  return (float)(int)((((o & 124u) * R) >> 2) + (o >> 7));
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// rows [m0, m0 + rows) of a [M, width] matrix -> shared memory, asynchronously when the run is 16-byte aligned and whole
+__device__ __forceinline__ void grp_stage_rows(float* dst, const float* __restrict__ src, int64_t m0, int width, int rows, int full_rows,
+                                               bool aligned, int lane) {
+  const float* g = src + m0 * width;
+  const int nfl = rows * width;
+  if (aligned && rows == full_rows) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    for (int i = lane * 4; i < nfl; i += 128) cp_async16(d + 4 * i, g + i);
+  } else {
+    for (int i = lane; i < nfl; i += 32) dst[i] = ld_stream1(g + i);
+  }
+}
+
+constexpr int kGrpLb = 1, kGrpStats = 2;  // kernel flavours: lower bound (mc_return given), summaries (stats given)
+
+template <int NT, int FLAGS>
+__global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
+  using C = GrpCfg<NT>;
+  constexpr int E = C::E, LPT = C::LPT, G = C::G, R = C::R, TP = C::TP;
+  constexpr bool LB = (FLAGS & kGrpLb) != 0, STATS = (FLAGS & kGrpStats) != 0;
+  constexpr int NQ = STATS ? 3 : 1;  // per-transition sums reduced over the warp: loss, sum q, sum q^2
+  extern __shared__ __align__(16) float grp_smem[];
+  __shared__ double sm_stats[3];
+  const int lane = lane_id(), wib = threadIdx.x >> 5;
+  float* W = grp_smem + wib * C::kWarpFloats;
+  float2* QT = reinterpret_cast<float2*>(W + 2 * C::kZY);
+  float* qs = W + 4 * C::kZY;
+  float* sc = qs + G * NT;
+  float* red = sc + C::kSc * G;  // [3 * G][33]: per-lane partial sums, one row per (quantity, transition)
+  const uint32_t aW = (uint32_t)__cvta_generic_to_shared(W), aQ = aW + 8 * C::kZY;
+  const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
+  const uint32_t one = (uint32_t)min(n, 1);  // 1, opaque to the compiler (see grp_search_steps)
+  const float Kf = (float)K;
+  const float inv_n = 1.f / (float)n;
+  const float inv_nk = 1.f / ((float)n * (float)K);
+  const float inv_nm1 = n > 1 ? 1.f / (float)(n - 1) : 0.f;
+  const float half_over_n = (float)(0.5 / (double)n);
+  if (STATS && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
+  if (STATS) __syncthreads();
+  double st_sum = 0.0, st_var = 0.0;
+  int viol = 0;
+  // phase B constants of this lane: :98, tau over the pooled atoms: fl32(fl32(j / n) + fl32(1/2/n)) for j = lane + 32 s
+  float taus[R], omts[R], validf[R];
+#pragma unroll
+  for (int s = 0; s < R; ++s) {
+    taus[s] = __fadd_rn(__fdiv_rn((float)(lane + 32 * s), (float)n), half_over_n);
+    omts[s] = 1.f - taus[s];
+    validf[s] = lane + 32 * s < n ? 1.f : 0.f;
+  }
+  // phase A constants
+  const int grp = lane / LPT, sl = lane % LPT;
+  const int kk = K - sl * E;                  // kept slots of this lane: s < kk
+  const int c_src = grp * LPT + (K / 2) / E;  // lane holding a kept target near the median in slot 0
+  const uint32_t physK4 = 4u * (uint32_t)((K % R) * 32 + K / R);
+  const bool zal = (reinterpret_cast<uintptr_t>(a.next_z) & 15) == 0, qal = (reinterpret_cast<uintptr_t>(a.q_pred) & 15) == 0;
+
+  const int64_t n_groups = (a.M + G - 1) / G;
+  const int64_t wstride = (int64_t)gridDim.x * kGrpWarps;
+  int64_t gi = (int64_t)blockIdx.x * kGrpWarps + wib;
+  int buf = 0;
+  if (gi < n_groups) grp_stage_rows(W, a.next_z, gi * G, nz, (int)min((int64_t)G, a.M - gi * G), G, zal, lane);
+  cp_async_commit();
+  for (; gi < n_groups; gi += wstride, buf ^= 1) {
+    const int64_t m0 = gi * G;
+    const int rows = (int)min((int64_t)G, a.M - m0);
+    float* Zb = W + buf * C::kZY;
+    const uint32_t aZb = aW + 4 * buf * C::kZY;
+    grp_stage_rows(qs, a.q_pred, m0, n, rows, G, qal, lane);
+    cp_async_commit();
+    cp_async_wait<1>();  // this round's next_z rows have landed
+    __syncwarp();
+
+    // ================= phase A: LPT lanes per transition =================
+    {
+      const bool live = grp < rows;
+      const int64_t mm = live ? m0 + grp : a.M - 1;
+      const float* zst = Zb + grp * nz;
+      float e[E];
+#pragma unroll
+      for (int s = 0; s < E; ++s) {
+        const int j = s * LPT + sl;  // any split of the row over the lanes will do: it is sorted next
+        float v = CUDART_INF_F;
+        if (j < nz) v = live ? zst[j] : 0.f;
+        e[s] = v;
+      }
+      const float rew = a.reward ? __ldg(a.reward + mm) : 0.f, msk = a.mask ? __ldg(a.mask + mm) : 1.f;
+      const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
+      const float ent = a.next_log_pi ? __fmul_rn(alpha, -__ldg(a.next_log_pi + mm)) : 0.f;
+      const float Gv = LB ? __ldg(a.mc_return + mm) : 0.f;
+      const float gs = a.grad_scale ? __ldg(a.grad_scale + mm) : 1.f;
+      const float mg = __fmul_rn(msk, a.gamma);
+
+      grp_sort_from<E, NT, 2>(e, sl);  // sorted position of (sl, s) is i = sl * E + s
+
+      // soft target (:50-58) in the reference's operator order; raw mode (quantile_huber_loss_f): targets as given
+      if (a.reward) {
+        if (a.next_log_pi) {
+#pragma unroll
+          for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(e[s], ent)));
+        } else {
+#pragma unroll
+          for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, e[s]));
+        }
+      }
+      if (a.td_target && live) {
+#pragma unroll
+        for (int s = 0; s < E; ++s)
+          if (s < kk) a.td_target[(m0 + grp) * K + sl * E + s] = e[s];
+      }
+      // centre on a kept target near the median, cut the top n_drop (+inf), this lane's sums of y and y^2.
+      // Entries at sorted index >= K hold +inf and make every later prefix non-finite; no search ever lands past K.
+      const float c0 = __shfl_sync(kFull, e[0], c_src);
+      float l1 = 0.f, l2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < E; ++s) {
+        const float y = s < kk ? e[s] - c0 : CUDART_INF_F;
+        e[s] = y;
+        l1 += y;
+        l2 = fmaf(y, y, l2);
+      }
+      float x1 = l1, x2 = l2;  // inclusive scan over the LPT lanes of the transition
+#pragma unroll
+      for (int d = 1; d < LPT; d <<= 1) {
+        const float o1 = __shfl_up_sync(kFull, x1, d, LPT), o2 = __shfl_up_sync(kFull, x2, d, LPT);
+        if (sl >= d) {
+          x1 += o1;
+          x2 += o2;
+        }
+      }
+      float p1 = __shfl_up_sync(kFull, x1, 1, LPT), p2 = __shfl_up_sync(kFull, x2, 1, LPT);  // exclusive
+      if (sl == 0) p1 = p2 = 0.f;
+      p1 = -p1;
+      __syncwarp();  // every lane has read its staged row: the buffer becomes the tables
+      float* Yt = Zb + grp * TP + sl * (E / R);
+      float2* Qt = QT + grp * TP + sl * (E / R);
+#pragma unroll
+      for (int s = 0; s < E; ++s) {
+        const int ph = (s % R) * 32 + s / R;
+        Yt[ph] = e[s];
+        Qt[ph] = make_float2(p1, p2);  // {-P1_i, P2_i}
+        p1 -= e[s];
+        p2 = fmaf(e[s], e[s], p2);
+      }
+      if (sl == 0) {
+        sc[grp * C::kSc + 0] = c0;
+        sc[grp * C::kSc + 1] = Gv - c0;
+        sc[grp * C::kSc + 2] = gs;
+      }
+    }
+    __syncwarp();
+    {  // next round's next_z rows into the other buffer (its tables are dead)
+      const int64_t gnext = gi + wstride;
+      if (gnext < n_groups)
+        grp_stage_rows(W + (buf ^ 1) * C::kZY, a.next_z, gnext * G, nz, (int)min((int64_t)G, a.M - gnext * G), G, zal, lane);
+      cp_async_commit();
+    }
+    cp_async_wait<1>();  // this round's q_pred rows have landed
+    __syncwarp();
+
+    // ================= phase B: the warp per transition =================
+    for (int t = 0; t < rows; ++t) {
+      const float c0 = sc[t * C::kSc + 0], gs = sc[t * C::kSc + 2];
+      const float Gc = LB ? sc[t * C::kSc + 1] : 0.f;
+      const uint32_t aYt = aZb + 4 * t * TP, aQt = aQ + 8 * t * TP;
+      const float nT1 = lds_f32(aQt + 2 * physK4);  // -(sum of the kept centred targets)
+      const float gscale = inv_nk * gs, glb = -inv_n * gs;
+      const float* qrow = qs + t * n + lane;
+      float* __restrict__ grow_ = a.grad_q ? a.grad_q + (m0 + t) * n + lane : nullptr;
+      float acc = 0.f, lbacc = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const bool ok = validf[s] != 0.f;
+        const float qc = ok ? qrow[32 * s] - c0 : 0.f;
+        uint32_t oa = aYt, ob = aYt, oc = aYt;
+        grp_search_steps<R, NT / 2, false>(oa, qc - 1.f, one);  // a = #(y < q-1)
+        grp_search_steps<R, NT / 2, false>(ob, qc, one);        // b = #(y < q)
+        grp_search_steps<R, NT / 2, true>(oc, qc + 1.f, one);   // c = #(y <= q+1)
+        oa -= aYt;
+        ob -= aYt;
+        oc -= aYt;
+        const float2 Qa = lds2_at(aQt + 2 * oa), Qb = lds2_at(aQt + 2 * ob), Qc = lds2_at(aQt + 2 * oc);
+        const float ia = grp_count<R>(oa), ib = grp_count<R>(ob), ic = grp_count<R>(oc);
+        // L_i(q) = sum_{k<i} (q - y_k),  F_i(q) = sum_{k<i} (y_k - q)^2   (table: x = -P1_i, y = P2_i)
+        const float La = fmaf(ia, qc, Qa.x), Lb = fmaf(ib, qc, Qb.x), Lc = fmaf(ic, qc, Qc.x);
+        const float Fa = fmaf(qc, La + Qa.x, Qa.y), Fb = fmaf(qc, Lb + Qb.x, Qb.y), Fc = fmaf(qc, Lc + Qc.x, Qc.y);
+        const float LK = fmaf(Kf, qc, nT1);
+        const float kc = Kf - ic;
+        const float neg = fmaf(0.5f, Fb - Fa, fmaf(-0.5f, ia, La));       // delta < 0 : weight 1 - tau
+        const float pos = fmaf(0.5f, Fc - Fb, fmaf(-0.5f, kc, Lc - LK));  // delta >= 0: weight tau
+        const float lj = fmaf(omts[s], neg, taus[s] * pos);
+        const float gneg = ia + (Lb - La);
+        const float gpos = (Lc - Lb) - kc;
+        const float gj = fmaf(omts[s], gneg, taus[s] * gpos);
+        float gl = 0.f;
+        if constexpr (LB) {  // :76-79 lower bound relu(mc_return - q)
+          const float lbj = fmaxf(Gc - qc, 0.f);
+          const bool on = lbj > 0.f;
+          gl = on ? glb : 0.f;
+          lbacc = fmaf(lbj, validf[s], lbacc);
+          if constexpr (STATS) viol += (on && ok) ? 1 : 0;
+        }
+        acc = fmaf(lj, validf[s], acc);
+        if (grow_ != nullptr && ok) st_stream1(grow_ + 32 * s, fmaf(gj, gscale, gl));
+        if constexpr (STATS) {
+          s1 += qc;  // padded slots hold 0
+          s2 = fmaf(qc, qc, s2);
+        }
+      }
+      red[(0 * G + t) * 33 + lane] = fmaf(acc, inv_nk, lbacc * inv_n);
+      if constexpr (STATS) {
+        red[(1 * G + t) * 33 + lane] = s1;
+        red[(2 * G + t) * 33 + lane] = s2;
+      }
+    }
+    __syncwarp();
+    // per-transition sums over the lanes: lane i adds up row i of `red` (pitch 33: conflict free)
+#pragma unroll
+    for (int base = 0; base < NQ * G; base += 32) {
+      const int idx = base + lane;
+      float sum = 0.f;
+      if (idx < NQ * G) {
+        const float* rrow = red + idx * 33;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sum += rrow[k];
+      }
+      const int t = idx % G, q = idx / G;
+      if (q == 0 && t < rows && a.loss && idx < NQ * G) a.loss[m0 + t] = sum;
+      if constexpr (STATS) {  // :66-67,80-82 q_pred mean, mean row variance (unbiased) from the centred moments
+        static_assert(!STATS || 3 * G <= 32 || G == 16, "layout of the summaries reduction");
+        if constexpr (3 * G <= 32) {
+          const float S1 = __shfl_sync(kFull, sum, G + (lane % G)), S2 = __shfl_sync(kFull, sum, 2 * G + (lane % G));
+          if (lane < rows) {
+            st_sum += (double)S1 + (double)n * (double)sc[lane * C::kSc + 0];
+            st_var += ((double)S2 - (double)S1 * (double)S1 * (double)inv_n) * (double)inv_nm1;
+          }
+        } else {  // G == 16: rows 0..15 loss, 16..31 sum q (first pass); 32..47 sum q^2 (second pass)
+          if (base == 0) {
+            const float S1 = __shfl_sync(kFull, sum, 16 + (lane % 16));
+            if (lane < rows) {
+              st_sum += (double)S1 + (double)n * (double)sc[lane * C::kSc + 0];
+              st_var -= (double)S1 * (double)S1 * (double)inv_n * (double)inv_nm1;
+            }
+          } else if (lane < rows) {
+            st_var += (double)sum * (double)inv_nm1;
+          }
+        }
+      }
+    }
+    __syncwarp();  // the q_pred staging, the scalars and `red` are rewritten in the next round
+  }
+  cp_async_wait<0>();
+  if constexpr (STATS) {
+    const int vsum = __reduce_add_sync(kFull, viol);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      st_sum += shfl_xor_f64(st_sum, d);
+      st_var += shfl_xor_f64(st_var, d);
+    }
+    if (lane == 0) {
+      atomicAdd(&sm_stats[0], st_sum);
+      atomicAdd(&sm_stats[1], st_var);
+      atomicAdd(&sm_stats[2], (double)vsum);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(a.stats + threadIdx.x, sm_stats[threadIdx.x]);
+    if (threadIdx.x == 3 && blockIdx.x == 0) atomicAdd(a.stats + 3, (double)a.M);
+  }
+}
+
 // ---- non-distributional variant: min over atoms, smooth-L1, lower bound replaces the TD term where active ----
 struct SacArgs {
   int64_t M;
@@ -423,13 +805,49 @@ static int num_sms() {
   return g_num_sms;
 }
 
+int g_tqc_warp_kernel = 0;  // test hook: 1 = always the warp-per-transition kernel
+
+template <int NT, int FLAGS>
+static int launch_tqc_group_f(const TqcArgs& a, cudaStream_t st) {
+  using C = GrpCfg<NT>;
+  constexpr size_t smem = (size_t)kGrpWarps * C::kWarpFloats * sizeof(float);
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tqc_loss_group_kernel<NT, FLAGS>, kGrpWarps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int64_t n_groups = (a.M + C::G - 1) / C::G;
+  int64_t blocks = (n_groups + kGrpWarps - 1) / kGrpWarps;
+  const int64_t resident = (int64_t)num_sms() * per_sm;
+  if (blocks > resident) blocks = resident;
+  tqc_loss_group_kernel<NT, FLAGS><<<(unsigned)blocks, kGrpWarps * 32, smem, st>>>(a);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+template <int NT>
+static int launch_tqc_group(const TqcArgs& a, cudaStream_t st) {
+  const int flags = (a.mc_return ? kGrpLb : 0) | (a.stats ? kGrpStats : 0);
+  switch (flags) {
+    case 0: return launch_tqc_group_f<NT, 0>(a, st);
+    case 1: return launch_tqc_group_f<NT, 1>(a, st);
+    case 2: return launch_tqc_group_f<NT, 2>(a, st);
+    default: return launch_tqc_group_f<NT, 3>(a, st);
+  }
+}
+
 static int launch_tqc(const TqcArgs& a, cudaStream_t st) {
+  // the sort network holds n_z - n_drop < capacity kept targets plus +inf padding
+  int need = a.n_atoms > a.n_z ? a.n_atoms : a.n_z;
+  if (a.n_z - a.n_drop + 1 > need) need = a.n_z - a.n_drop + 1;
+  if (need <= 128 && !g_tqc_warp_kernel) {
+    if (need <= 32) return launch_tqc_group<32>(a, st);
+    if (need <= 64) return launch_tqc_group<64>(a, st);
+    return launch_tqc_group<128>(a, st);
+  }
   int64_t blocks = (a.M + kTqcWarps - 1) / kTqcWarps;
   const int64_t max_blocks = (int64_t)num_sms() * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  // the sort network holds n_z - n_drop < 32*VPL kept targets plus +inf padding; atoms ride VPL per lane
-  int need = a.n_atoms > a.n_z ? a.n_atoms : a.n_z;
-  if (a.n_z - a.n_drop + 1 > need) need = a.n_z - a.n_drop + 1;
   if (need <= 32) tqc_loss_kernel<1><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
   else if (need <= 64) tqc_loss_kernel<2><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
   else if (need <= 128) tqc_loss_kernel<4><<<(unsigned)blocks, kTqcWarps * 32, 0, st>>>(a);
@@ -443,6 +861,12 @@ static int launch_tqc(const TqcArgs& a, cudaStream_t st) {
 using namespace fdql;
 
 extern "C" {
+
+int fdql_debug_tqc_warp_kernel(int on) {
+  const int old = g_tqc_warp_kernel;
+  g_tqc_warp_kernel = on;
+  return old;
+}
 
 int fdql_tqc_loss(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_z, const float* q_pred,
                   const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,

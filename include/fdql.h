@@ -142,6 +142,10 @@ int fdql_sample_gather(const fdql_arena* a, int64_t n_windows, int32_t T, int64_
  * warp-per-window kernels instead of the tile kernel */
 int fdql_debug_force_generic_gather(int on);
 
+/* test hook (returns the previous setting): 1 routes the TQC / quantile-Huber losses through the warp-per-transition kernel
+ * that serves more than 128 atoms instead of the quad kernel (4 lanes per transition) */
+int fdql_debug_tqc_warp_kernel(int on);
+
 /* DistributionalSoftActorCritic.q_loss from the MLP outputs onward + quantile_huber_loss_f, forward and backward
  * (franQ/Agent/components/distributional_soft_actor_critic.py:50-58,70,76-82,90-103): pool+sort the n_atoms target
  * atoms, keep the n_atoms-n_drop smallest, y = reward + mask*gamma*(z + alpha*(-log_pi)), quantile-Huber against
