@@ -2,6 +2,7 @@
 // Replaces franQ/Replay/replay_memory.py:18-46 (ring), franQ/Replay/wrappers/nstep_return.py:36-72 (return-to-go at
 // episode flush) and franQ/Replay/wrappers/her.py:55-95 (hindsight copy) -- see include/fdql.h for the contract.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "goal_eval.cuh"
@@ -368,6 +369,8 @@ int fdql_arena_destroy(fdql_arena* a) {
   if (a->step_sync_ready) {
     for (int i = 0; i < 3; ++i) cudaStreamDestroy(a->step_streams[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(a->step_events[i]);
+    for (int i = 0; i < a->n_slice_events; ++i) cudaEventDestroy(a->slice_events[i]);
+    free(a->slice_events);
   }
   delete a;
   return FDQL_OK;

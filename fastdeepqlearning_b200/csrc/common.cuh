@@ -153,6 +153,8 @@ struct Arena {
   size_t step_bytes;
   cudaStream_t step_streams[3];
   cudaEvent_t step_events[8];
+  cudaEvent_t* slice_events;  // two per slice of fdql_hotpath_step_host (copies landed, kernels done), grown on demand
+  int n_slice_events;
   int step_sync_ready;
   int num_sms;
 };

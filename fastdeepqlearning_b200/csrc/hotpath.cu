@@ -1,8 +1,11 @@
 // Host-buffer form of one whole pass of the hot path (include/fdql.h: fdql_hotpath_step_host): what a caller that
 // owns no device memory binds.  Index/goal streams and the critics' outputs come from (pinned) host memory, the
 // gathered + relabelled batch stays in HBM for the device-side MLPs, loss and dloss/dq_pred go back to host memory.
-// The batch is cut into slices that travel on three internal streams so that the H2D copy of slice i+1, the
-// kernels of slice i and the D2H copy of slice i-1 overlap; the caller's stream is joined on both ends.
+// The batch is cut into slices; one internal stream carries every H2D copy back to back, a second one the kernels and
+// a third one the D2H copies, chained per slice by events, so that the H2D copy of slice i+1, the kernels of slice i and
+// the D2H copy of slice i-1 overlap and the upstream copy engine never idles; the caller's stream is joined on both ends.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace fdql;
@@ -72,36 +75,62 @@ int fdql_hotpath_step_host(fdql_arena* a, int64_t n, int32_t T, int64_t len, con
   if (n >= 16384) slice = 8192;
   else if (n >= 4096) slice = (n + 1) / 2;
   const int64_t n_slices = (n + slice - 1) / slice;
+  if (2 * n_slices > a->n_slice_events) {
+    cudaEvent_t* ev = static_cast<cudaEvent_t*>(realloc(a->slice_events, sizeof(cudaEvent_t) * 2 * n_slices));
+    FDQL_REQUIRE(ev != nullptr, "out of host memory");
+    a->slice_events = ev;
+    for (int64_t i = a->n_slice_events; i < 2 * n_slices; ++i) {
+      FDQL_CUDA(cudaEventCreateWithFlags(&a->slice_events[i], cudaEventDisableTiming));
+      a->n_slice_events = (int)i + 1;
+    }
+  }
+  cudaStream_t s_in = a->step_streams[0], s_run = a->step_streams[1], s_out = a->step_streams[2];
   FDQL_CUDA(cudaEventRecord(a->step_events[0], user));
   for (int i = 0; i < 3; ++i) FDQL_CUDA(cudaStreamWaitEvent(a->step_streams[i], a->step_events[0], 0));
+  // the small per-window streams travel whole and first (a handful of copies instead of four per slice): the gathers can then
+  // run ahead of the critic outputs, which make up 98% of the upstream bytes
+  FDQL_CUDA(cudaMemcpyAsync(d_starts, starts_host, (size_t)n * 8, cudaMemcpyHostToDevice, s_in));
+  if (relabel) {
+    FDQL_CUDA(cudaMemcpyAsync(d_flags, flags_host, (size_t)n, cudaMemcpyHostToDevice, s_in));
+    FDQL_CUDA(cudaMemcpyAsync(d_goal, goal_rows_host, (size_t)n * 8, cudaMemcpyHostToDevice, s_in));
+  }
+  if (next_log_pi_host) FDQL_CUDA(cudaMemcpyAsync(d_lp, next_log_pi_host, (size_t)M * 4, cudaMemcpyHostToDevice, s_in));
   for (int64_t c = 0; c < n_slices; ++c) {
-    cudaStream_t st = a->step_streams[c % 3];
     const int64_t b0 = c * slice, b1 = (b0 + slice < n) ? b0 + slice : n, nb = b1 - b0;
-    FDQL_CUDA(cudaMemcpyAsync(d_starts + b0, starts_host + b0, nb * 8, cudaMemcpyHostToDevice, st));
-    if (relabel) {
-      FDQL_CUDA(cudaMemcpyAsync(d_flags + b0, flags_host + b0, nb, cudaMemcpyHostToDevice, st));
-      FDQL_CUDA(cudaMemcpyAsync(d_goal + b0, goal_rows_host + b0, nb * 8, cudaMemcpyHostToDevice, st));
+    cudaEvent_t landed = a->slice_events[2 * c], done = a->slice_events[2 * c + 1];
+    // ---- upstream: critic outputs of this slice ----
+    for (int t = 0; t + 1 < T; ++t) {
+      const int64_t m0 = (int64_t)t * n + b0;
+      FDQL_CUDA(cudaMemcpyAsync(d_z + m0 * n_atoms, next_z_host + m0 * n_atoms, (size_t)nb * n_atoms * 4, cudaMemcpyHostToDevice, s_in));
+      FDQL_CUDA(cudaMemcpyAsync(d_q + m0 * n_atoms, q_pred_host + m0 * n_atoms, (size_t)nb * n_atoms * 4, cudaMemcpyHostToDevice, s_in));
     }
+    FDQL_CUDA(cudaEventRecord(landed, s_in));
+    // ---- kernels ----
+    FDQL_CUDA(cudaStreamWaitEvent(s_run, landed, 0));
     int rc = launch_gather(a, n, b0, b1, T, len, d_starts, relabel ? d_flags : nullptr, relabel ? d_goal : nullptr, reward_op,
                            reward_params_host, n_params, gamma, opts | FDQL_OPT_EMIT_LEARNER_AUX, (int32_t)n, out, d_mask,
-                           d_contig, d_weight, st);
+                           d_contig, d_weight, s_run);
     if (rc) return rc;
     for (int t = 0; t + 1 < T; ++t) {
       const int64_t m0 = (int64_t)t * n + b0;
-      FDQL_CUDA(cudaMemcpyAsync(d_z + m0 * n_atoms, next_z_host + m0 * n_atoms, (size_t)nb * n_atoms * 4, cudaMemcpyHostToDevice, st));
-      FDQL_CUDA(cudaMemcpyAsync(d_q + m0 * n_atoms, q_pred_host + m0 * n_atoms, (size_t)nb * n_atoms * 4, cudaMemcpyHostToDevice, st));
-      if (next_log_pi_host) FDQL_CUDA(cudaMemcpyAsync(d_lp + m0, next_log_pi_host + m0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
       // the target reads reward / mask / mc_return of the NEXT row (t+1), quirk Q10
       rc = fdql_tqc_loss(nb, n_atoms, n_drop, d_z + m0 * n_atoms, d_q + m0 * n_atoms, next_log_pi_host ? d_lp + m0 : nullptr,
                          o_reward + m0 + n, d_mask + m0 + n, o_ret ? o_ret + m0 + n : nullptr, d_weight + m0, alpha, (float)gamma,
-                         d_loss + m0, grad_q_host ? d_grad + m0 * n_atoms : nullptr, nullptr, nullptr, st);
+                         d_loss + m0, grad_q_host ? d_grad + m0 * n_atoms : nullptr, nullptr, nullptr, s_run);
       if (rc) return rc;
-      FDQL_CUDA(cudaMemcpyAsync(loss_host + m0, d_loss + m0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    }
+    FDQL_CUDA(cudaEventRecord(done, s_run));
+    // ---- downstream: loss and dloss/dq of this slice ----
+    FDQL_CUDA(cudaStreamWaitEvent(s_out, done, 0));
+    for (int t = 0; t + 1 < T; ++t) {
+      const int64_t m0 = (int64_t)t * n + b0;
+      FDQL_CUDA(cudaMemcpyAsync(loss_host + m0, d_loss + m0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s_out));
       if (grad_q_host)
-        FDQL_CUDA(cudaMemcpyAsync(grad_q_host + m0 * n_atoms, d_grad + m0 * n_atoms, (size_t)nb * n_atoms * 4, cudaMemcpyDeviceToHost, st));
+        FDQL_CUDA(cudaMemcpyAsync(grad_q_host + m0 * n_atoms, d_grad + m0 * n_atoms, (size_t)nb * n_atoms * 4, cudaMemcpyDeviceToHost, s_out));
     }
   }
-  for (int i = 0; i < 3; ++i) {
+  // every kernel precedes the last event of s_run, every upstream copy precedes a kernel: joining s_run and s_out is enough
+  for (int i = 1; i < 3; ++i) {
     FDQL_CUDA(cudaEventRecord(a->step_events[1 + i], a->step_streams[i]));
     FDQL_CUDA(cudaStreamWaitEvent(user, a->step_events[1 + i], 0));
   }
