@@ -13,15 +13,20 @@ def make(conf, **kwargs):
               for _ in range(conf.num_instances)]
     write_heads = read_heads = shards
     her_mode = getattr(conf, "her_mode", "final")
-    if her_mode == "vmap":
-        raise NotImplementedError("her_mode='vmap' (franQ/Replay/wrappers/her_vmap.py) is not part of this path yet; "
-                                  "use 'final', 'random', or the sample-time 'future' relabelling")
     if conf.use_nStep_lowerbounds:
-        write_heads = [wrappers.NStepReturn(r, conf.nStep_return_steps, conf.gamma) for r in write_heads]
+        if her_mode == "vmap":  # Replay/__init__.py:21-23; quirk Q7 is opt-in (conf.vmap_reference_done_quirk)
+            write_heads = [wrappers.NStepReturnVmap(r, conf.nStep_return_steps, conf.gamma,
+                                                    reference_done_quirk=getattr(conf, "vmap_reference_done_quirk", False))
+                           for r in write_heads]
+        else:
+            write_heads = [wrappers.NStepReturn(r, conf.nStep_return_steps, conf.gamma) for r in write_heads]
     if getattr(conf, "use_squashed_rewards", False) and not conf.use_HER:
         write_heads = [wrappers.SquashRewards(r) for r in write_heads]
     if conf.use_HER:
-        if her_mode == "future":  # sample-time relabelling (BASELINE.json configs[2]); rows are stored once
+        if her_mode == "vmap":  # Replay/__init__.py:30-32
+            write_heads = [wrappers.HindsightVmapWrite(r, kwargs["compute_reward"]) for r in write_heads]
+            read_heads = [wrappers.HindsightVmapRead(r) for r in read_heads]
+        elif her_mode == "future":  # sample-time relabelling (BASELINE.json configs[2]); rows are stored once
             for r in shards:
                 r.replay.set_reward_op(kwargs["compute_reward"], conf.gamma)
             read_heads = [wrappers.SampleTimeHindsight(r, relabel_prob=getattr(conf, "her_relabel_prob", 0.8)) for r in read_heads]

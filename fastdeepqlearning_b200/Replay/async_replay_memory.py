@@ -38,6 +38,10 @@ class AsyncReplayMemory:
         self._count(sum(int(x) for x in lens))
         return self.replay.add_hindsight_rows(src_begins, lens, goal_rows, **kw)
 
+    def add_vmap_rows(self, cols, L, picks):
+        self._count(L)
+        return self.replay.add_vmap_rows(cols, L, picks)
+
     def reserve_rows(self, n):
         self._count(n)
         return self.replay.reserve_rows(n)

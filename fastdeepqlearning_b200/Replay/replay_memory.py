@@ -180,6 +180,13 @@ class ReplayMemory:
                                  with_returns=with_returns, gamma=gamma)
         return begin
 
+    def add_vmap_rows(self, cols, L, picks):
+        """HindsightVmapWrite without an NStepReturnVmap underneath (use_nStep_lowerbounds=False): no virtual_mc_return key."""
+        begin = self.add_rows(cols, episode_lengths=[L])
+        rows = (begin + np.asarray(picks, dtype=np.int64)) % self._maxlen
+        self.vmap_flush([begin], [L], pick_rows=rows, fill=True, returns=False)
+        return begin
+
     def add_hindsight_rows(self, src_begins, lens, goal_rows, with_returns=True, gamma=None):
         """Write-time hindsight copy of whole episodes (her.py:55-95): reserves sum(lens) rows at the cursor and fills
         them on the device.  Returns the first destination row of each copy."""
@@ -203,6 +210,66 @@ class ReplayMemory:
                                                 float(self.gamma if gamma is None else gamma), int(bool(with_returns)),
                                                 _stream_ptr(self.device)))
         return dst
+
+    # ------------------------------------------------------------------ "vmap" hindsight variant (her_vmap.py, nstep_return_vmap.py)
+    VMAP_KEYS = ("virtual_goals", "virtual_rewards", "virtual_dones", "virtual_mc_return")
+
+    def _vmap_key_ids(self):
+        ids = [self._keys.index(k) if k in self._keys else -1 for k in self.VMAP_KEYS]
+        if min(ids[:3]) < 0:
+            raise KeyError("the ring has no virtual_goals / virtual_rewards / virtual_dones keys (write with HindsightVmapWrite)")
+        return ids
+
+    def vmap_flush(self, begins, lens, pick_rows=None, fill=True, returns=False, gamma=None, done_quirk=False):
+        """Fill the virtual columns of whole episodes already in the ring: goals / rewards / dones from `pick_rows`
+        ([n_eps, V] ring rows whose achieved_goal become the virtual goals; her_vmap.py:66-88) and / or the per-column
+        return-to-go (nstep_return_vmap.py:37-48,61-74; `done_quirk` reproduces the reference's `* dones[i]`, quirk Q7)."""
+        self.flush()
+        kg, kr, kd, kret = self._vmap_key_ids()
+        b = torch.as_tensor(begins, dtype=torch.int64).to(self.device).contiguous()
+        l = torch.as_tensor(lens).to(device=self.device, dtype=torch.int32).contiguous()
+        picks = None
+        if fill:
+            if self.reward_op is None:
+                raise ValueError("set_reward_op first")
+            picks = torch.as_tensor(np.asarray(pick_rows, dtype=np.int64)).to(self.device).contiguous()
+            V = self._widths[kr] - 1
+            if picks.numel() != b.numel() * V:
+                raise ValueError(f"pick_rows must hold {V} rows per episode")
+        op = self.reward_op or RewardOp(L.REWARD_NONE)
+        params, n_params = op.c_params()
+        check(self._lib.fdql_vmap_flush_episodes(self._h, int(b.numel()), C.c_void_p(b.data_ptr()), C.c_void_p(l.data_ptr()),
+                                                 C.c_void_p(picks.data_ptr()) if picks is not None else None, kg, kr, kd,
+                                                 kret if returns else -1, op.op, params, n_params,
+                                                 float(self.gamma if gamma is None else gamma), (1 if fill else 0) | (2 if returns else 0),
+                                                 int(bool(done_quirk)), _stream_ptr(self.device)))
+
+    def vmap_temporal_sample(self, column, starts=None, aux=False, n=None, length=None):
+        """HindsightVmapRead.temporal_sample (her_vmap.py:104-123): the window batch with desired_goal / reward / task_done /
+        mc_return taken from virtual column `column` and the virtual keys removed.  Only that column is read from HBM."""
+        _len = len(self) if length is None else int(length)
+        Tn = self._temporal_len
+        if starts is None:
+            starts, _, _ = self.draw_streams(self._batch_size if n is None else int(n), Tn)
+        starts = self._to_dev_i64(starts)
+        res = self.temporal_sample(starts=starts, length=_len, exclude_keys=self.VMAP_KEYS)
+        kg, kr, kd, kret = self._vmap_key_ids()
+        nw = starts.numel()
+        if kret >= 0 and "mc_return" not in res:
+            res["mc_return"] = torch.empty((Tn, nw, 1), dtype=torch.float32, device=self.device)
+        aux_t = [None, None, None]
+        if aux:
+            aux_t = [torch.empty((Tn, nw, 1), dtype=torch.float32, device=self.device),
+                     torch.empty((Tn - 1, nw, 1), dtype=torch.float32, device=self.device),
+                     torch.empty((Tn - 1, nw, 1), dtype=torch.float32, device=self.device)]
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(self._lib.fdql_vmap_select_column(self._h, nw, Tn, _len, C.c_void_p(starts.data_ptr()), int(column), kg, kr, kd, kret, nw,
+                                                ptr(res.get("desired_goal")), ptr(res.get("reward")), ptr(res.get("task_done")),
+                                                ptr(res.get("mc_return")) if kret >= 0 else None, *[ptr(t) for t in aux_t],
+                                                _stream_ptr(self.device)))
+        if aux:
+            res["mask"], res["is_contiguous"], res["loss_weight"] = aux_t
+        return res
 
     def ensure_schema(self, cols):
         """Allocate the arena from a column dict if no row has been added yet (replay_memory.py:23-35)."""
@@ -252,11 +319,12 @@ class ReplayMemory:
         self.flush()
         return self._meta(0).view(torch.int32).reshape(-1), self._meta(1).view(torch.int32).reshape(-1)
 
-    def _outputs(self, lead: tuple, reuse: bool):
-        key = lead
+    def _outputs(self, lead: tuple, reuse: bool, exclude: tuple = ()):
+        key = lead + exclude
         if reuse and key in self._out_cache:
             return self._out_cache[key]
-        out = {k: torch.empty(lead + (w,), dtype=torch.float32, device=self.device) for k, w in zip(self._keys, self._widths)}
+        out = {k: torch.empty(lead + (w,), dtype=torch.float32, device=self.device) for k, w in zip(self._keys, self._widths)
+               if k not in exclude}
         if reuse:
             self._out_cache[key] = out
         return out
@@ -316,7 +384,7 @@ class ReplayMemory:
         return self[idx]
 
     def temporal_sample(self, starts=None, flags=None, goal_rows=None, exact_episode_step=False, aux=False,
-                        reuse_outputs=False, n=None, relabel_prob=0.0, goal_mode=None, length=None):
+                        reuse_outputs=False, n=None, relabel_prob=0.0, goal_mode=None, length=None, exclude_keys=()):
         """[T, B, w] window gather (replay_memory.py:54-66).  `starts` (and for hindsight relabelling `flags`,
         `goal_rows`) inject the index streams; when absent they are drawn on the device.  With `aux=True` the dict
         also carries `mask`, `is_contiguous` and `loss_weight` (deepQlearning.py:201-203,222-225)."""
@@ -335,7 +403,7 @@ class ReplayMemory:
             goal_rows = self._to_dev_i64(goal_rows)
             if self.reward_op is None:
                 raise ValueError("relabelling needs set_reward_op(...)")
-        out = self._outputs((Tn, n), reuse=reuse_outputs)
+        out = self._outputs((Tn, n), reuse=reuse_outputs, exclude=tuple(exclude_keys))
         opts = (L.OPT_EXACT_EPISODE_STEP if exact_episode_step else 0) | (L.OPT_EMIT_LEARNER_AUX if aux else 0)
         aux_t = [None, None, None]
         if aux:
@@ -355,7 +423,7 @@ class ReplayMemory:
             C.c_void_p(flags.data_ptr()) if flags is not None else None,
             C.c_void_p(goal_rows.data_ptr()) if flags is not None else None,
             op.op if flags is not None else L.REWARD_NONE, params, n_params, float(self.gamma), opts, n,
-            L.ptr_array([out[k].data_ptr() for k in self._keys]),
+            L.ptr_array([out[k].data_ptr() if k in out else 0 for k in self._keys]),
             *[C.c_void_p(t.data_ptr()) if t is not None else None for t in aux_t], _stream_ptr(self.device)))
         res = dict(out)
         if aux:

@@ -75,3 +75,56 @@ class NStepReturn(ReplayMemoryWrapper):
                 self.replay_buffer.q3_duplicate(int(dst[0]), self.n_step, dup, self.discount)
             out.append(int(dst[0]))
         return out
+
+
+class NStepReturnVmap(ReplayMemoryWrapper):
+    """Mirror of franQ/Replay/wrappers/nstep_return_vmap.py:8-74: the per-column return-to-go `virtual_mc_return [V+1]` of rows
+    that carry `virtual_rewards` / `virtual_dones`, computed on the device at episode end (fdql_vmap_flush_episodes, mode 2).
+
+    quirk Q7: the reference's recurrence multiplies by `dones[i]` (nstep_return_vmap.py:74), so its returns accumulate only
+    ACROSS virtual terminals.  `reference_done_quirk=True` reproduces that arithmetic bit for bit; the default multiplies by
+    `1 - dones[i]` (the return stops at a virtual terminal), which is what a lower bound on Q needs."""
+
+    def __init__(self, replay_buffer, n_step, discount, reward_name="virtual_rewards", task_done_name="virtual_dones",
+                 return_name="virtual_mc_return", done_name="episode_done", reference_done_quirk=False):
+        ReplayMemoryWrapper.__init__(self, replay_buffer)
+        if (reward_name, task_done_name, return_name, done_name) != ("virtual_rewards", "virtual_dones", "virtual_mc_return",
+                                                                     "episode_done"):
+            raise NotImplementedError("the device path binds the virtual columns by the reference's default key names")
+        self.n_step, self.discount, self.reference_done_quirk = n_step, discount, bool(reference_done_quirk)
+        self.reward_name, self.task_done_name, self.return_name, self.done_name = reward_name, task_done_name, return_name, done_name
+        self._reset()
+
+    def _reset(self):
+        self.rows = []
+
+    def _check_len(self, L):
+        if L > self.n_step:
+            raise NotImplementedError("vmap mode: episodes longer than nStep_return_steps (the reference's _pop duplicate, "
+                                      "nstep_return_vmap.py:50-57) are not supported")
+
+    def add(self, experience):
+        """Rows that already carry virtual_rewards / virtual_dones (nstep_return_vmap.py:23-35)."""
+        self.rows.append(dict(experience))
+        if experience[self.done_name]:
+            rows = self.rows
+            self._reset()
+            L = len(rows)
+            self._check_len(L)
+            cols = stack_rows(rows)
+            cols[self.return_name] = np.zeros_like(cols[self.reward_name])
+            begin = self.replay_buffer.add_rows(cols, episode_lengths=[L])
+            self.replay_buffer.vmap_flush([begin], [L], fill=False, returns=True, gamma=self.discount,
+                                          done_quirk=self.reference_done_quirk)
+
+    def add_vmap_rows(self, cols, L, picks):
+        """Episode-batched protocol used by HindsightVmapWrite: goals / rewards / dones and the returns in one device pass."""
+        import torch
+        self._check_len(L)
+        cols = dict(cols)
+        cols[self.return_name] = torch.zeros_like(cols[self.reward_name])
+        begin = self.replay_buffer.add_rows(cols, episode_lengths=[L])
+        rows = (begin + np.asarray(picks, dtype=np.int64)) % self._maxlen
+        self.replay_buffer.vmap_flush([begin], [L], pick_rows=rows, fill=True, returns=True, gamma=self.discount,
+                                      done_quirk=self.reference_done_quirk)
+        return begin

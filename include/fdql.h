@@ -113,6 +113,32 @@ int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row);
  * recurrence over the rewards of rows src_row .. src_row+n_step-1. */
 int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t dst_row, double gamma, void* stream);
 
+/* ---- "vmap" hindsight variant (her_mode="vmap"): V virtual goals per row instead of one relabelled copy -------------------
+ * The virtual columns are ordinary keys of the arena, named by their key index: virtual_goals [V+1, G] (flattened),
+ * virtual_rewards [V+1], virtual_dones [V+1], virtual_mc_return [V+1] (key_returns = -1: absent); column V is the real goal.
+ *
+ * fdql_vmap_flush_episodes: for n_eps complete episodes already in the ring,
+ *   mode bit 0  HindsightVmapWrite._hindsight_flush + _virtual_episode_calc (franQ/Replay/wrappers/her_vmap.py:30-43,66-88):
+ *               virtual goal v of episode e := achieved_goal[pick_rows[e*V + v]] (the reference draws the picks with
+ *               np.random.randint(0, L, V), :75), virtual_reward = (reward - R(ag, dg)) + R(ag, vg) in float32,
+ *               virtual_done = (task_done and not done(R(ag, dg))) or done(R(ag, vg));
+ *   mode bit 1  NStepReturnVmap._flush + _inner (franQ/Replay/wrappers/nstep_return_vmap.py:37-48,61-74): per column the
+ *               recurrence G_j = fl32(r_j + G_{j+1} * gamma * m_j) in fp64, newest row first; done_quirk != 0 uses
+ *               m_j = dones[j] exactly as the reference does (quirk Q7), 0 uses m_j = 1 - dones[j]. */
+int fdql_vmap_flush_episodes(fdql_arena* a, int32_t n_eps, const int64_t* ep_begin, const int32_t* ep_len, const int64_t* pick_rows,
+                             int32_t key_goals, int32_t key_rewards, int32_t key_dones, int32_t key_returns, int32_t reward_op,
+                             const float* reward_params_host, int32_t n_params, double gamma, int32_t mode, int32_t done_quirk,
+                             void* stream);
+
+/* HindsightVmapRead.temporal_sample (franQ/Replay/wrappers/her_vmap.py:104-123) for windows (starts[b]+t) % len, t<T:
+ * desired_goal [T,n,G] := virtual_goals[..., column, :], reward / task_done / mc_return [T,n,1] := the same column of
+ * virtual_rewards / virtual_dones / virtual_mc_return.  Only the chosen column is read.  Outputs and aux may be NULL;
+ * aux (mask [T,n,1], is_contiguous [T-1,n,1], loss weight [T-1,n,1]) follows the selected dones (deepQlearning.py:201-203,222-225). */
+int fdql_vmap_select_column(const fdql_arena* a, int64_t n_windows, int32_t T, int64_t len, const int64_t* starts, int32_t column,
+                            int32_t key_goals, int32_t key_rewards, int32_t key_dones, int32_t key_returns, int32_t batch_for_weight,
+                            float* out_desired_goal, float* out_reward, float* out_task_done, float* out_mc_return, float* aux_mask,
+                            float* aux_contig, float* aux_weight, void* stream);
+
 /* np.random.randint(0, len-T, B) (replay_memory.py:59) + HER goal choice (her.py:48-53), drawn on the device with a
  * counter-based generator.  Parity runs inject the streams instead.  flags[b]=1 with probability relabel_prob.
  * counter_dev (may be NULL): two uint64 in device memory {draw counter, 0}; when given, the draw uses counter + *counter_dev and

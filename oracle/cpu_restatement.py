@@ -272,6 +272,70 @@ class HindsightOracle:
             self.sink.add(out)
 
 
+# ----------------------------------------------------------------------------------------------
+# "vmap" hindsight variant  (franQ/Replay/wrappers/her_vmap.py, nstep_return_vmap.py)
+# ----------------------------------------------------------------------------------------------
+def vmap_virtual_columns(achieved_goal, desired_goal, reward, task_done, virtual_goals, reward_fn):
+    """``_virtual_episode_calc`` (her_vmap.py:30-43) for one episode, chronological rows.
+
+    virtual_reward[t, v] = fl32(fl32(reward_t - R(ag_t, dg_t)) + R(ag_t, vg_v))                          (:34,39)
+    virtual_done[t, v]   = (task_done_t and not done(R(ag_t, dg_t))) or done(R(ag_t, vg_v))              (:37,40)
+    Returns ([L, V+1] float32, [L, V+1] bool, [L, V+1, G]) with the real goal / reward / done appended as column V (:85-87)."""
+    ag, dg = np.asarray(achieved_goal), np.asarray(desired_goal)
+    vg = np.asarray(virtual_goals)
+    L, V = ag.shape[0], vg.shape[0]
+    r = np.asarray(reward, np.float32).reshape(L)
+    d = np.asarray(task_done).astype(bool).reshape(L)
+    Rd, dd = reward_fn(ag, dg)
+    ga_r = (r - np.asarray(Rd, np.float32)).astype(np.float32)
+    ga_d = d & ~np.asarray(dd).astype(bool)
+    vr = np.zeros((L, V + 1), np.float32)
+    vd = np.zeros((L, V + 1), bool)
+    goals = np.zeros((L, V + 1) + ag.shape[1:], np.float64)
+    for v in range(V):
+        Rv, dv = reward_fn(ag, np.broadcast_to(vg[v], ag.shape))
+        vr[:, v] = (ga_r + np.asarray(Rv, np.float32)).astype(np.float32)
+        vd[:, v] = ga_d | np.asarray(dv).astype(bool)
+        goals[:, v] = vg[v]
+    vr[:, V], vd[:, V], goals[:, V] = r, d, dg
+    return vr, vd, goals
+
+
+def vmap_returns(virtual_rewards, virtual_dones, gamma, reference_done_quirk=True):
+    """``calculate_montecarlo_return`` / ``_inner`` of nstep_return_vmap.py:61-74 for one episode, chronological [L, V+1]:
+    G_t = fl32(r_t + G_{t+1} * gamma * m_t) evaluated in fp64, m_t = dones[t] as the reference has it (quirk Q7) or
+    1 - dones[t] (``reference_done_quirk=False``: the return stops at a virtual terminal)."""
+    r = np.asarray(virtual_rewards, np.float32).copy()
+    d = np.asarray(virtual_dones).astype(bool)
+    m = d if reference_done_quirk else ~d
+    for t in range(r.shape[0] - 2, -1, -1):
+        r[t] = (r[t].astype(np.float64) + r[t + 1].astype(np.float64) * float(gamma) * m[t]).astype(np.float32)
+    return r
+
+
+def vmap_write_episode(cols, picks_chrono, reward_fn, gamma=None, reference_done_quirk=True):
+    """HindsightVmapWrite._hindsight_flush (+ NStepReturnVmap._flush when gamma is given) for one episode given as
+    chronological columns; ``picks_chrono`` are the rows whose achieved_goal become the virtual goals (her_vmap.py:75)."""
+    vg = np.asarray(cols["achieved_goal"])[np.asarray(picks_chrono)]
+    vr, vd, goals = vmap_virtual_columns(cols["achieved_goal"], cols["desired_goal"], cols["reward"], cols["task_done"], vg, reward_fn)
+    out = {k: np.asarray(v) for k, v in cols.items()}
+    out["virtual_goals"], out["virtual_rewards"], out["virtual_dones"] = goals, vr, vd
+    if gamma is not None:
+        out["virtual_mc_return"] = vmap_returns(vr, vd, gamma, reference_done_quirk)
+    return out
+
+
+def vmap_read_select(batch, column):
+    """HindsightVmapRead.temporal_sample + cleanup (her_vmap.py:104-123) on a gathered [T, B, ...] batch."""
+    out = {k: v for k, v in batch.items() if not k.startswith("virtual_")}
+    out["desired_goal"] = batch["virtual_goals"][:, :, column]
+    out["reward"] = batch["virtual_rewards"][:, :, column, None]
+    out["task_done"] = batch["virtual_dones"][:, :, column, None]
+    if "virtual_mc_return" in batch:
+        out["mc_return"] = batch["virtual_mc_return"][:, :, column, None]
+    return out
+
+
 def pohlen_transform(x, epsilon=1e-2, power=0.5):
     """franQ/Replay/wrappers/squash_rewards.py:5-7."""
     x = np.asarray(x, np.float64)

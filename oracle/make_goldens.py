@@ -212,6 +212,76 @@ def golden_her(ref):
     np.savez_compressed(os.path.join(GOLDEN, "her.npz"), **out)
 
 
+def _run_her_vmap(ref, reward_fn, episodes, picks, gamma, goal_dtype, V, with_returns):
+    """The reference's vmap write chain HindsightVmapWrite -> NStepReturnVmap -> ReplayMemory (Replay/__init__.py:21-23,30-31),
+    executed with the numpy stand-in for jax.vmap (oracle/ref_loader.py); goal picks injected through np.random.randint."""
+    mem = ref.ReplayMemory(4096, 8, 2)
+    inner = ref.NStepReturnVmap(mem, 1000, gamma) if with_returns else mem
+    her = ref.HindsightVmapWrite(inner, reward_fn, num_virtual_goals=V)
+    pick_iter = iter(picks)
+    real_randint = np.random.randint
+
+    def injected_randint(low, high=None, size=None, **kw):  # her_vmap.py:75 indexes the newest-first deque
+        p = np.asarray(next(pick_iter))
+        assert p.shape == (size,) and p.min() >= low and p.max() < high
+        return p
+
+    np.random.randint = injected_randint
+    try:
+        for ep in episodes:
+            L = len(ep["reward"])
+            for t in range(L):
+                her.add({"obs_1d": ep["obs"][t], "action": ep["action"][t],
+                         "achieved_goal": ep["ag"][t].astype(goal_dtype), "desired_goal": ep["dg"][t].astype(goal_dtype),
+                         "reward": float(ep["reward"][t]), "task_done": bool(ep["task_done"][t]),
+                         "episode_done": t == L - 1, "episode_step": t, "info": {}})
+    finally:
+        np.random.randint = real_randint
+    n = len(mem)
+    return mem, {k: np.asarray(v[:n]).copy() for k, v in mem.memory.items()}
+
+
+def golden_her_vmap(ref):
+    """her_vmap.py / nstep_return_vmap.py: stored rows of the write chain and what the read head returns for every column."""
+    out = {}
+    rng = np.random.default_rng(11)
+    V = 5
+    # episodes of a single row are left out: the reference's calculate_montecarlo_return squeezes [1, V+1] rewards to [V+1],
+    # walks the goal columns as if they were time steps and then fails with an IndexError (nstep_return_vmap.py:62-66,43-44)
+    cases = [("bitflip", bitflip_reward, [e for e in _bitflip_episodes(rng, 20, 3, 12) if len(e["reward"]) > 1], np.int64),
+             ("all_geq", all_geq_reward, _float_goal_episodes(rng, 10, 2, 10), np.float64)]
+    for name, fn, eps, gdt in cases:
+        # deque index (newest first) of every virtual goal, as np.random.randint(0, L, V) would return it
+        picks = [rng.integers(0, len(e["reward"]), V) for e in eps]
+        out[f"{name}_n_eps"] = len(eps)
+        out[f"{name}_picks_deque"] = np.concatenate(picks)
+        out[f"{name}_lengths"] = np.array([len(e["reward"]) for e in eps])
+        for k in ("obs", "action", "ag", "dg", "reward", "task_done"):
+            out[f"{name}_in_{k}"] = np.concatenate([e[k] for e in eps])
+        for tag, with_returns in (("ret", True), ("noret", False)):
+            mem, stored = _run_her_vmap(ref, fn, eps, picks, 0.98, gdt, V, with_returns)
+            for k, v in stored.items():
+                out[f"{name}_{tag}_{k}"] = v.astype(np.float64) if v.dtype == bool else v
+            if with_returns:  # read head: inject the window starts and the column (random.randint(0, V), her_vmap.py:107)
+                read = ref.HindsightVmapRead(mem)
+                starts = rng.integers(0, len(mem) - 2, 8)
+                out[f"{name}_read_starts"] = starts
+                real_ts, real_ri = mem.temporal_sample, random.randint
+                mem.temporal_sample = lambda: mem._temporal_sample_idxes(starts, len(mem))
+                try:
+                    for col in range(V + 1):
+                        random.randint = lambda a, b, _c=col: _c
+                        got = read.temporal_sample()
+                        assert "virtual_goals" not in got
+                        for k, v in got.items():
+                            out[f"{name}_read{col}_{k}"] = np.asarray(v).astype(np.float64)
+                finally:
+                    mem.temporal_sample, random.randint = real_ts, real_ri
+    out["gamma"] = 0.98
+    out["V"] = V
+    np.savez_compressed(os.path.join(GOLDEN, "her_vmap.npz"), **out)
+
+
 class _Fixed(torch.nn.Module):
     def __init__(self, value):
         super().__init__()
@@ -397,6 +467,7 @@ def main():
             golden_ring(ref)
             golden_nstep(ref)
             golden_her(ref)
+            golden_her_vmap(ref)
             golden_tqc(ref)
             golden_get_losses(ref)
         finally:

@@ -194,3 +194,56 @@ def test_sample_time_relabel_equals_write_time_rows():
             np.testing.assert_array_equal(out[k][0], g[f"{name}_random_{k}"][hs].astype(np.float32), err_msg=k)
         np.testing.assert_allclose(out["reward"][0], g[f"{name}_random_reward"][hs], rtol=1e-6)
         np.testing.assert_allclose(out["mc_return"][0], g[f"{name}_random_mc_return"][hs], rtol=1e-6, atol=1e-7)
+
+
+def _vmap_case(g, name):
+    lengths = g[f"{name}_lengths"]
+    V = int(g["V"])
+    picks_deque = g[f"{name}_picks_deque"].reshape(len(lengths), V)
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    return lengths, V, picks_deque, offs
+
+
+@pytest.mark.parametrize("name,fn", [("bitflip", O.reward_bitflip), ("all_geq", O.reward_all_geq)])
+def test_vmap_write_chain_matches_reference(name, fn):
+    """HindsightVmapWrite -> NStepReturnVmap -> ReplayMemory of the reference (executed with a numpy stand-in for jax.vmap,
+    oracle/ref_loader.py) vs the restatement: stored virtual goals / rewards / dones / returns, bit for bit."""
+    g = load_golden("her_vmap")
+    lengths, V, picks_deque, offs = _vmap_case(g, name)
+    for e, L in enumerate(lengths):
+        sl = slice(offs[e], offs[e + 1])
+        cols = {"achieved_goal": g[f"{name}_in_ag"][sl], "desired_goal": g[f"{name}_in_dg"][sl],
+                "reward": g[f"{name}_in_reward"][sl], "task_done": g[f"{name}_in_task_done"][sl]}
+        picks = L - 1 - picks_deque[e]  # deque index (newest first) -> chronological row
+        got = O.vmap_write_episode(cols, picks, fn, gamma=float(g["gamma"]), reference_done_quirk=True)
+        for tag in ("ret", "noret"):
+            np.testing.assert_array_equal(got["virtual_goals"], g[f"{name}_{tag}_virtual_goals"][sl])
+            np.testing.assert_array_equal(got["virtual_rewards"], g[f"{name}_{tag}_virtual_rewards"][sl])
+            np.testing.assert_array_equal(got["virtual_dones"], g[f"{name}_{tag}_virtual_dones"][sl])
+        np.testing.assert_array_equal(got["virtual_mc_return"], g[f"{name}_ret_virtual_mc_return"][sl])
+        assert f"{name}_noret_virtual_mc_return" not in g.files
+        # the stored real rows are untouched
+        np.testing.assert_array_equal(g[f"{name}_ret_reward"][sl].reshape(-1), np.float32(cols["reward"]))
+
+
+@pytest.mark.parametrize("name", ["bitflip", "all_geq"])
+def test_vmap_read_head_matches_reference(name):
+    g = load_golden("her_vmap")
+    V = int(g["V"])
+    stored = {k[len(name) + 5:]: g[k] for k in g.files if k.startswith(f"{name}_ret_")}
+    starts = g[f"{name}_read_starts"]
+    idx = np.arange(2)[:, None] + starts[None, :]
+    batch = {k: v[idx] for k, v in stored.items()}
+    for col in range(V + 1):
+        got = O.vmap_read_select(batch, col)
+        want = {k[len(f"{name}_read{col}_"):]: g[k] for k in g.files if k.startswith(f"{name}_read{col}_")}
+        assert set(got) == set(want)
+        for k in want:
+            np.testing.assert_array_equal(np.asarray(got[k], np.float64), want[k], err_msg=k)
+
+
+def test_vmap_returns_sane_mode_stops_at_virtual_terminals():
+    r = np.array([[1.0], [2.0], [3.0]], np.float32)
+    d = np.array([[0], [1], [0]], bool)
+    np.testing.assert_allclose(O.vmap_returns(r, d, 0.5, reference_done_quirk=False).reshape(-1), [2.0, 2.0, 3.0])
+    np.testing.assert_allclose(O.vmap_returns(r, d, 0.5, reference_done_quirk=True).reshape(-1), [1.0, 3.5, 3.0])
