@@ -393,9 +393,13 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()
     kernels = {
-        "sample_streams_kernel": {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS},
-        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + BYTES_RELABEL},
-        "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC},
+        "sample_streams_kernel": {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS, "symbol": "fdql::sample_streams_kernel"},
+        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + BYTES_RELABEL,
+                                 "symbol": "fdql::sample_gather_tile_kernel<1, true>",
+                                 "limiter": "HBM latency on random 32-256 B segments (ncu r1: long-scoreboard stalls dominate, DRAM traffic = algorithmic bytes)"},
+        "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC, "symbol": "fdql::tqc_loss_group_kernel<128, 3>",
+                            "limiter": "instruction issue (72% active, ALU pipe 61%) and shared-memory wavefronts (72% of peak): 128-value sort "
+                                       "network + 375 seven-level searches per transition; not HBM (ncu r1, profiles/r1_ncu_summary.md)"},
     }
     for kd in kernels.values():
         kd["achieved_gbs"] = kd["bytes_per_transition"] * M / (kd["ms"] * 1e-3) / 1e9

@@ -19,7 +19,15 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
         "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
-        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct"]
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
 ik = hdr.index("Kernel Name")
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0, "second": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}
 out, traffic = [f"# ncu --set full summary ({tag}); source report: {os.path.basename(rep)} (scratch, not tracked)\n"], {}
@@ -37,7 +45,7 @@ for r in data:
                 pass
     if "dram__bytes_read.sum" in vals:
         tot = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-        key = "sample_gather_kernel" if "sample_gather" in name else name.split("<")[0]
+        key = "sample_gather_kernel" if "sample_gather" in name else "tqc_loss_kernel" if "tqc_loss" in name else name.split("<")[0]
         traffic[key] = tot
         dur = vals.get("gpu__time_duration.sum")
         out.append(f"| dram bytes read+write per launch | {tot:.4g} | byte |")
