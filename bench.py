@@ -44,7 +44,8 @@ ROW_BYTES = 4 * (OBS + ACT + 2 * GOAL) + 4 * 5  # 436 B, SURVEY.md section 8(d)
 #      the bytes THIS algorithm needs, and `survey_bytes_per_transition` reports the SURVEY figure beside it.)
 #   D TQC: next_z + q_pred + grad_q (3 x 4*125) + 4 scalars in + loss out   = 1500 + 20       = 1520
 BYTES_GATHER = 4 * ROW_BYTES + 8
-BYTES_RELABEL = P_RELABEL * ((4 * GOAL + 25) + 16 * (LEP + 1) / 2)
+BYTES_RELABEL_SCAN = P_RELABEL * ((4 * GOAL + 25) + 16 * (LEP + 1) / 2)  # --tail-scan: 16 B scan record per tail row
+BYTES_RELABEL = P_RELABEL * ((4 * GOAL + 25) + 16 * T)  # goal row + its link record + streams + one link record per window row
 BYTES_RELABEL_SURVEY = P_RELABEL * ((4 * GOAL + 5) + 72 * (LEP + 1) / 2)
 BYTES_TQC = 3 * 4 * CQ + 20
 BYTES_STREAMS = 32 + 17  # read the start row's record sector, write start/flag/goal
@@ -65,6 +66,7 @@ def parse():
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--no-updates", action="store_true")
     ap.add_argument("--exact-episode-step", action="store_true")
+    ap.add_argument("--tail-scan", action="store_true", help="relabelled returns by scanning the episode tail instead of the link records")
     return ap.parse_args()
 
 
@@ -186,6 +188,9 @@ def run_ours(args):
     stats = torch.zeros(4, dtype=torch.float64, device=device)
     params, n_params = ring.reward_op.c_params()
     opts = L.OPT_EMIT_LEARNER_AUX | (L.OPT_EXACT_EPISODE_STEP if args.exact_episode_step else 0)
+    if args.tail_scan:
+        lib.fdql_debug_force_generic_gather(16)  # tile kernel without the link records
+    bytes_relabel = BYTES_RELABEL_SCAN if args.tail_scan else BYTES_RELABEL
     stream = torch.cuda.current_stream(device)
     sp = C.c_void_p(stream.cuda_stream)
     p = lambda t: C.c_void_p(t.data_ptr())
@@ -394,9 +399,11 @@ def run_ours(args):
     peak, peak_src = peaks()
     kernels = {
         "sample_streams_kernel": {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS, "symbol": "fdql::sample_streams_kernel"},
-        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + BYTES_RELABEL,
+        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + bytes_relabel,
                                  "symbol": "fdql::sample_gather_tile_kernel<1, true>",
-                                 "limiter": "HBM latency on random 32-256 B segments (ncu r1: long-scoreboard stalls dominate, DRAM traffic = algorithmic bytes)"},
+                                 "limiter": "HBM latency on random 32-256 B segments (ncu r1: long-scoreboard stalls dominate, DRAM traffic = algorithmic bytes)",
+                                 "relabelled_returns": "tail scan (16 B per tail row)" if args.tail_scan else
+                                 "link records: chain of equal achieved goals + goal-agnostic return, O(hits) per window"},
         "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC, "symbol": "fdql::tqc_loss_group_kernel<128, 3>",
                             "limiter": "instruction issue (72% active, ALU pipe 61%) and shared-memory wavefronts (72% of peak): 128-value sort "
                                        "network + 375 seven-level searches per transition; not HBM (ncu r1, profiles/r1_ncu_summary.md)"},
@@ -423,7 +430,7 @@ def run_ours(args):
     line = {"metric": "sampled+relabelled+targeted transitions/s", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
-            "config": {"workload": "HER(future,k=4: relabel p=0.8, full-episode-tail return recompute) + TQC 5x25 drop 10 + "
+            "config": {"workload": "HER(future,k=4: relabel p=0.8, return-to-go recomputed over the whole episode tail) + TQC 5x25 drop 10 + "
                                    "n-step lower bound; obs64/act8/goal16; ring %d rows/GPU (L=128 episodes); batch 4096, T=2"
                                    % (len(ring) + 1),
                        "batch": B, "temporal_len": T, "batches_per_step": D, "transitions_per_step_per_gpu": M,

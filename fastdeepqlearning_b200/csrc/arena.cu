@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) append_kernel(ArenaDev A, SrcPtrs src, in
       *reinterpret_cast<float4*>(rec + c0) = make_float4(t[0], t[1], t[2], t[3]);
     }
     A.scan[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+    A.link[row] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -102,6 +103,52 @@ __device__ __forceinline__ float exact_return_chunk(float r, int jb, int L, doub
     if (lane == i) mine = acc;
   }
   return mine;
+}
+
+// -------------------------------------------------------------------------------------------------
+// link records of one episode (common.cuh), one warp; the scan records of the episode must be written and visible.
+// -------------------------------------------------------------------------------------------------
+__device__ void build_link_records(const ArenaDev& A, int64_t s, int L, double gamma) {
+  const int lane = lane_id();
+  // goal-agnostic return-to-go: GA_j = (ga_j - 1) + gamma * GA_{j+1}, walked from the last row in fp64
+  double acc = 0.0;
+  for (int jb = ((L - 1) / 32) * 32; jb >= 0; jb -= 32) {
+    const int j = jb + lane;
+    const bool valid = j < L;
+    const int64_t row = ring_row(s, valid ? j : 0, A.capacity);
+    const float ga = valid ? A.scan[row].z : 0.f;
+    double mine = 0.0;
+    for (int i = 31; i >= 0; --i) {
+      const float gi = __shfl_sync(kFull, ga, i);
+      if (jb + i < L) acc = ((double)gi - 1.0) + acc * gamma;
+      if (lane == i) mine = acc;
+    }
+    if (valid) A.link[row] = make_float4((float)mine, ga, 0.f, 0.f);
+  }
+  __syncwarp();
+  // chain of bit-identical achieved goals: lane <-> row j looks for the nearest later row with the same hash, verified
+  const bool chain_ok = L <= 32767;
+  for (int jb = 0; jb < L; jb += 32) {
+    const int j = jb + lane;
+    if (j >= L) continue;
+    const int64_t row = ring_row(s, j, A.capacity);
+    const float4 me = A.scan[row];
+    const bool nan = (__float_as_uint(me.w) & 1u) != 0u;
+    int next = 0;
+    if (chain_ok && !nan) {
+      for (int k = j + 1; k < L; ++k) {
+        const int64_t rk = ring_row(s, k, A.capacity);
+        const float4 o = __ldg(A.scan + rk);
+        if (__float_as_uint(o.x) == __float_as_uint(me.x) && __float_as_uint(o.y) == __float_as_uint(me.y) &&
+            rows_equal(A, row, rk)) {
+          next = k - j;
+          reinterpret_cast<int*>(A.link + rk)[3] = next;  // the successor's distance back to this row
+          break;
+        }
+      }
+    }
+    reinterpret_cast<int*>(A.link + row)[2] = next | (nan ? (1 << 30) : 0) | (chain_ok ? 0 : (int)0x80000000);
+  }
 }
 
 template <int LPR>
@@ -147,6 +194,10 @@ commit_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ ep_begin, c
       const float g = exact_return_chunk(r, jb, L, gamma, acc, first);
       if (valid) rec[A.col_mc_return] = g;
     }
+  }
+  if (A.wide_ag >= 0) {
+    __syncwarp();  // the scan records of the whole episode are in place
+    build_link_records(A, s, L, gamma);
   }
 }
 
@@ -209,6 +260,7 @@ her_flush_kernel(ArenaDev A, int32_t n_eps, const int64_t* __restrict__ src_begi
       rd[A.col_ep_end] = __int_as_float((int)dend);
       A.scan[drow] = make_float4(__uint_as_float((uint32_t)h), __uint_as_float((uint32_t)(h >> 32)), ga,
                                  __uint_as_float(has_nan ? 1u : 0u));
+      A.link[drow] = A.link[srow];  // same achieved goals and goal-agnostic rewards: same chain (distances) and GA
     }
     if (bal) seg_first = jb + 32 - __clz(bal);
   }
@@ -244,7 +296,10 @@ __global__ void __launch_bounds__(32) q3_duplicate_kernel(ArenaDev A, int64_t sr
     if (c == A.col_ep_start || c == A.col_ep_end) v = __int_as_float(-1);  // a lone row: never relabelled at sample time
     A.rec[dst * (int64_t)A.rec_stride + c] = v;
   }
-  if (lane == 0) A.scan[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane == 0) {
+    A.scan[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+    A.link[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (A.col_mc_return < 0 || A.col_reward < 0) return;
   float acc = 0.f, g0 = 0.f;
   bool first = true;
@@ -343,6 +398,7 @@ int fdql_arena_create(int64_t capacity, int32_t n_keys, const int32_t* widths, c
   for (int s = 0; s < D.n_wide && ok; ++s) ok = alloc(&D.wide[s].base, (size_t)capacity * D.wide[s].stride);
   ok = ok && alloc(&D.rec, (size_t)capacity * D.rec_stride);
   ok = ok && alloc(reinterpret_cast<float**>(&D.scan), (size_t)capacity * 4);
+  ok = ok && alloc(reinterpret_cast<float**>(&D.link), (size_t)capacity * 4);
   ok = ok && alloc(&a->reward_params_dev, kMaxRewardParams + 4);
   if (!ok) {
     set_error("cudaMalloc failed while allocating the arena (%zu bytes so far): %s", total,
@@ -363,6 +419,7 @@ int fdql_arena_destroy(fdql_arena* a) {
     if (a->dev.wide[s].base) cudaFree(a->dev.wide[s].base);
   if (a->dev.rec) cudaFree(a->dev.rec);
   if (a->dev.scan) cudaFree(a->dev.scan);
+  if (a->dev.link) cudaFree(a->dev.link);
   if (a->reward_params_dev) cudaFree(a->reward_params_dev);
   if (a->stage_dev) cudaFree(a->stage_dev);
   if (a->step_dev) cudaFree(a->step_dev);
@@ -509,6 +566,12 @@ int fdql_commit_episodes(fdql_arena* a, int32_t n_eps, const int64_t* ep_begin, 
     lpr = lanes_per_row(a->dev.wide[a->dev.wide_ag].vecs);
   }
   const unsigned blocks = (unsigned)(((int64_t)n_eps * 32 + 255) / 256);
+  if (a->link_state == 0) {
+    a->link_gamma = gamma;
+    a->link_state = 1;
+  } else if (a->link_state == 1 && a->link_gamma != gamma) {
+    a->link_state = 2;  // mixed discounts: sample-time relabelling falls back to the tail scan
+  }
   FDQL_DISPATCH_LPR(lpr, (commit_kernel<LPR><<<blocks, 256, 0, (cudaStream_t)stream>>>(a->dev, n_eps, ep_begin, ep_len, gamma,
                                                                                          with_returns, rs)));
   FDQL_CUDA(cudaGetLastError());

@@ -41,6 +41,15 @@ void set_error(const char* fmt, ...);
 //   .w     bit 0: the achieved_goal holds a NaN (never equal to anything)
 // Episode scans read it as one contiguous run of 16 B per row; for equality rewards the hash decides "differs" exactly
 // and only hash matches are verified against the full vectors.
+// link: [capacity] 16-byte link record per row, written with the scan record (equality rewards only need THIS at sample time):
+//   .x  goal-agnostic return-to-go  GA_j = sum_{m>=j} gamma^(m-j) (ga_m - 1)  over the rest of the real episode (fp64 sum, fp32 store)
+//   .y  the goal-agnostic reward ga_j again (so that a window row needs one record, not two)
+//   .z  int: bits 0-14 distance to the NEXT row of the episode with a bit-identical achieved_goal (0 = none; verified on the full
+//            vectors when the chain is built), bit 30: the row's achieved_goal holds a NaN (equal to nothing), bit 31: no chain
+//            (episode longer than 32767 rows)
+//   .w  int: distance to the PREVIOUS such row (0 = none)
+// Under an equality reward R(ag, g*) = 0 iff ag == g*, so the rows that hit a hindsight goal g* = achieved_goal[goal_row] are exactly
+// the chain through goal_row, and the relabelled return is GA_t + sum_{hits m >= t} gamma^(m-t): O(hits) instead of O(tail).
 struct WideSlab {
   float* base;
   int32_t stride;  // floats, multiple of 4
@@ -55,6 +64,7 @@ struct ArenaDev {
   WideSlab wide[FDQL_MAX_KEYS];
   float* rec;
   float4* scan;
+  float4* link;
   int32_t scal_key[FDQL_MAX_KEYS];  // record column -> caller's key index
   int32_t col_ep_start, col_ep_end;
   int32_t col_reward, col_task_done, col_ep_done, col_ep_step, col_mc_return;  // record column or -1
@@ -156,6 +166,8 @@ struct Arena {
   cudaEvent_t* slice_events;  // two per slice of fdql_hotpath_step_host (copies landed, kernels done), grown on demand
   int n_slice_events;
   int step_sync_ready;
+  double link_gamma;    // discount the link records were built with
+  int link_state;       // 0: none yet, 1: link_gamma valid, 2: episodes were committed with different discounts (links unusable)
   int num_sms;
 };
 

@@ -103,6 +103,8 @@ struct GatherArgs {
   float* aux_contig;
   float* aux_weight;
   int32_t tile;  // tile kernel: windows per block iteration (32..256)
+  int32_t use_link;  // tile kernel, equality rewards: link records are valid for this gamma -> O(hits) relabelled returns
+  double log2_gamma, inv_gamma;
 };
 
 __device__ __forceinline__ double warp_suffix_scan(double v, double g, int lane) {
@@ -895,7 +897,52 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
         }
         return m;
       };
-      if (HASH && relabel) {
+      // ---- link path (common.cuh): the rows that hit g* are the chain of bit-identical achieved goals through the goal row, so
+      // the relabelled return of window row t is GA_t + sum_{hits m >= t} gamma^(m-t); nothing is read from the rest of the tail
+      bool linked = false;
+      uint32_t inwin = 0;  // bit t: window row t hits the goal
+      double W = 0.0;      // sum over the hits m >= 0 (relative to the window start) of gamma^m
+      int seg_first = -1;  // first row of the synthetic episode the window starts in, episode-relative (exact mode)
+      int j0 = 0;
+      if (HASH && relabel) j0 = s - ep_first + (s < ep_first ? cap32 : 0);
+      if (HASH && relabel && g.use_link) {
+        const int jg = grow - ep_first + (grow < ep_first ? cap32 : 0);
+        const float4 lg = __ldg(A.link + grow);
+        const int pk = __float_as_int(lg.z);
+        if (pk >= 0 && jg <= j0 + tail_last) {  // a chain exists and the goal row belongs to this episode
+          linked = true;
+          int near_before = -0x40000000;
+          if (((pk >> 30) & 1) == 0) {  // a goal holding a NaN is hit by nothing, not even by its own row
+            auto visit = [&](int m) {
+              if (m >= 0) {
+                W += exp2((double)m * g.log2_gamma);
+                if (m < T) inwin |= 1u << m;
+              } else {
+                near_before = max(near_before, m);
+              }
+            };
+            const int mg = jg - j0;
+            visit(mg);
+            if (mg >= 0) {  // towards the window start; the first hit before it ends the walk
+              int cur = mg, d = __float_as_int(lg.w);
+              while (d > 0) {
+                cur -= d;
+                visit(cur);
+                if (cur < 0) break;
+                d = __float_as_int(__ldg(A.link + ring_row32(ep_first, j0 + cur, cap32)).w);
+              }
+            }
+            int cur = mg, d = pk & 0x7fff;
+            while (d > 0) {  // towards the episode end
+              cur += d;
+              visit(cur);
+              d = __float_as_int(__ldg(A.link + ring_row32(ep_first, j0 + cur, cap32)).z) & 0x7fff;
+            }
+          }
+          if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) seg_first = near_before < 0 && near_before > -0x40000000 ? j0 + near_before + 1 : 0;
+        }
+      }
+      if (HASH && relabel && !linked) {
         gsc = __ldg(A.scan + grow);
         gd = grow - s + (grow < s ? cap32 : 0);
         // return-to-go over the whole real episode with relabelled rewards (quirk Q5), newest row first, each step in fp64
@@ -918,12 +965,7 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
             if (j < T && o_ret != nullptr) st_stream1(o_ret + (int64_t)j * g.n + b, acc);
           }
         }
-      }
-      // first row of the synthetic episode the window starts in (exact mode scans the episode prefix, her.py:72-83)
-      int seg_first = -1;
-      int j0 = 0;
-      if (HASH && relabel) {
-        j0 = s - ep_first + (s < ep_first ? cap32 : 0);
+        // first row of the synthetic episode the window starts in (exact mode scans the episode prefix, her.py:72-83)
         if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
           seg_first = 0;
           for (int j = j0 - 1; j >= 0; --j) {
@@ -941,6 +983,7 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
           }
         }
       }
+      double gp = 1.0, gi = 1.0, Wsub = 0.0;  // gamma^t, gamma^-t, hits before window row t
       // forward over the window rows: scalar keys (with the hindsight overrides) and the learner aux
       float prev_step = 0.f, prev_mask = 0.f, csum = 0.f;
       for (int t = 0; t < T; ++t) {
@@ -951,9 +994,20 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
         float v_done = A.col_task_done >= 0 ? __ldg(rec + A.col_task_done) : 0.f;
         float v_rew = 0.f;
         if (in_ep) {
-          const float4 r = __ldg(A.scan + ring_row32(s, t, cap32));
-          const bool m = matches(t, r);
-          v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
+          bool m;
+          if (linked) {
+            const float4 lt = __ldg(A.link + ring_row32(s, t, cap32));
+            m = ((inwin >> t) & 1u) != 0u;
+            v_rew = (float)((double)lt.y + (m ? 0.0 : -1.0));
+            if (o_ret != nullptr) st_stream1(o_ret + (int64_t)t * g.n + b, (float)((double)lt.x + gi * (W - Wsub)));
+            if (m) Wsub += gp;
+            gp *= g.gamma;
+            gi *= g.inv_gamma;
+          } else {
+            const float4 r = __ldg(A.scan + ring_row32(s, t, cap32));
+            m = matches(t, r);
+            v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
+          }
           v_done = m ? 1.f : 0.f;
           if (seg_first >= 0 && A.col_ep_step >= 0)
             v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + A.col_ep_step);
@@ -1113,6 +1167,11 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     while (tile_w > 64 && (b_end - b_begin + tile_w - 1) / tile_w < (int64_t)a->num_sms * 3) tile_w >>= 1;
     if (g_tile_override) tile_w = g_tile_override;
     g.tile = tile_w;
+    // link records (chain of equal achieved goals + goal-agnostic return) serve equality rewards when they were built with this
+    // discount and the window fits the 32-bit hit mask; otherwise the kernel scans the episode tail
+    g.use_link = hash_ok && a->link_state == 1 && a->link_gamma == gamma && gamma > 0.0 && T <= 32 && !(g_force_generic_gather & 16);
+    g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
+    g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
     int64_t tiles = (b_end - b_begin + tile_w - 1) / tile_w;
 #define FDQL_LAUNCH_TILE(SV, HASHV)                                                                              \
   do {                                                                                                           \
@@ -1217,8 +1276,8 @@ extern "C" {
 int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
   g_tile_override = (on >> 8) & 0x1ff;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
-  g_force_generic_gather = on & 13;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
-                                     // bit 3: warp-per-window kernels instead of the tile kernel
+  g_force_generic_gather = on & 29;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
+                                     // bit 3: warp-per-window kernels instead of the tile kernel, bit 4: tile kernel without link records
   g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }

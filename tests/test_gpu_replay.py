@@ -374,13 +374,15 @@ def test_warp_per_window_kernels(R, fdql, T, G, max_len):
         lib.fdql_debug_force_generic_gather(old)
 
 
+@pytest.mark.parametrize("links", [True, False])
 @pytest.mark.parametrize("tile", [32, 256])
-@pytest.mark.parametrize("T,G,max_len", [(1, 16, 40), (2, 16, 130), (5, 3, 70), (50, 64, 200), (2, 100, 33)])
-def test_tile_kernel_on_small_batches(R, fdql, tile, T, G, max_len):
-    """Batches below ~48K windows take the warp-per-window kernels; force the tile kernel (thread-per-window scalar phase, exact
-    return recurrence, warp-per-window wide-key phase) on the small parity cases, with partial and full tiles."""
+@pytest.mark.parametrize("T,G,max_len", [(1, 16, 40), (2, 16, 130), (5, 3, 70), (50, 64, 200), (2, 100, 33), (32, 8, 90)])
+def test_tile_kernel_on_small_batches(R, fdql, tile, T, G, max_len, links):
+    """Batches below ~48K windows take the warp-per-window kernels; force the tile kernel (thread-per-window scalar phase,
+    warp-per-window wide-key phase) on the small parity cases, with partial and full tiles, with the link records (chain of equal
+    achieved goals + goal-agnostic return: O(hits) relabelled returns) and with the tail scan (exact return recurrence)."""
     lib = fdql.lib()
-    old = lib.fdql_debug_force_generic_gather(tile << 8)
+    old = lib.fdql_debug_force_generic_gather((tile << 8) | (0 if links else 16))
     try:
         test_sample_time_relabel_vs_oracle(R, fdql, T, G, max_len)
         test_hash_scan_verifies_matches_and_nans(R, fdql)
