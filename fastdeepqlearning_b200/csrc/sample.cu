@@ -1158,18 +1158,20 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   for (int w = 0; w < a->dev.n_wide; ++w) wide_vecs += a->dev.wide[w].vecs;
   const int wslots = (wide_vecs + 31) / 32;
   const bool hash_ok = relabel && reward_op == FDQL_REWARD_BITFLIP && !g_force_full_vector_relabel;
-  // small launches are latency-bound and run faster with one warp per window (measured: 4096 windows 20 us vs 29 us);
+  // small tail-scanning launches are latency-bound and run faster with one warp per window (measured: 4096 windows 20 us vs 29 us);
   // from ~48K windows on, the tile kernel's lower instruction count wins (262144 windows: 209 us vs 261 us)
-  const bool big = (b_end - b_begin) >= 49152 || g_tile_override != 0;
+  // link records (chain of equal achieved goals + goal-agnostic return) serve equality rewards when they were built with this
+  // discount and the window fits the 32-bit hit mask; otherwise the kernels scan the episode tail
+  const bool link_ok = hash_ok && a->link_state == 1 && a->link_gamma == gamma && gamma > 0.0 && T <= 32 && !(g_force_generic_gather & 16);
+  // with link records the tile kernel has no tail loop and wins from ~1K windows on (measured 4096 windows: 14.7 us vs 19.5 us per call)
+  const bool big = (b_end - b_begin) >= 49152 || (link_ok && (b_end - b_begin) >= 1024) || g_tile_override != 0;
   if (wslots <= 4 && (!relabel || hash_ok) && big && !(g_force_generic_gather & (1 | 8))) {
     // tile size: 256 windows when there is enough work to fill the machine, down to 32 for small batches
     int tile_w = kTileWindows;
     while (tile_w > 64 && (b_end - b_begin + tile_w - 1) / tile_w < (int64_t)a->num_sms * 3) tile_w >>= 1;
     if (g_tile_override) tile_w = g_tile_override;
     g.tile = tile_w;
-    // link records (chain of equal achieved goals + goal-agnostic return) serve equality rewards when they were built with this
-    // discount and the window fits the 32-bit hit mask; otherwise the kernel scans the episode tail
-    g.use_link = hash_ok && a->link_state == 1 && a->link_gamma == gamma && gamma > 0.0 && T <= 32 && !(g_force_generic_gather & 16);
+    g.use_link = link_ok;
     g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
     g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
     int64_t tiles = (b_end - b_begin + tile_w - 1) / tile_w;
