@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--no-updates", action="store_true")
     ap.add_argument("--exact-episode-step", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="learner step launched eagerly instead of as one CUDA graph")
     ap.add_argument("--tail-scan", action="store_true", help="relabelled returns by scanning the episode tail instead of the link records")
     return ap.parse_args()
 
@@ -370,7 +371,7 @@ def run_ours(args):
         lconf = Agent.LearnerConf(training_device=str(device), obs_space={"obs_1d": OBS, "achieved_goal": GOAL, "desired_goal": GOAL},
                                   action_space=types.SimpleNamespace(shape=(ACT,)), num_critics=C_CRIT, num_q_predictions=Q_ATOMS,
                                   top_quantiles_to_drop=N_DROP / CQ + 1e-9, batch_size=B, temporal_len=T, gamma=GAMMA,
-                                  use_cuda_graph=(world == 1))
+                                  use_cuda_graph=not args.no_graph, graph_allreduce=True)
         learner = Agent.Learner(lconf, [SampleTimeHindsight(ring, relabel_prob=P_RELABEL)])
         for _ in range(5):
             learner.train_step()
@@ -393,7 +394,7 @@ def run_ours(args):
                    "params": int(sum(p.numel() for p in learner.params)), "loss": float(last),
                    "cuda_graph": bool(lconf.use_cuda_graph),
                    "note": "policy/critic MLPs are ordinary PyTorch fp32 modules; sample/relabel/target/loss are this repo's CUDA kernels; "
-                           "at N=1 the whole step (kernels + MLP fwd/bwd + Adam + target update) is one captured CUDA graph"}
+                           "the whole step (kernels + MLP fwd/bwd + gradient all-reduce + Adam + target update) is one captured CUDA graph"}
 
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()
@@ -452,9 +453,21 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(args, steps=3, warmup=1, quiet=True)["cpu_baseline"]
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist:
+        # NCCL kernels captured in the learner's CUDA graph must go before the communicator does; a watchdog ends the process
+        # if the teardown still blocks (the JSON line is out by then)
+        import gc
+        import threading
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        if not args.no_updates:
+            learner.close()
+        learner = None  # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize(device)
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

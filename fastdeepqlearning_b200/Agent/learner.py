@@ -58,6 +58,13 @@ class Learner:
         self._flat = None
         self.last_summaries = {}
 
+    def close(self):
+        """Drop the captured step graphs.  Call before torch.distributed.destroy_process_group(): a CUDA graph that captured the
+        gradient all-reduce keeps NCCL work alive and can block the communicator's teardown."""
+        self._graphs.clear()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def enable_training(self, replays):
         """deepQlearning.py:64-71,96-103: register the read heads (already device loaders)."""
         self.replays = list(replays)
