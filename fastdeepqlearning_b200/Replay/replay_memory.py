@@ -289,6 +289,48 @@ class ReplayMemory:
         """quirk Q3: the oldest row of an episode longer than n_step, stored once more with the n-step-truncated return."""
         check(self._lib.fdql_q3_duplicate(self._h, int(src_row), int(n_step), int(dst_row), float(gamma), _stream_ptr(self.device)))
 
+    # ------------------------------------------------------------------ snapshot / restore (the reference never persists its replay;
+    # its dormant analogue is memmap_replay_memory.py).  Every slab is saved raw -- user keys, episode extents, scan and link
+    # records -- so the restored ring answers any call bit for bit, stale (partly overwritten) episodes included.
+    def _meta_rows(self, which):
+        base, stride, col = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(self._lib.fdql_arena_meta_view(self._h, which, C.byref(base), C.byref(stride), C.byref(col)))
+        return torch.as_tensor(_DevView(base.value, (self._maxlen, 4), (4 * stride.value, 4)), device=self.device)
+
+    def state_dict(self):
+        self.flush()
+        es, ee = self.episode_extents()
+        gam, st = C.c_double(), C.c_int32()
+        check(self._lib.fdql_arena_link_state(self._h, 0, C.byref(gam), C.byref(st)))
+        return {"maxlen": self._maxlen, "keys": list(self._keys), "widths": list(self._widths), "shapes": dict(self._shapes),
+                "top": self._top, "len": self._curr_len, "gamma": self.gamma, "link": (gam.value, st.value),
+                "reward_op": None if self.reward_op is None else (self.reward_op.op, list(self.reward_op.params or [])),
+                "memory": {k: v.cpu().clone() for k, v in self.memory.items()}, "ep_start": es.cpu().clone(), "ep_end": ee.cpu().clone(),
+                "scan": self._meta_rows(2).view(torch.int32).cpu().clone(), "links": self._meta_rows(3).view(torch.int32).cpu().clone()}
+
+    def load_state_dict(self, sd):
+        if self._h is not None:
+            raise RuntimeError("load_state_dict needs a fresh ReplayMemory")
+        if int(sd["maxlen"]) != self._maxlen:
+            raise ValueError(f"snapshot of a ring of {sd['maxlen']} rows, this one has {self._maxlen}")
+        self._jit_initialize(dict(zip(sd["keys"], sd["widths"])), sd["shapes"])
+        self.gamma = float(sd["gamma"])
+        if sd["reward_op"] is not None:
+            self.reward_op = RewardOp(sd["reward_op"][0], sd["reward_op"][1] or ())
+        dev = [sd["memory"][k].to(self.device, dtype=torch.float32).reshape(self._maxlen, w).contiguous()
+               for k, w in zip(self._keys, self._widths)]
+        check(self._lib.fdql_arena_append(self._h, self._maxlen, L.ptr_array([t.data_ptr() for t in dev]), _stream_ptr(self.device)))
+        check(self._lib.fdql_arena_set_cursor(self._h, int(sd["top"]), int(sd["len"])))
+        self._top, self._curr_len = int(sd["top"]), int(sd["len"])
+        es, ee = self.episode_extents()
+        es.copy_(sd["ep_start"].to(self.device))
+        ee.copy_(sd["ep_end"].to(self.device))
+        self._meta_rows(2).view(torch.int32).copy_(sd["scan"].to(self.device))
+        self._meta_rows(3).view(torch.int32).copy_(sd["links"].to(self.device))
+        gam, st = C.c_double(float(sd["link"][0])), C.c_int32(int(sd["link"][1]))
+        check(self._lib.fdql_arena_link_state(self._h, 1, C.byref(gam), C.byref(st)))
+        torch.cuda.current_stream(self.device).synchronize()
+
     # ------------------------------------------------------------------ read side (replay_memory.py:48-70)
     def __len__(self):
         return self._curr_len

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "fdql_arena_set_cursor": (C.c_int, [_p, _i64, _i64]),
     "fdql_arena_key_view": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i32)]),
     "fdql_arena_meta_view": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i32)]),
+    "fdql_arena_link_state": (C.c_int, [_p, _i32, C.POINTER(_f64), C.POINTER(_i32)]),
     "fdql_arena_append": (C.c_int, [_p, _i64, _pp, _p]),
     "fdql_arena_append_host": (C.c_int, [_p, _i64, _pp, _p]),
     "fdql_commit_episodes": (C.c_int, [_p, _i32, _p, _p, _f64, _i32, _i32, C.POINTER(_f32), _i32, _p]),

@@ -465,12 +465,29 @@ int fdql_arena_key_view(const fdql_arena* a, int32_t key, float** base, int64_t*
   return FDQL_OK;
 }
 
+int fdql_arena_link_state(fdql_arena* a, int32_t set, double* gamma, int32_t* state) {
+  FDQL_REQUIRE(a != nullptr && gamma != nullptr && state != nullptr, "null argument");
+  if (set) {
+    FDQL_REQUIRE(*state >= 0 && *state <= 2, "bad link state");
+    a->link_gamma = *gamma;
+    a->link_state = *state;
+  } else {
+    *gamma = a->link_gamma;
+    *state = a->link_state;
+  }
+  return FDQL_OK;
+}
+
 int fdql_arena_meta_view(const fdql_arena* a, int32_t which, float** base, int64_t* row_stride, int32_t* col) {
-  FDQL_REQUIRE(a != nullptr && which >= 0 && which <= 2, "bad meta column");
+  FDQL_REQUIRE(a != nullptr && which >= 0 && which <= 3, "bad meta column");
   if (which == 2) {
     *base = reinterpret_cast<float*>(a->dev.scan);
     *row_stride = 4;
     *col = 2;
+  } else if (which == 3) {
+    *base = reinterpret_cast<float*>(a->dev.link);
+    *row_stride = 4;
+    *col = 0;
   } else {
     *base = a->dev.rec;
     *row_stride = a->dev.rec_stride;

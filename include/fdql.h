@@ -82,8 +82,12 @@ int fdql_arena_info(const fdql_arena* a, int64_t* capacity, int64_t* top, int64_
 int fdql_arena_set_cursor(fdql_arena* a, int64_t top, int64_t len);
 /* raw view of one key's storage for zero-copy host-language views: element (row, c) lives at base[row*row_stride + col + c] */
 int fdql_arena_key_view(const fdql_arena* a, int32_t key, float** base, int64_t* row_stride, int32_t* col);
-/* internal columns: which=0 ep_start(int32 bits), 1 ep_end(int32 bits) inside the scalar record; 2 goal-agnostic reward slab */
+/* internal columns: which=0 ep_start(int32 bits), 1 ep_end(int32 bits) inside the scalar record; 2 goal-agnostic reward (column 2 of
+ * the 16-byte scan records); 3 the 16-byte link records (column 0).  Used for zero-copy views and for snapshot / restore. */
 int fdql_arena_meta_view(const fdql_arena* a, int32_t which, float** base, int64_t* row_stride, int32_t* col);
+/* discount the link records were built with (state 0: none yet, 1: gamma valid, 2: mixed -> sample-time relabelling scans the tail);
+ * set != 0 writes *gamma / *state into the arena (restore of a snapshot), else reads them */
+int fdql_arena_link_state(fdql_arena* a, int32_t set, double* gamma, int32_t* state);
 
 /* ReplayMemory.add for n rows at once (replay_memory.py:38-46): src[k] is a dense [n_rows, width_k] fp32 array.
  * Rows land at top, top+1, ... modulo capacity; the cursor advances with Q1 semantics. */

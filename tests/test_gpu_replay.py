@@ -434,3 +434,35 @@ def test_wide_rows_take_the_generic_kernel(R):
     idx = np.arange(3)[:, None] + starts[None]
     np.testing.assert_array_equal(npy(out["obs"]), cols["obs"][idx])
     np.testing.assert_array_equal(npy(out["reward"]), cols["reward"][idx])
+
+
+def test_snapshot_restore_roundtrip(R, fdql):
+    """state_dict / load_state_dict: same rows, cursor and episode table; scan and link records are rebuilt on the device, so a
+    relabelled window batch drawn with the same streams is identical (incl. a wrapped ring and write-time hindsight copies)."""
+    rng = np.random.default_rng(77)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 40, 60, 8)
+    N = int(lengths.sum())
+    ring = R.ReplayMemory(N - 37, 16, 2)  # smaller than the data: the ring wraps and the oldest episodes are partly overwritten
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.98)
+    off = 0
+    for L in lengths:  # episode by episode so that extents of overwritten episodes go stale like in real use
+        ring.add_rows({k: v[off:off + L] for k, v in cols.items()}, episode_lengths=[int(L)])
+        off += L
+    sd = ring.state_dict()
+    twin = R.ReplayMemory(N - 37, 16, 2)
+    twin.load_state_dict(sd)
+    assert (twin._top, len(twin)) == (ring._top, len(ring))
+    for k in ring.keys:
+        np.testing.assert_array_equal(npy(twin.memory[k]), npy(ring.memory[k]), err_msg=k)
+    n = len(ring)
+    es, ee = (npy(x) for x in ring.episode_extents())
+    starts = rng.integers(0, n - 2, 3000)
+    ok = es[starts] >= 0
+    starts = starts[ok]
+    tail = (ee[starts] - starts) % (N - 37)
+    goal_rows = (starts + (rng.random(len(starts)) * (tail + 1)).astype(np.int64)) % (N - 37)
+    flags = (rng.random(len(starts)) < 0.8).astype(np.uint8)
+    a = ring.temporal_sample(starts=starts, flags=flags, goal_rows=goal_rows, aux=True, exact_episode_step=True)
+    b = twin.temporal_sample(starts=starts, flags=flags, goal_rows=goal_rows, aux=True, exact_episode_step=True)
+    for k in a:
+        np.testing.assert_array_equal(npy(a[k]), npy(b[k]), err_msg=k)
