@@ -348,9 +348,11 @@ struct GrpCfg {
   static constexpr int kZY = G * TP;    // floats: staged rows of next_z, later the G sorted tables (two buffers)
   static constexpr int kSc = 8;         // per-transition scalars
   // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars |
-  static constexpr int kRed = 3 * G * 33 + (4 - (3 * G * 33) % 4) % 4;  // per-lane partial sums, [3*G][33]
-  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | red |
-  static constexpr int kWarpFloats = 2 * kZY + 2 * kZY + G * NT + kSc * G + kRed;
+  static constexpr int kRedPitch = 36;  // rows of 32 per-lane partial sums, 16-byte aligned, consecutive rows 4 banks apart
+  static constexpr int kRed = 3 * G * kRedPitch;
+  static constexpr int kIn = 8 * G;     // staged per-transition inputs {reward, mask, log_pi, mc_return, grad_scale}[G], two buffers
+  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | red | in[0] | in[1] |
+  static constexpr int kWarpFloats = 2 * kZY + 2 * kZY + G * NT + kSc * G + kRed + 2 * kIn;
   static_assert(kZY % 4 == 0 && kWarpFloats % 4 == 0, "16-byte alignment of the staging buffers");
 };
 
@@ -434,16 +436,24 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 // rows [m0, m0 + rows) of a [M, width] matrix -> shared memory, asynchronously when the run is 16-byte aligned and whole
+// (MAXF = capacity of the destination in floats: the copy is unrolled into MAXF/128 predicated 16-byte cp.async per lane)
+template <int MAXF>
 __device__ __forceinline__ void grp_stage_rows(float* dst, const float* __restrict__ src, int64_t m0, int width, int rows, int full_rows,
                                                bool aligned, int lane) {
-  const float* g = src + m0 * width;
+  const float* g = src + m0 * width + lane * 4;
   const int nfl = rows * width;
   if (aligned && rows == full_rows) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-    for (int i = lane * 4; i < nfl; i += 128) cp_async16(d + 4 * i, g + i);
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + 16 * lane;
+#pragma unroll
+    for (int k = 0; k < (MAXF + 127) / 128; ++k)
+      if (lane * 4 + 128 * k < nfl) cp_async16(d + 512 * k, g + 128 * k);
   } else {
-    for (int i = lane; i < nfl; i += 32) dst[i] = ld_stream1(g + i);
+    const float* g1 = src + m0 * width;
+    for (int i = lane; i < nfl; i += 32) dst[i] = ld_stream1(g1 + i);
   }
 }
 
@@ -462,7 +472,8 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
   float2* QT = reinterpret_cast<float2*>(W + 2 * C::kZY);
   float* qs = W + 4 * C::kZY;
   float* sc = qs + G * NT;
-  float* red = sc + C::kSc * G;  // [3 * G][33]: per-lane partial sums, one row per (quantity, transition)
+  float* red = sc + C::kSc * G;  // [3 * G][kRedPitch]: per-lane partial sums, one row per (quantity, transition)
+  float* inb = red + C::kRed;    // [2][5][G] staged per-transition inputs
   const uint32_t aW = (uint32_t)__cvta_generic_to_shared(W), aQ = aW + 8 * C::kZY;
   const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
   const uint32_t one = (uint32_t)min(n, 1);  // 1, opaque to the compiler (see grp_search_steps)
@@ -489,19 +500,33 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
   const int c_src = grp * LPT + (K / 2) / E;  // lane holding a kept target near the median in slot 0
   const uint32_t physK4 = 4u * (uint32_t)((K % R) * 32 + K / R);
   const bool zal = (reinterpret_cast<uintptr_t>(a.next_z) & 15) == 0, qal = (reinterpret_cast<uintptr_t>(a.q_pred) & 15) == 0;
+  // per-transition inputs travel with next_z, one round ahead: lane l < 5*G copies array l / G of transition l % G (4-byte cp.async)
+  // (NT = 32 has G = 16: lanes take up to three slots)
+  const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
+  auto stage_inputs = [&](int b, int64_t m0) {
+#pragma unroll
+    for (int slot = lane; slot < 5 * G; slot += 32) {
+      const int which = slot / G, t = slot % G;
+      const float* src = which == 0 ? a.reward : which == 1 ? a.mask : which == 2 ? a.next_log_pi : which == 3 ? a.mc_return : a.grad_scale;
+      if (src != nullptr && m0 + t < a.M) cp_async4(aW + 4 * (uint32_t)((inb - W) + b * C::kIn + which * G + t), src + m0 + t);
+    }
+  };
 
   const int64_t n_groups = (a.M + G - 1) / G;
   const int64_t wstride = (int64_t)gridDim.x * kGrpWarps;
   int64_t gi = (int64_t)blockIdx.x * kGrpWarps + wib;
   int buf = 0;
-  if (gi < n_groups) grp_stage_rows(W, a.next_z, gi * G, nz, (int)min((int64_t)G, a.M - gi * G), G, zal, lane);
+  if (gi < n_groups) {
+    grp_stage_rows<G * NT>(W, a.next_z, gi * G, nz, (int)min((int64_t)G, a.M - gi * G), G, zal, lane);
+    stage_inputs(0, gi * G);
+  }
   cp_async_commit();
   for (; gi < n_groups; gi += wstride, buf ^= 1) {
     const int64_t m0 = gi * G;
     const int rows = (int)min((int64_t)G, a.M - m0);
     float* Zb = W + buf * C::kZY;
     const uint32_t aZb = aW + 4 * buf * C::kZY;
-    grp_stage_rows(qs, a.q_pred, m0, n, rows, G, qal, lane);
+    grp_stage_rows<G * NT>(qs, a.q_pred, m0, n, rows, G, qal, lane);
     cp_async_commit();
     cp_async_wait<1>();  // this round's next_z rows have landed
     __syncwarp();
@@ -509,7 +534,6 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
     // ================= phase A: LPT lanes per transition =================
     {
       const bool live = grp < rows;
-      const int64_t mm = live ? m0 + grp : a.M - 1;
       const float* zst = Zb + grp * nz;
       float e[E];
 #pragma unroll
@@ -519,11 +543,11 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
         if (j < nz) v = live ? zst[j] : 0.f;
         e[s] = v;
       }
-      const float rew = a.reward ? __ldg(a.reward + mm) : 0.f, msk = a.mask ? __ldg(a.mask + mm) : 1.f;
-      const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
-      const float ent = a.next_log_pi ? __fmul_rn(alpha, -__ldg(a.next_log_pi + mm)) : 0.f;
-      const float Gv = LB ? __ldg(a.mc_return + mm) : 0.f;
-      const float gs = a.grad_scale ? __ldg(a.grad_scale + mm) : 1.f;
+      const float* in = inb + buf * C::kIn + grp;
+      const float rew = (a.reward && live) ? in[0 * G] : 0.f, msk = (a.mask && live) ? in[1 * G] : 1.f;
+      const float ent = (a.next_log_pi && live) ? __fmul_rn(alpha, -in[2 * G]) : 0.f;
+      const float Gv = (LB && live) ? in[3 * G] : 0.f;
+      const float gs = (a.grad_scale && live) ? in[4 * G] : 1.f;
       const float mg = __fmul_rn(msk, a.gamma);
 
       grp_sort_from<E, NT, 2>(e, sl);  // sorted position of (sl, s) is i = sl * E + s
@@ -586,8 +610,10 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
     __syncwarp();
     {  // next round's next_z rows into the other buffer (its tables are dead)
       const int64_t gnext = gi + wstride;
-      if (gnext < n_groups)
-        grp_stage_rows(W + (buf ^ 1) * C::kZY, a.next_z, gnext * G, nz, (int)min((int64_t)G, a.M - gnext * G), G, zal, lane);
+      if (gnext < n_groups) {
+        grp_stage_rows<G * NT>(W + (buf ^ 1) * C::kZY, a.next_z, gnext * G, nz, (int)min((int64_t)G, a.M - gnext * G), G, zal, lane);
+        stage_inputs(buf ^ 1, gnext * G);
+      }
       cp_async_commit();
     }
     cp_async_wait<1>();  // this round's q_pred rows have landed
@@ -642,43 +668,38 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
           s2 = fmaf(qc, qc, s2);
         }
       }
-      red[(0 * G + t) * 33 + lane] = fmaf(acc, inv_nk, lbacc * inv_n);
+      red[(0 * G + t) * C::kRedPitch + lane] = fmaf(acc, inv_nk, lbacc * inv_n);
       if constexpr (STATS) {
-        red[(1 * G + t) * 33 + lane] = s1;
-        red[(2 * G + t) * 33 + lane] = s2;
+        red[(1 * G + t) * C::kRedPitch + lane] = s1;
+        red[(2 * G + t) * C::kRedPitch + lane] = s2;
       }
     }
     __syncwarp();
-    // per-transition sums over the lanes: lane i adds up row i of `red` (pitch 33: conflict free)
+    // per-transition sums over the lanes: the 32 / G lanes of transition t each add G columns of its rows (128-bit loads), then a
+    // log2(32 / G)-step butterfly; lane t * (32 / G) ends up with the loss, sum q and sum q^2 of transition t
+    {
+      constexpr int LB_ = 32 / G;  // lanes per transition
+      const int t = lane / LB_, part = lane % LB_;
+      float sums[NQ];
 #pragma unroll
-    for (int base = 0; base < NQ * G; base += 32) {
-      const int idx = base + lane;
-      float sum = 0.f;
-      if (idx < NQ * G) {
-        const float* rrow = red + idx * 33;
+      for (int qn = 0; qn < NQ; ++qn) {
+        const float4* rrow = reinterpret_cast<const float4*>(red + (qn * G + t) * C::kRedPitch + part * G);
+        float sacc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) sum += rrow[k];
+        for (int k = 0; k < G / 4; ++k) {
+          const float4 v = rrow[k];
+          sacc += (v.x + v.y) + (v.z + v.w);
+        }
+#pragma unroll
+        for (int d = LB_ / 2; d >= 1; d >>= 1) sacc += __shfl_xor_sync(kFull, sacc, d);
+        sums[qn] = sacc;
       }
-      const int t = idx % G, q = idx / G;
-      if (q == 0 && t < rows && a.loss && idx < NQ * G) a.loss[m0 + t] = sum;
-      if constexpr (STATS) {  // :66-67,80-82 q_pred mean, mean row variance (unbiased) from the centred moments
-        static_assert(!STATS || 3 * G <= 32 || G == 16, "layout of the summaries reduction");
-        if constexpr (3 * G <= 32) {
-          const float S1 = __shfl_sync(kFull, sum, G + (lane % G)), S2 = __shfl_sync(kFull, sum, 2 * G + (lane % G));
-          if (lane < rows) {
-            st_sum += (double)S1 + (double)n * (double)sc[lane * C::kSc + 0];
-            st_var += ((double)S2 - (double)S1 * (double)S1 * (double)inv_n) * (double)inv_nm1;
-          }
-        } else {  // G == 16: rows 0..15 loss, 16..31 sum q (first pass); 32..47 sum q^2 (second pass)
-          if (base == 0) {
-            const float S1 = __shfl_sync(kFull, sum, 16 + (lane % 16));
-            if (lane < rows) {
-              st_sum += (double)S1 + (double)n * (double)sc[lane * C::kSc + 0];
-              st_var -= (double)S1 * (double)S1 * (double)inv_n * (double)inv_nm1;
-            }
-          } else if (lane < rows) {
-            st_var += (double)sum * (double)inv_nm1;
-          }
+      if (part == 0 && t < rows) {
+        if (a.loss) a.loss[m0 + t] = sums[0];
+        if constexpr (STATS) {  // :66-67,80-82 q_pred mean, mean row variance (unbiased) from the centred moments
+          const double S1 = (double)sums[1], S2 = (double)sums[2];
+          st_sum += S1 + (double)n * (double)sc[t * C::kSc + 0];
+          st_var += (S2 - S1 * S1 * (double)inv_n) * (double)inv_nm1;
         }
       }
     }
