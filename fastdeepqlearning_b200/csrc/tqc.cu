@@ -552,28 +552,35 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
 
       grp_sort_from<E, NT, 2>(e, sl);  // sorted position of (sl, s) is i = sl * E + s
 
+      // centre: a kept target near the median.  Fetched here, before any per-slot predicate is live: a shuffle inside the loop
+      // has an out-of-line non-converged path, and ptxas would pack and unpack every live predicate around it.
+      float c0 = __shfl_sync(kFull, e[0], c_src);
+      int kkl = kk;
+      asm volatile("" : "+r"(kkl));  // keeps the `s < kk` compares below the shuffle
+
       // soft target (:50-58) in the reference's operator order; raw mode (quantile_huber_loss_f): targets as given
       if (a.reward) {
         if (a.next_log_pi) {
 #pragma unroll
           for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(e[s], ent)));
+          c0 = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(c0, ent)));
         } else {
 #pragma unroll
           for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, e[s]));
+          c0 = __fadd_rn(rew, __fmul_rn(mg, c0));
         }
       }
       if (a.td_target && live) {
 #pragma unroll
         for (int s = 0; s < E; ++s)
-          if (s < kk) a.td_target[(m0 + grp) * K + sl * E + s] = e[s];
+          if (s < kkl) a.td_target[(m0 + grp) * K + sl * E + s] = e[s];
       }
-      // centre on a kept target near the median, cut the top n_drop (+inf), this lane's sums of y and y^2.
+      // cut the top n_drop (+inf), centre, this lane's sums of y and y^2.
       // Entries at sorted index >= K hold +inf and make every later prefix non-finite; no search ever lands past K.
-      const float c0 = __shfl_sync(kFull, e[0], c_src);
       float l1 = 0.f, l2 = 0.f;
 #pragma unroll
       for (int s = 0; s < E; ++s) {
-        const float y = s < kk ? e[s] - c0 : CUDART_INF_F;
+        const float y = s < kkl ? e[s] - c0 : CUDART_INF_F;
         e[s] = y;
         l1 += y;
         l2 = fmaf(y, y, l2);
