@@ -2,8 +2,9 @@
 """bench.py -- sampled+relabelled+targeted transitions/s of the B200 learner hot path (BASELINE.json metric).
 
 One step = one pass of the hot path over `batches_per_step` batches of 4096 sampled windows (T=2, one TD pair per window):
-  fdql_sample_streams  (uniform starts, hindsight flag p=0.8 = "future, k=4", goal row)            [sampled]
-  fdql_sample_gather   (window gather + sample-time HER relabel + reward recompute + return scan)  [relabelled]
+  fdql_sample_gather_draw  (uniform starts, hindsight flag p=0.8 = "future, k=4", goal row drawn in the kernel   [sampled]
+                            + window gather + sample-time HER relabel + reward and return recompute;            [relabelled]
+                            --separate-streams: fdql_sample_streams + fdql_sample_gather, two launches)
   fdql_tqc_loss        (pool 5x25 target atoms, sort, drop 10, soft target, quantile-Huber fwd+bwd,
                         n-step lower bound) on synthetic critic outputs resident in HBM             [targeted]
 on a 1e7-row ring (obs 64, act 8, goal 16+16, 5 scalars; fp32).  `value` is device-timed with everything resident in
@@ -67,6 +68,7 @@ def parse():
     ap.add_argument("--no-updates", action="store_true")
     ap.add_argument("--exact-episode-step", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="learner step launched eagerly instead of as one CUDA graph")
+    ap.add_argument("--separate-streams", action="store_true", help="draw the index / goal streams in their own launch (fdql_sample_streams)")
     ap.add_argument("--tail-scan", action="store_true", help="relabelled returns by scanning the episode tail instead of the link records")
     return ap.parse_args()
 
@@ -201,12 +203,18 @@ def run_ours(args):
     def step(ev=None):
         if ev:
             ev[0].record(stream)
-        L.check(lib.fdql_sample_streams(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], None, p(starts), p(flags), p(goals), sp))
-        counter[0] += 1
+        if args.separate_streams:
+            L.check(lib.fdql_sample_streams(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], None, p(starts), p(flags), p(goals), sp))
         if ev:
             ev[1].record(stream)
-        L.check(lib.fdql_sample_gather(h, n, T, rlen, p(starts), p(flags), p(goals), ring.reward_op.op, params, n_params, GAMMA,
-                                       opts, B, outp, p(aux_mask), p(aux_contig), p(aux_weight), sp))
+        if args.separate_streams:
+            L.check(lib.fdql_sample_gather(h, n, T, rlen, p(starts), p(flags), p(goals), ring.reward_op.op, params, n_params, GAMMA,
+                                           opts, B, outp, p(aux_mask), p(aux_contig), p(aux_weight), sp))
+        else:  # streams drawn inside the gather kernel: one launch
+            L.check(lib.fdql_sample_gather_draw(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], None, p(starts), p(flags), p(goals),
+                                                ring.reward_op.op, params, n_params, GAMMA, opts, B, outp, p(aux_mask), p(aux_contig),
+                                                p(aux_weight), sp))
+        counter[0] += 1
         if ev:
             ev[2].record(stream)
         # the target reads reward / mask / mc_return of the NEXT row (t=1), quirk Q10
@@ -399,9 +407,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()
     kernels = {
-        "sample_streams_kernel": {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS, "symbol": "fdql::sample_streams_kernel"},
-        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + bytes_relabel,
-                                 "symbol": "fdql::sample_gather_tile_kernel<1, true>",
+        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + bytes_relabel + (0 if args.separate_streams else 17),
+                                 "symbol": "fdql::sample_gather_tile_kernel<1, true>" + ("" if args.separate_streams else " (draws its own index / goal streams)"),
                                  "limiter": "HBM latency on random 32-256 B segments (ncu r1: long-scoreboard stalls dominate, DRAM traffic = algorithmic bytes)",
                                  "relabelled_returns": "tail scan (16 B per tail row)" if args.tail_scan else
                                  "link records: chain of equal achieved goals + goal-agnostic return, O(hits) per window"},
@@ -409,6 +416,8 @@ def run_ours(args):
                             "limiter": "instruction issue (72% active, ALU pipe 61%) and shared-memory wavefronts (72% of peak): 128-value sort "
                                        "network + 375 seven-level searches per transition; not HBM (ncu r1, profiles/r1_ncu_summary.md)"},
     }
+    if args.separate_streams:
+        kernels["sample_streams_kernel"] = {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS, "symbol": "fdql::sample_streams_kernel"}
     for kd in kernels.values():
         kd["achieved_gbs"] = kd["bytes_per_transition"] * M / (kd["ms"] * 1e-3) / 1e9
         kd["frac"] = kd["achieved_gbs"] / peak
@@ -439,9 +448,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (random rows of a %.1f GB arena; %d MB of critic outputs per step)"
                              % ((len(ring) + 1) * (ROW_BYTES + 16) / 1e9, M * CQ * 8 // 2 ** 20),
                        "exact_episode_step": bool(args.exact_episode_step), "parallelism": f"replay shards x{world}, no data-path collective"},
-            "roofline": roofline, "gpu_launches": 3 * K, "clocks": clk,
+            "roofline": roofline, "gpu_launches": (3 if args.separate_streams else 2) * K, "clocks": clk,
             "single_batch_launches": {"windows_per_launch": B, "ms_per_batch": small_ms, "transitions_per_s": world * B / (small_ms * 1e-3),
-                                      "note": "3 launches per 4096-window batch from Python, launch-latency bound",
+                                      "note": "3 launches per 4096-window batch from Python (streams, gather, loss), launch-latency bound",
                                       "cuda_graph_4_streams": {"ms_per_batch": graph_ms, "transitions_per_s": world * B / (graph_ms * 1e-3),
                                                                "note": "16 batches x 3 launches captured once, round-robin over four streams"}},
             "checks": {"loss_mean": float(loss.mean()), "relabel_frac": float(flags.float().mean()),

@@ -436,7 +436,16 @@ class ReplayMemory:
         if (_len < (Tn * 2)) or (_len < self._batch_size):
             raise OversampleError("Trying to sample more memories than available!")
         self.flush()
-        if starts is None:
+        fused = starts is None and length is None  # streams drawn inside the gather kernel (fdql_sample_gather_draw)
+        if fused:
+            self._sync_cursor()
+            starts = torch.empty(n, dtype=torch.int64, device=self.device)
+            if relabel_prob > 0:
+                flags = torch.empty(n, dtype=torch.uint8, device=self.device)
+                goal_rows = torch.empty(n, dtype=torch.int64, device=self.device)
+            if self._rng_counter_dev is None:
+                self._rng_counter_dev = torch.zeros(2, dtype=torch.int64, device=self.device)
+        elif starts is None:
             starts, flags, goal_rows = self.draw_streams(n, Tn, goal_mode, relabel_prob)
         starts = self._to_dev_i64(starts)
         n = starts.numel()
@@ -460,6 +469,22 @@ class ReplayMemory:
                     self._out_cache[ck] = aux_t
         op = self.reward_op or RewardOp(L.REWARD_NONE)
         params, n_params = op.c_params()
+        if fused:
+            check(self._lib.fdql_sample_gather_draw(
+                self._h, n, Tn, L.GOAL_FUTURE if goal_mode is None else int(goal_mode), float(relabel_prob), self._rng_seed,
+                self._rng_counter, C.c_void_p(self._rng_counter_dev.data_ptr()) if self.device_counter else None,
+                C.c_void_p(starts.data_ptr()), C.c_void_p(flags.data_ptr()) if flags is not None else None,
+                C.c_void_p(goal_rows.data_ptr()) if flags is not None else None,
+                op.op if flags is not None else L.REWARD_NONE, params, n_params, float(self.gamma), opts, n,
+                L.ptr_array([out[k].data_ptr() if k in out else 0 for k in self._keys]),
+                *[C.c_void_p(t.data_ptr()) if t is not None else None for t in aux_t], _stream_ptr(self.device)))
+            if not self.device_counter:
+                self._rng_counter += 1
+            self.last_streams = (starts, flags, goal_rows)
+            res = dict(out)
+            if aux:
+                res["mask"], res["is_contiguous"], res["loss_weight"] = aux_t
+            return res
         check(self._lib.fdql_sample_gather(
             self._h, n, Tn, _len, C.c_void_p(starts.data_ptr()),
             C.c_void_p(flags.data_ptr()) if flags is not None else None,

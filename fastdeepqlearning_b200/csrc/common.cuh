@@ -178,10 +178,22 @@ int upload_reward_spec(const Arena* a, int32_t op, const float* params_host, int
 
 struct fdql_arena;
 namespace fdql {
+// fused draw of the index / goal streams inside the gather (tile kernel only); the drawn streams are also written out
+struct DrawSpec {
+  int64_t range;
+  int32_t goal_mode;
+  float relabel_prob;
+  uint64_t seed, counter;
+  unsigned long long* counter_dev;
+  int64_t* starts_out;
+  uint8_t* flags_out;
+  int64_t* goal_out;
+};
+// returns FDQL_OK, an error, or (with draw != nullptr) 1 when this shape is not served by the fused kernel (nothing launched)
 int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts,
                   const uint8_t* flags, const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host,
                   int32_t n_params, double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out, float* aux_mask,
-                  float* aux_contig, float* aux_weight, cudaStream_t st);
+                  float* aux_contig, float* aux_weight, cudaStream_t st, const DrawSpec* draw = nullptr);
 }
 
 struct fdql_arena : fdql::Arena {};

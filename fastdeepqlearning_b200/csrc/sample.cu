@@ -33,41 +33,21 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr_lo, uint64_t ctr_hi, ui
   return make_uint4(c0, c1, c2, c3);
 }
 
-// starts ~ U[0, len-T) like np.random.randint(0, len-T, B) (replay_memory.py:59); flag ~ Bernoulli(p); goal row by mode
-// over the committed extents of the start row's episode (her.py:48-53).  Uncommitted rows are never relabelled.
-__global__ void __launch_bounds__(256)
-sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int goal_mode, float relabel_prob, uint64_t seed, uint64_t counter,
-                      unsigned long long* counter_dev, int64_t* __restrict__ starts, uint8_t* __restrict__ flags,
-                      int64_t* __restrict__ goal_rows) {
-  // counter_dev (optional): {draw counter, block ticket} in device memory, so that a captured CUDA graph draws fresh streams at
-  // every replay.  Every block reads the counter before it takes its ticket; the last block to finish advances it.
-  __shared__ unsigned long long sh_ctr;
-  if (counter_dev != nullptr) {
-    if (threadIdx.x == 0) sh_ctr = *reinterpret_cast<volatile unsigned long long*>(counter_dev);
-    __syncthreads();
-    counter += sh_ctr;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned long long ticket = atomicAdd(counter_dev + 1, 1ull);
-      if (ticket == (unsigned long long)gridDim.x - 1) {
-        counter_dev[1] = 0ull;
-        counter_dev[0] = sh_ctr + 1ull;
-        __threadfence();
-      }
-    }
-  }
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n) return;
+// one window's streams: start ~ U[0, range), flag ~ Bernoulli(p) (never for rows of uncommitted episodes), goal row by mode
+__device__ __forceinline__ void draw_window(const ArenaDev& A, int64_t b, int64_t range, int goal_mode, float relabel_prob, uint64_t seed,
+                                            uint64_t counter, bool want_flags, int64_t& s, bool& f, int64_t& g, int& es, int& ee) {
   const uint4 x = philox4x32((uint64_t)b, counter, seed);
   const uint64_t r64 = ((uint64_t)x.x << 32) | x.y;
-  const int64_t s = (int64_t)__umul64hi(r64, (uint64_t)range);
-  starts[b] = s;
-  if (flags == nullptr) return;
+  s = (int64_t)__umul64hi(r64, (uint64_t)range);
+  f = false;
+  g = s;
+  es = -1;
+  ee = -1;
+  if (!want_flags) return;
   const float* rec = A.rec + s * (int64_t)A.rec_stride;
-  const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
-  bool f = (es >= 0) && ((float)x.z * 2.3283064365386963e-10f < relabel_prob);
-  int64_t g = s;
+  es = __float_as_int(__ldg(rec + A.col_ep_start));
+  ee = __float_as_int(__ldg(rec + A.col_ep_end));
+  f = (es >= 0) && ((float)x.z * 2.3283064365386963e-10f < relabel_prob);
   if (f) {
     const int64_t cap = A.capacity;
     if (goal_mode == FDQL_GOAL_FINAL) {
@@ -80,6 +60,43 @@ sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int goal_mode, float
       g = m == 0 ? ee : ring_row(s, 1 + (int64_t)__umulhi(x.w, (uint32_t)m), cap);
     }
   }
+}
+// counter_dev (optional): {draw counter, block ticket} in device memory, so that a captured CUDA graph draws fresh streams at
+// every replay.  Every block reads the counter before it takes its ticket; the block with the last ticket advances it.
+__device__ __forceinline__ uint64_t device_draw_counter(unsigned long long* counter_dev, uint64_t counter) {
+  __shared__ unsigned long long sh_ctr;
+  if (counter_dev == nullptr) return counter;
+  if (threadIdx.x == 0) sh_ctr = *reinterpret_cast<volatile unsigned long long*>(counter_dev);
+  __syncthreads();
+  counter += sh_ctr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(counter_dev + 1, 1ull);
+    if (ticket == (unsigned long long)gridDim.x - 1) {
+      counter_dev[1] = 0ull;
+      counter_dev[0] = sh_ctr + 1ull;
+      __threadfence();
+    }
+  }
+  return counter;
+}
+
+// starts ~ U[0, len-T) like np.random.randint(0, len-T, B) (replay_memory.py:59); flag ~ Bernoulli(p); goal row by mode
+// over the committed extents of the start row's episode (her.py:48-53).  Uncommitted rows are never relabelled.
+__global__ void __launch_bounds__(256)
+sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int goal_mode, float relabel_prob, uint64_t seed, uint64_t counter,
+                      unsigned long long* counter_dev, int64_t* __restrict__ starts, uint8_t* __restrict__ flags,
+                      int64_t* __restrict__ goal_rows) {
+  counter = device_draw_counter(counter_dev, counter);
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  int64_t s, g;
+  bool f;
+  int es, ee;
+  draw_window(A, b, range, goal_mode, relabel_prob, seed, counter, flags != nullptr, s, f, g, es, ee);
+  starts[b] = s;
+  if (flags == nullptr) return;
   flags[b] = f ? 1 : 0;
   if (goal_rows) goal_rows[b] = g;
 }
@@ -103,6 +120,15 @@ struct GatherArgs {
   float* aux_contig;
   float* aux_weight;
   int32_t tile;  // tile kernel: windows per block iteration (32..256)
+  // tile kernel, fused draw (draw_range > 0): the streams are drawn in the kernel exactly as sample_streams_kernel draws them
+  int64_t draw_range;
+  int32_t goal_mode;
+  float relabel_prob;
+  uint64_t seed, counter;
+  unsigned long long* counter_dev;
+  int64_t* starts_out;
+  uint8_t* flags_out;
+  int64_t* goal_out;
   int32_t use_link;  // tile kernel, equality rewards: link records are valid for this gamma -> O(hits) relabelled returns
   double log2_gamma, inv_gamma;
 };
@@ -817,7 +843,7 @@ constexpr int kTileWindows = 256;
 #define WIN_UNROLL 2
 #endif
 
-template <int S, bool HASH>
+template <int S, bool HASH, bool DRAW>
 __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_kernel(const __grid_constant__ GatherArgs g) {
   __shared__ int sm_s[kTileWindows], sm_grow[kTileWindows], sm_tail[kTileWindows];
   const ArenaDev& A = g.A;
@@ -857,6 +883,7 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
   }
   const WideSlab AG = HASH ? A.wide[A.wide_ag] : A.wide[0];
 
+  const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter) : 0;
   const int tile_w = g.tile;  // small launches use small tiles so that every SM gets work
   const int64_t n_tiles = (g.b_end - g.b_begin + tile_w - 1) / tile_w;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -866,21 +893,38 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
     // ================= phase 1: thread <-> window =================
     if ((int)threadIdx.x < n_here) {
       const int64_t b = b0 + threadIdx.x;
-      int64_t s64 = __ldg(g.starts + b);
-      if (s64 >= g.len) s64 %= g.len;
-      const int s = (int)s64;
+      int64_t s64;
       bool relabel = false;
       int tail_last = -1, ep_first = 0, grow = 0;
-      if (HASH && g.flags != nullptr && __ldg(g.flags + b) != 0) {
-        const float* rec = A.rec + (int64_t)s * A.rec_stride;
-        const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
-        if (es >= 0) {
+      if (DRAW) {  // fused draw: same generator, same streams as sample_streams_kernel
+        int64_t g64;
+        bool f;
+        int es, ee;
+        draw_window(A, b, g.draw_range, g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64, es, ee);
+        if (g.starts_out) g.starts_out[b] = s64;
+        if (g.flags_out) g.flags_out[b] = f ? 1 : 0;
+        if (g.goal_out) g.goal_out[b] = g64;
+        if (HASH && f) {
           relabel = true;
           ep_first = es;
-          tail_last = ee - s + (ee < s ? cap32 : 0);
-          grow = (int)__ldg(g.goal_rows + b);
+          tail_last = ee - (int)s64 + (ee < (int)s64 ? cap32 : 0);
+          grow = (int)g64;
+        }
+      } else {
+        s64 = __ldg(g.starts + b);
+        if (s64 >= g.len) s64 %= g.len;
+        if (HASH && g.flags != nullptr && __ldg(g.flags + b) != 0) {
+          const float* rec = A.rec + s64 * A.rec_stride;
+          const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
+          if (es >= 0) {
+            relabel = true;
+            ep_first = es;
+            tail_last = ee - (int)s64 + (ee < (int)s64 ? cap32 : 0);
+            grow = (int)__ldg(g.goal_rows + b);
+          }
         }
       }
+      const int s = (int)s64;
       sm_s[threadIdx.x] = s;
       sm_grow[threadIdx.x] = grow;
       sm_tail[threadIdx.x] = tail_last;
@@ -1116,9 +1160,20 @@ int g_force_full_vector_relabel = 0;  // ... and this to cover MODE 1 with the b
 int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts, const uint8_t* flags,
                          const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host, int32_t n_params,
                          double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out, float* aux_mask,
-                         float* aux_contig, float* aux_weight, cudaStream_t st) {
+                         float* aux_contig, float* aux_weight, cudaStream_t st, const DrawSpec* draw) {
   GatherArgs g;
   memset(&g, 0, sizeof(g));
+  if (draw != nullptr) {
+    g.draw_range = draw->range;
+    g.goal_mode = draw->goal_mode;
+    g.relabel_prob = draw->relabel_prob;
+    g.seed = draw->seed;
+    g.counter = draw->counter;
+    g.counter_dev = draw->counter_dev;
+    g.starts_out = draw->starts_out;
+    g.flags_out = draw->flags_out;
+    g.goal_out = draw->goal_out;
+  }
   g.A = a->dev;
   for (int k = 0; k < a->n_keys; ++k) g.out.p[k] = out[k];
   g.starts = starts;
@@ -1135,10 +1190,10 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   g.aux_mask = aux_mask;
   g.aux_contig = aux_contig;
   g.aux_weight = aux_weight;
-  const bool relabel = flags != nullptr;
+  const bool relabel = draw != nullptr ? draw->flags_out != nullptr : flags != nullptr;
   int lpr = 1;
   if (relabel) {
-    FDQL_REQUIRE(goal_rows != nullptr, "flags without goal_rows");
+    FDQL_REQUIRE(draw != nullptr || goal_rows != nullptr, "flags without goal_rows");
     FDQL_REQUIRE(a->dev.wide_ag >= 0 && a->dev.wide_dg >= 0, "relabelling needs achieved_goal and desired_goal keys");
     FDQL_REQUIRE(reward_op != FDQL_REWARD_NONE, "relabelling needs a reward functor");
     FDQL_REQUIRE(a->dev.wide[a->dev.wide_ag].vecs <= 32, "goal wider than 128 floats is not supported");
@@ -1177,13 +1232,14 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     int64_t tiles = (b_end - b_begin + tile_w - 1) / tile_w;
 #define FDQL_LAUNCH_TILE(SV, HASHV)                                                                              \
   do {                                                                                                           \
-    auto kern = sample_gather_tile_kernel<SV, HASHV>;                                                            \
-    static int per_sm_cached = 0;                                                                                \
-    if (per_sm_cached == 0) {                                                                                    \
-      FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, kern, kTileWindows, 0));           \
-      if (per_sm_cached < 1) per_sm_cached = 1;                                                                  \
+    auto kern = draw != nullptr ? sample_gather_tile_kernel<SV, HASHV, true> : sample_gather_tile_kernel<SV, HASHV, false>; \
+    static int per_sm_cached[2] = {0, 0};                                                                        \
+    int& per_sm = per_sm_cached[draw != nullptr ? 1 : 0];                                                        \
+    if (per_sm == 0) {                                                                                           \
+      FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWindows, 0));                  \
+      if (per_sm < 1) per_sm = 1;                                                                                \
     }                                                                                                            \
-    if (tiles > (int64_t)a->num_sms * per_sm_cached) tiles = (int64_t)a->num_sms * per_sm_cached;                \
+    if (tiles > (int64_t)a->num_sms * per_sm) tiles = (int64_t)a->num_sms * per_sm;                              \
     kern<<<(unsigned)tiles, kTileWindows, 0, st>>>(g);                                                           \
   } while (0)
 #define FDQL_TILE_S(HASHV)                                   \
@@ -1199,6 +1255,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     FDQL_CUDA(cudaGetLastError());
     return FDQL_OK;
   }
+  if (draw != nullptr) return 1;  // only the tile kernel draws; the caller falls back to sample_streams + gather
   if (slots <= 4 && !(g_force_generic_gather & 1)) {
     // persistent-style grid: as many blocks as stay resident, each warp strides over the windows
 #define FDQL_LAUNCH_FAST(SV, LPRV, MODEV)                                                                              \
@@ -1305,6 +1362,33 @@ int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_
                                                                                        starts, flags, goal_rows);
   FDQL_CUDA(cudaGetLastError());
   return FDQL_OK;
+}
+
+int fdql_sample_gather_draw(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
+                            uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows,
+                            int32_t reward_op, const float* reward_params_host, int32_t n_params, double gamma, uint32_t opts,
+                            int32_t batch_for_weight, float* const* out, float* aux_mask, float* aux_contig, float* aux_weight,
+                            void* stream) {
+  FDQL_REQUIRE(a != nullptr && starts != nullptr && out != nullptr, "null argument");
+  FDQL_REQUIRE(T >= 1 && n_windows >= 0, "bad sizes");
+  FDQL_REQUIRE((flags == nullptr) == (goal_rows == nullptr), "flags and goal_rows come together");
+  FDQL_REQUIRE(goal_mode >= FDQL_GOAL_FINAL && goal_mode <= FDQL_GOAL_FUTURE, "bad goal mode");
+  if (a->len < 1 || a->len < 2 * (int64_t)T) {  // replay_memory.py:57-58
+    set_error("OversampleError: ring holds %lld rows, asked for %lld windows of %d", (long long)a->len, (long long)n_windows, T);
+    return FDQL_EOVERSAMPLE;
+  }
+  if (n_windows == 0) return FDQL_OK;
+  if (opts & FDQL_OPT_EMIT_LEARNER_AUX)
+    FDQL_REQUIRE(a->dev.col_task_done >= 0 && a->dev.col_ep_step >= 0, "learner aux needs task_done and episode_step keys");
+  DrawSpec d{a->len - T, goal_mode, relabel_prob, seed, counter, reinterpret_cast<unsigned long long*>(counter_dev), starts, flags, goal_rows};
+  int rc = launch_gather(a, n_windows, 0, n_windows, T, a->len, nullptr, nullptr, nullptr, reward_op, reward_params_host, n_params, gamma,
+                         opts, batch_for_weight, out, aux_mask, aux_contig, aux_weight, (cudaStream_t)stream, &d);
+  if (rc != 1) return rc;
+  // shapes the fused kernel does not serve (small batches, long windows, other reward functors): two launches
+  rc = fdql_sample_streams(a, n_windows, T, goal_mode, relabel_prob, seed, counter, counter_dev, starts, flags, goal_rows, stream);
+  if (rc) return rc;
+  return launch_gather(a, n_windows, 0, n_windows, T, a->len, starts, flags, goal_rows, reward_op, reward_params_host, n_params, gamma, opts,
+                       batch_for_weight, out, aux_mask, aux_contig, aux_weight, (cudaStream_t)stream);
 }
 
 int fdql_gather_rows(const fdql_arena* a, int64_t n, const int64_t* idx, float* const* out, void* stream) {

@@ -151,6 +151,16 @@ int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_
                         uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows,
                         void* stream);
 
+/* fdql_sample_streams + fdql_sample_gather in one launch: the window starts, hindsight flags and goal rows are drawn inside the
+ * gather kernel with the same counter-based generator (identical streams for the same seed / counter), written to starts / flags /
+ * goal_rows (flags and goal_rows NULL: no relabelling) and used at once.  len is the ring's current length.  Shapes the fused kernel
+ * does not serve (small batches, T > 32 with relabelling, other reward functors) run as the two separate launches. */
+int fdql_sample_gather_draw(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
+                            uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows,
+                            int32_t reward_op, const float* reward_params_host, int32_t n_params, double gamma, uint32_t opts,
+                            int32_t batch_for_weight, float* const* out, float* aux_mask, float* aux_contig, float* aux_weight,
+                            void* stream);
+
 /* ReplayMemory.__getitem__ / sample (replay_memory.py:48-52,68-70): out[k] is [n, width_k]. */
 int fdql_gather_rows(const fdql_arena* a, int64_t n, const int64_t* idx, float* const* out, void* stream);
 

@@ -466,3 +466,30 @@ def test_snapshot_restore_roundtrip(R, fdql):
     b = twin.temporal_sample(starts=starts, flags=flags, goal_rows=goal_rows, aux=True, exact_episode_step=True)
     for k in a:
         np.testing.assert_array_equal(npy(a[k]), npy(b[k]), err_msg=k)
+
+
+@pytest.mark.parametrize("n,T", [(5000, 2), (300, 2), (2048, 5), (1500, 40)])
+def test_fused_draw_equals_separate_launches(R, fdql, n, T):
+    """fdql_sample_gather_draw (streams drawn inside the tile gather) vs fdql_sample_streams + fdql_sample_gather with the same
+    seed and counter: identical streams, identical batch; small batches / long windows take the two-launch fallback."""
+    rng = np.random.default_rng(n + T)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 60, 90, 16)
+    ring = R.ReplayMemory(int(lengths.sum()) + 5, 16, T, seed=1234)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.98)
+    ring.add_rows(cols, episode_lengths=lengths)
+    for relabel_prob in (0.8, 0.0):
+        c = ring._rng_counter
+        s, f, g = ring.draw_streams(n, relabel_prob=relabel_prob)
+        want = ring.temporal_sample(starts=s, flags=f, goal_rows=g, aux=True)
+        want = {k: v.clone() for k, v in want.items()}
+        ring._rng_counter = c
+        got = ring.temporal_sample(n=n, relabel_prob=relabel_prob, aux=True)
+        assert ring._rng_counter == c + 1
+        s2, f2, g2 = ring.last_streams
+        np.testing.assert_array_equal(npy(s2), npy(s))
+        if relabel_prob > 0:
+            np.testing.assert_array_equal(npy(f2), npy(f))
+            np.testing.assert_array_equal(npy(g2), npy(g))
+            assert 0.5 < float(f.float().mean()) < 0.95
+        for k in want:
+            np.testing.assert_array_equal(npy(got[k]), npy(want[k]), err_msg=k)
