@@ -35,6 +35,59 @@ class MLPEnsemble(nn.Module):
         return torch.cat([net(x) for net in self.nets], dim=-1)
 
 
+class BatchedMLPEnsemble(nn.Module):
+    """The same function as MLPEnsemble (E independent SkipHeadMLPs, outputs concatenated on the last dim) with the members'
+    weights stacked as [E, in, out] and every layer evaluated by one torch.baddbmm: E times fewer GEMM launches per forward and
+    backward pass, which is what bounds a 4096-row learner step.  Still an ordinary torch module (no custom kernels).
+    `load_member_state_dicts` / `member_state_dicts` convert from / to the per-member layout (franQ's `nets.{i}.hidden.{l}.weight`)."""
+
+    def __init__(self, in_features, out_features, hidden_sizes, ensemble_size):
+        super().__init__()
+        self.E, self.in_features, self.out_features = int(ensemble_size), int(in_features), int(out_features)
+        dims = [in_features] + list(hidden_sizes)
+        self.dims = dims
+        self.hidden_w = nn.ParameterList([nn.Parameter(torch.empty(self.E, a, b)) for a, b in zip(dims[:-1], dims[1:])])
+        self.hidden_b = nn.ParameterList([nn.Parameter(torch.zeros(self.E, 1, b)) for b in dims[1:]])
+        self.head_w = nn.Parameter(torch.empty(self.E, sum(dims), out_features))
+        self.head_b = nn.Parameter(torch.zeros(self.E, 1, out_features))
+        self.act = nn.LeakyReLU()
+        for w in list(self.hidden_w) + [self.head_w]:
+            for e in range(self.E):  # xavier_uniform_ per member on the [out, in] view, like nn.Linear in SkipHeadMLP
+                nn.init.xavier_uniform_(w.data[e].t())
+
+    def forward(self, x):
+        lead = x.shape[:-1]
+        h = x.reshape(1, -1, x.shape[-1]).expand(self.E, -1, -1)
+        feats = [h]
+        for w, b in zip(self.hidden_w, self.hidden_b):
+            h = self.act(torch.baddbmm(b, h, w))
+            feats.append(h)
+        y = torch.baddbmm(self.head_b, torch.cat(feats, dim=-1), self.head_w)  # [E, M, out]
+        return y.permute(1, 0, 2).reshape(*lead, self.E * self.out_features)
+
+    @torch.no_grad()
+    def load_member_state_dicts(self, members):
+        """members[e] = state_dict of a SkipHeadMLP (hidden.{l}.weight [out, in], hidden.{l}.bias, head.weight, head.bias)."""
+        for e, sd in enumerate(members):
+            for l in range(len(self.hidden_w)):
+                self.hidden_w[l][e].copy_(sd[f"hidden.{l}.weight"].t())
+                self.hidden_b[l][e, 0].copy_(sd[f"hidden.{l}.bias"])
+            self.head_w[e].copy_(sd["head.weight"].t())
+            self.head_b[e, 0].copy_(sd["head.bias"])
+
+    def member_state_dicts(self):
+        out = []
+        for e in range(self.E):
+            sd = {}
+            for l in range(len(self.hidden_w)):
+                sd[f"hidden.{l}.weight"] = self.hidden_w[l][e].t().detach().clone()
+                sd[f"hidden.{l}.bias"] = self.hidden_b[l][e, 0].detach().clone()
+            sd["head.weight"] = self.head_w[e].t().detach().clone()
+            sd["head.bias"] = self.head_b[e, 0].detach().clone()
+            out.append(sd)
+        return out
+
+
 class GaussianPolicy(SkipHeadMLP):
     """returns (action, log_prob [..., 1], tanh(mean)) like GaussianMLP.forward (gaussian_mlp.py:15-39)"""
 

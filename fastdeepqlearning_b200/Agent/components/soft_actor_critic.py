@@ -21,7 +21,8 @@ def make_actor(conf, input_dim):
 
 def make_critic(conf, input_dim):
     act = conf.action_space.n if getattr(conf, "discrete", False) else conf.action_space.shape[-1]
-    return models.MLPEnsemble(input_dim + act, conf.num_q_predictions, conf.critic_hidden_dims, ensemble_size=conf.num_critics)
+    cls = models.BatchedMLPEnsemble if getattr(conf, "batched_critics", True) else models.MLPEnsemble
+    return cls(input_dim + act, conf.num_q_predictions, conf.critic_hidden_dims, ensemble_size=conf.num_critics)
 
 
 def _summaries_from_stats(stats, n_atoms, with_violations):
