@@ -56,14 +56,20 @@ class BatchedMLPEnsemble(nn.Module):
                 nn.init.xavier_uniform_(w.data[e].t())
 
     def forward(self, x):
-        lead = x.shape[:-1]
-        h = x.reshape(1, -1, x.shape[-1]).expand(self.E, -1, -1)
-        feats = [h]
-        for w, b in zip(self.hidden_w, self.hidden_b):
-            h = self.act(torch.baddbmm(b, h, w))
-            feats.append(h)
-        y = torch.baddbmm(self.head_b, torch.cat(feats, dim=-1), self.head_w)  # [E, M, out]
-        return y.permute(1, 0, 2).reshape(*lead, self.E * self.out_features)
+        lead, E, d = x.shape[:-1], self.E, self.dims
+        x2 = x.reshape(-1, d[0])
+        M = x2.shape[0]
+        head = torch.split(self.head_w, d, dim=1)  # the head sees the input and every hidden layer: one weight block per source
+        # the input is shared by the members: its two products (first hidden layer, input block of the head) are single GEMMs over
+        # the members' weights laid side by side, read back as strided [E, M, .] views -- no expanded copy of x, no concatenation
+        w0 = self.hidden_w[0].permute(1, 0, 2).reshape(d[0], E * d[1])
+        h = self.act(torch.addmm(self.hidden_b[0].reshape(E * d[1]), x2, w0)).view(M, E, d[1]).transpose(0, 1)
+        y = torch.addmm(self.head_b.reshape(E * self.out_features), x2, head[0].permute(1, 0, 2).reshape(d[0], E * self.out_features))
+        y = torch.baddbmm(y.view(M, E, self.out_features).transpose(0, 1), h, head[1])
+        for l in range(1, len(self.hidden_w)):
+            h = self.act(torch.baddbmm(self.hidden_b[l], h, self.hidden_w[l]))
+            y = torch.baddbmm(y, h, head[l + 1])
+        return y.transpose(0, 1).reshape(*lead, E * self.out_features)
 
     @torch.no_grad()
     def load_member_state_dicts(self, members):
