@@ -163,3 +163,22 @@ def test_autograd_drop_in(ops):
                                 float(g[p + "gamma"]), int(g[p + "n_drop"]))
     (l * dev(g[p + "upstream"])).sum().backward()
     grad_close(qp.grad.cpu().numpy(), g[p + "grad"], g[p + "grad"])
+
+
+@pytest.mark.parametrize("n,n_drop", [(125, 10), (50, 10), (30, 3)])
+def test_unaligned_rows_take_the_plain_staging_path(ops, n, n_drop):
+    """The group kernel stages rows with 16-byte cp.async when the row run is aligned; views that start in the middle of an
+    allocation (row stride 4n bytes: 500 B for 125 atoms) use plain loads.  Same results bit for bit, stats included."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(n)
+    M = 1031
+    zf, qf = torch.randn(M + 1, n, device="cuda", generator=g) * 3, torch.randn(M + 1, n, device="cuda", generator=g) * 3
+    lpf, rf, mcf = (torch.randn(M + 1, 1, device="cuda", generator=g) for _ in range(3))
+    mkf = (torch.rand(M + 1, 1, device="cuda", generator=g) > 0.1).float()
+    a = ops.tqc_loss(qf[1:], zf[1:], lpf[1:], rf[1:], mkf[1:], mcf[1:], 0.7, 0.99, n_drop, want_target=True, want_stats=True)
+    assert qf[1:].data_ptr() % 16 != 0 or n % 4 == 0
+    b = ops.tqc_loss(qf[1:].clone(), zf[1:].clone(), lpf[1:].clone(), rf[1:].clone(), mkf[1:].clone(), mcf[1:].clone(), 0.7, 0.99, n_drop,
+                     want_target=True, want_stats=True)
+    for k in ("loss", "grad", "td_target"):
+        assert torch.equal(a[k], b[k]), k
+    torch.testing.assert_close(a["stats"], b["stats"], rtol=1e-12, atol=0)
