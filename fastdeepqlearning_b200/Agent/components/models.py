@@ -7,11 +7,11 @@ from torch import nn
 
 
 class SkipHeadMLP(nn.Module):
-    def __init__(self, in_features, out_features, hidden_sizes):
+    def __init__(self, in_features, out_features, hidden_sizes, activation_class=nn.LeakyReLU):
         super().__init__()
         dims = [in_features] + list(hidden_sizes)
         self.hidden = nn.ModuleList([nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])])
-        self.act = nn.LeakyReLU()
+        self.act = activation_class()
         self.head = nn.Linear(sum(dims), out_features)
         for m in self.modules():
             if isinstance(m, nn.Linear):
@@ -112,3 +112,23 @@ class GaussianPolicy(SkipHeadMLP):
         normal_log_prob = -0.5 * eps.pow(2) - log_std - 0.9189385332046727  # log(sqrt(2*pi))
         log_prob = (normal_log_prob - torch.log((1 - action.pow(2)) + self.epsilon)).sum(-1, keepdim=True)
         return action, log_prob, torch.tanh(mean)
+
+
+class GumbelPolicy(SkipHeadMLP):
+    """Discrete policy like franQ/Agent/models/gumbel_mlp.py:7-54: returns (straight-through one-hot action, log_prob [..., 1], logits).
+    The relaxed sample is softmax((logits + Gumbel noise) / temperature); the action is its arg-max one-hot with the relaxed
+    sample's gradient (:43-49); log_prob = sum(action * log_softmax(logits)) (:51-54).  Written without torch.distributions
+    (argument validation there syncs with the host and cannot be captured in a CUDA graph)."""
+
+    def __init__(self, in_features, n_actions, hidden_sizes, temperature=1.0):
+        super().__init__(in_features, n_actions, hidden_sizes, activation_class=nn.ReLU)
+        self.temperature = float(temperature)
+
+    def forward(self, state):
+        logits = super().forward(state)
+        u = torch.rand_like(logits).clamp_(1e-20, 1.0 - 1e-7)
+        relaxed = torch.softmax((logits - torch.log(-torch.log(u))) / self.temperature, dim=-1)
+        hard = torch.nn.functional.one_hot(relaxed.argmax(dim=-1), logits.shape[-1]).to(logits.dtype)
+        action = (hard - relaxed).detach() + relaxed
+        log_prob = (action * torch.log_softmax(logits, dim=-1)).sum(-1, keepdim=True)
+        return action, log_prob, logits

@@ -14,8 +14,8 @@ from ... import ops
 
 
 def make_actor(conf, input_dim):
-    if getattr(conf, "discrete", False):
-        raise NotImplementedError("discrete (Gumbel-softmax) policies stay franQ's own torch module; plug it in via actor_factory")
+    if getattr(conf, "discrete", False):  # soft_actor_critic.py:12-14
+        return models.GumbelPolicy(input_dim, conf.action_space.n, conf.pi_hidden_dims)
     return models.GaussianPolicy(input_dim, conf.action_space.shape[0], conf.pi_hidden_dims)
 
 

@@ -87,6 +87,9 @@ class Learner:
             xp["is_contiguous"] = ((step[1:] == step[:-1] + 1) & (xp["mask"][:-1] != 0)).to(step.dtype)
         is_contiguous = xp.pop("is_contiguous")
         xp.pop("loss_weight", None)
+        if getattr(conf, "discrete", False):  # :206-210 one-hot of the stored action index (fdql_action_onehot)
+            from .. import ops
+            xp["action_onehot"] = ops.action_onehot(xp["action"], conf.action_space.n)
         xp["state"] = self.encoder.forward_train(xp)
         curr, nxt = self._temporal_difference_shift(xp)
         q_loss, _, summ = self.actor_critic.q_loss(curr, nxt)

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "fdql_arena_append_host": (C.c_int, [_p, _i64, _pp, _p]),
     "fdql_commit_episodes": (C.c_int, [_p, _i32, _p, _p, _f64, _i32, _i32, C.POINTER(_f32), _i32, _p]),
     "fdql_her_flush_episodes": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _i32, _p]),
+    "fdql_action_onehot": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),
     "fdql_vmap_flush_episodes": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), _i32, _f64, _i32, _i32, _p]),
     "fdql_vmap_select_column": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "fdql_q3_duplicate": (C.c_int, [_p, _i64, _i32, _i64, _f64, _p]),

@@ -149,6 +149,19 @@ __global__ void __launch_bounds__(256) vmap_select_kernel(ArenaDev A, VmapKeys K
   }
 }
 
+// deepQlearning.py:206-210: action_onehot = eye(n)[action.long()] for every row of the [T, B, 1] action column
+__global__ void __launch_bounds__(256) onehot_kernel(int64_t n_rows, int32_t n_actions, const float* __restrict__ action,
+                                                    float* __restrict__ out, int32_t* __restrict__ bad) {
+  const int64_t total = n_rows * n_actions;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n_actions;
+    const int c = (int)(i - r * n_actions);
+    const int64_t a = (int64_t)__ldg(action + r);  // .long(): truncation towards zero
+    if (c == 0 && (a < 0 || a >= n_actions) && bad != nullptr) atomicExch(bad, 1);
+    st_stream1(out + i, a == c ? 1.f : 0.f);
+  }
+}
+
 static int vmap_keys(const fdql_arena* a, int32_t key_goals, int32_t key_rewards, int32_t key_dones, int32_t key_returns, VmapKeys* out) {
   auto slab = [&](int32_t key, WideSlab* w) -> bool {
     if (key < 0 || key >= a->n_keys || a->key_wide[key] < 0) return false;
@@ -173,6 +186,17 @@ static int vmap_keys(const fdql_arena* a, int32_t key_goals, int32_t key_rewards
 using namespace fdql;
 
 extern "C" {
+
+int fdql_action_onehot(int64_t n_rows, int32_t n_actions, const float* action, float* out, int32_t* out_of_range, void* stream) {
+  FDQL_REQUIRE(n_rows >= 0 && n_actions >= 1, "bad sizes");
+  if (n_rows == 0) return FDQL_OK;
+  FDQL_REQUIRE(action != nullptr && out != nullptr, "null argument");
+  int64_t blocks = (n_rows * n_actions + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  onehot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, n_actions, action, out, out_of_range);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
 
 int fdql_vmap_flush_episodes(fdql_arena* a, int32_t n_eps, const int64_t* ep_begin, const int32_t* ep_len, const int64_t* pick_rows,
                              int32_t key_goals, int32_t key_rewards, int32_t key_dones, int32_t key_returns, int32_t reward_op,

@@ -35,6 +35,16 @@ def n_atoms_dropped(top_quantiles_to_drop, n_atoms):
     return int(top_quantiles_to_drop * n_atoms)
 
 
+def action_onehot(action, n_actions):
+    """deepQlearning.py:206-210: eye(n)[action.long()] for a gathered [..., 1] action column -> [..., n] (fp32)."""
+    lead = tuple(action.shape[:-1])
+    a = _flat(action)
+    out = torch.empty((a.numel(), int(n_actions)), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        L.check(L.lib().fdql_action_onehot(a.numel(), int(n_actions), _p(a), _p(out), None, _stream(a)))
+    return out.reshape(lead + (int(n_actions),))
+
+
 def tqc_loss(q_pred, next_z, next_log_pi, reward, mask, mc_return, alpha, gamma, n_drop, grad_scale=None,
              want_target=False, want_stats=False, want_grad=True):
     """DistributionalSoftActorCritic.q_loss from the critics' outputs onward (distributional_soft_actor_critic.py:50-82).

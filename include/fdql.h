@@ -117,6 +117,12 @@ int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row);
  * recurrence over the rewards of rows src_row .. src_row+n_step-1. */
 int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t dst_row, double gamma, void* stream);
 
+/* DeepQLearning.get_losses pre-processing for discrete actions (franQ/Agent/deepQlearning.py:206-210):
+ * out[r, :] = eye(n_actions)[(long)action[r]] for the n_rows rows of a gathered [T, B, 1] action column (fp32 in, fp32 out).
+ * torch's indexing raises on an out-of-range action; here the row becomes all zeros and *out_of_range (device int32, may be NULL,
+ * caller-zeroed) is set to 1. */
+int fdql_action_onehot(int64_t n_rows, int32_t n_actions, const float* action, float* out, int32_t* out_of_range, void* stream);
+
 /* ---- "vmap" hindsight variant (her_mode="vmap"): V virtual goals per row instead of one relabelled copy -------------------
  * The virtual columns are ordinary keys of the arena, named by their key index: virtual_goals [V+1, G] (flattened),
  * virtual_rewards [V+1], virtual_dones [V+1], virtual_mc_return [V+1] (key_returns = -1: absent); column V is the real goal.

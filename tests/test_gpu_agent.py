@@ -157,3 +157,47 @@ def test_cuda_graph_step_matches_eager_and_draws_fresh_streams(fdql):
     le, _ = build(False)
     le_losses = [float(le.train_step()) for _ in range(3)]
     assert all(np.isfinite(le_losses))
+
+
+def test_action_onehot_kernel_golden_and_random(fdql):
+    """deepQlearning.py:206-210: eye(n)[action.long()] -- the one-hot the reference's get_losses built for the discrete golden case,
+    and torch's own indexing on random actions."""
+    import torch
+    from conftest import load_golden
+    from fastdeepqlearning_b200 import ops
+    g = load_golden("get_losses")
+    a = torch.as_tensor(g["gl1_action"], dtype=torch.float32, device="cuda")
+    got = ops.action_onehot(a, 3)
+    np.testing.assert_array_equal(got.cpu().numpy()[:-1], g["gl1_onehot"])
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    act = torch.randint(0, 64, (5, 4096, 1), device="cuda", generator=gen).float()
+    want = torch.eye(64, device="cuda")[act.view(5, 4096).long()]
+    assert torch.equal(ops.action_onehot(act, 64), want)
+
+
+def test_discrete_learner_config(fdql):
+    """BASELINE.json configs[1]: discrete Gumbel-softmax SAC on CartPole-shaped rows (obs 4, 2 actions, no goals) with n-step
+    returns: rows go through Replay.make's NStepReturn head, the learner one-hots the stored action index and steps."""
+    import torch
+    from fastdeepqlearning_b200 import Agent, Replay
+    torch.manual_seed(0)
+    conf = make_conf(Agent, obs_space={"obs_1d": 4}, obs_keys=("obs_1d",), action_space=types.SimpleNamespace(n=2, shape=()), discrete=True,
+                     replay_size=5000, use_HER=False, num_instances=1, temporal_len=2, batch_size=256, num_q_predictions=10,
+                     top_quantiles_to_drop=0.2, nStep_return_steps=1000)
+    read, write = Replay.make(conf)
+    rng = np.random.default_rng(0)
+    for ep in range(40):
+        L = int(rng.integers(8, 60))
+        for t in range(L):
+            write[0].add({"obs_1d": rng.standard_normal(4).astype(np.float32), "action": float(rng.integers(0, 2)), "reward": 1.0,
+                          "task_done": t == L - 1, "episode_done": t == L - 1, "episode_step": t})
+    learner = Agent.Learner(conf, read)
+    xp = read[0].temporal_sample()
+    assert tuple(xp["action"].shape) == (2, 256, 1) and "mc_return" in xp
+    loss = learner.get_losses(dict(xp))
+    assert torch.isfinite(loss)
+    losses = [float(learner.train_step()) for _ in range(3)]
+    assert all(np.isfinite(losses))
+    a, lp, logits = learner.actor_critic.actor(torch.randn(7, 4, device="cuda"))
+    assert tuple(a.shape) == (7, 2) and bool(((a.detach() == 0) | (a.detach() == 1)).all()) and bool((a.detach().sum(-1) == 1).all())
+    assert bool((lp <= 0).all()) and tuple(lp.shape) == (7, 1)
