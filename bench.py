@@ -161,6 +161,8 @@ def run_ours(args):
     pkg.lib()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    from fastdeepqlearning_b200 import parallel
+    numa_cpus = parallel.bind_to_gpu_numa_node(local) if world > 1 else None  # host buffers next to this rank's GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -447,7 +449,8 @@ def run_ours(args):
                        "ring_rows_per_gpu": len(ring) + 1,
                        "l2": "inputs larger than L2 (random rows of a %.1f GB arena; %d MB of critic outputs per step)"
                              % ((len(ring) + 1) * (ROW_BYTES + 16) / 1e9, M * CQ * 8 // 2 ** 20),
-                       "exact_episode_step": bool(args.exact_episode_step), "parallelism": f"replay shards x{world}, no data-path collective"},
+                       "exact_episode_step": bool(args.exact_episode_step), "parallelism": f"replay shards x{world}, no data-path collective",
+                       "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
             "roofline": roofline, "gpu_launches": (3 if args.separate_streams else 2) * K, "clocks": clk,
             "single_batch_launches": {"windows_per_launch": B, "ms_per_batch": small_ms, "transitions_per_s": world * B / (small_ms * 1e-3),
                                       "note": "3 launches per 4096-window batch from Python (streams, gather, loss), launch-latency bound",

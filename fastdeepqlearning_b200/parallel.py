@@ -35,3 +35,28 @@ def make_local_replays(conf, Replay, **kwargs):
     local.num_instances = len(mine)
     read, write = Replay.make(local, **kwargs)
     return mine, read, write
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs: /sys/bus/pci/devices/<bdf>/local_cpulist), so that
+    pinned staging buffers are first-touched next to the GPU and host<->device copies of different ranks do not cross sockets.
+    Returns the CPU set, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
