@@ -1,13 +1,15 @@
-// TQC target + quantile-Huber loss, forward and backward in one pass, one warp per transition.
+// TQC target + quantile-Huber loss, forward and backward in one pass.
 //   DistributionalSoftActorCritic.q_loss   franQ/Agent/components/distributional_soft_actor_critic.py:50-58,66-67,70,76-82
 //   quantile_huber_loss_f                  franQ/Agent/components/distributional_soft_actor_critic.py:90-103
 //   SoftActorCritic.q_loss                 franQ/Agent/components/soft_actor_critic.py:63-99,134
 //
 // The reference materialises the [n_atoms, K] pairwise tensor (14,375 pair evaluations per transition at 5x25 atoms).
-// Here the pooled target atoms are sorted in registers by a warp-level bitonic network (VPL values per lane), the top
-// n_drop are cut, and because the K kept targets y are sorted, the sum over k for one predicted atom q splits at
-// a = #(y < q-1), b = #(y < q), c = #(y <= q+1) into pieces that are linear in prefix sums of y and y^2
-// (SURVEY.md appendix B6).  y and q are shifted by a per-transition centre first so the fp32 prefix sums do not cancel.
+// Here the pooled target atoms are sorted in registers by a bitonic network, the top n_drop are cut, and because the K kept
+// targets y are sorted, the sum over k for one predicted atom q splits at a = #(y < q-1), b = #(y < q), c = #(y <= q+1) into
+// pieces that are linear in prefix sums of y and y^2.  y and q are shifted by a per-transition centre
+// first so the fp32 prefix sums do not cancel.
+// Two kernels: tqc_loss_group_kernel (up to 128 atoms: sub-warp sort, warp-wide search; the one bench.py times) and
+// tqc_loss_kernel (one warp per transition, kept for 129..256 atoms and as a cross-check behind fdql_debug_tqc_warp_kernel).
 #include <math_constants.h>
 
 #include "common.cuh"

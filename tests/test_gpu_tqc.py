@@ -182,3 +182,26 @@ def test_unaligned_rows_take_the_plain_staging_path(ops, n, n_drop):
     for k in ("loss", "grad", "td_target"):
         assert torch.equal(a[k], b[k]), k
     torch.testing.assert_close(a["stats"], b["stats"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("n,n_drop", [(125, 10), (50, 10), (20, 4)])
+def test_group_kernel_vs_warp_per_transition_kernel(ops, fdql, n, n_drop):
+    """Two independent implementations of the same loss (sub-warp sort + warp-wide search vs one warp per transition):
+    bit-identical td_target, losses / gradients / summaries equal to rounding."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(n)
+    M = 3001
+    z, q = torch.randn(M, n, device="cuda", generator=g) * 3, torch.randn(M, n, device="cuda", generator=g) * 3 + 1
+    lp, rw, mc = (torch.randn(M, 1, device="cuda", generator=g) for _ in range(3))
+    mk = (torch.rand(M, 1, device="cuda", generator=g) > 0.1).float()
+    a = ops.tqc_loss(q, z, lp, rw, mk, mc, 0.7, 0.99, n_drop, want_target=True, want_stats=True)
+    lib = fdql.lib()
+    old = lib.fdql_debug_tqc_warp_kernel(1)
+    try:
+        b = ops.tqc_loss(q, z, lp, rw, mk, mc, 0.7, 0.99, n_drop, want_target=True, want_stats=True)
+    finally:
+        lib.fdql_debug_tqc_warp_kernel(old)
+    assert torch.equal(a["td_target"], b["td_target"])
+    torch.testing.assert_close(a["loss"], b["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(a["grad"], b["grad"], rtol=1e-4, atol=1e-5 * float(b["grad"].abs().max()))
+    torch.testing.assert_close(a["stats"], b["stats"], rtol=1e-5, atol=1e-9)
