@@ -435,7 +435,16 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(dom)
+            pj = json.load(open(prof))
+            roofline["traffic"] = pj.get(dom)
+            # second view for kernels that are not HBM-bound: warp instructions per launch (ncu, profiles/) against the SM issue rate
+            # (148 SMs x 4 schedulers x 1 instruction per clock at the sampled SM clock), with this run's launch time
+            sm_clk = (clk.get("sm_mhz") or 1965.0) * 1e6
+            for name, kd in kernels.items():
+                wi = pj.get("warp_instructions", {}).get(name)
+                if wi and not args.tail_scan and not args.separate_streams:
+                    kd["issue"] = {"warp_instructions_per_launch": wi, "achieved_ginst_s": wi / (kd["ms"] * 1e-3) / 1e9,
+                                   "peak_ginst_s": 148 * 4 * sm_clk / 1e9, "frac": wi / (kd["ms"] * 1e-3) / (148 * 4 * sm_clk)}
         except Exception:
             pass
 

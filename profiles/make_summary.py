@@ -47,6 +47,8 @@ for r in data:
         tot = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
         key = "sample_gather_kernel" if "sample_gather" in name else "tqc_loss_kernel" if "tqc_loss" in name else name.split("<")[0]
         traffic[key] = tot
+        if "smsp__inst_executed.sum" in vals:
+            traffic.setdefault("warp_instructions", {})[key] = vals["smsp__inst_executed.sum"]
         dur = vals.get("gpu__time_duration.sum")
         out.append(f"| dram bytes read+write per launch | {tot:.4g} | byte |")
         if dur:
