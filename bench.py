@@ -259,12 +259,11 @@ def run_ours(args):
     # ---- single-batch launches (B=4096 windows per launch): latency-bound figure, reported beside the headline ----
     def small_step(i):
         o = (i % D) * B
-        L.check(lib.fdql_sample_streams(h, B, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, 10_000 + i, None, p(starts[o:]), p(flags[o:]),
-                                        p(goals[o:]), sp))
         outs = L.ptr_array([out[k].data_ptr() for k in keys])
         # outputs of a B-window launch are laid out [T, B, w] inside the first T*B rows of the big buffers
-        L.check(lib.fdql_sample_gather(h, B, T, rlen, p(starts[o:]), p(flags[o:]), p(goals[o:]), ring.reward_op.op, params,
-                                       n_params, GAMMA, opts, B, outs, p(aux_mask), p(aux_contig), p(aux_weight), sp))
+        L.check(lib.fdql_sample_gather_draw(h, B, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, 10_000 + i, None, p(starts[o:]), p(flags[o:]),
+                                            p(goals[o:]), ring.reward_op.op, params, n_params, GAMMA, opts, B, outs, p(aux_mask),
+                                            p(aux_contig), p(aux_weight), sp))
         L.check(lib.fdql_tqc_loss(B, CQ, N_DROP, p(z[o:]), p(q[o:]), p(lp[o:]), p(out["reward"].view(-1)[B:]),
                                   p(aux_mask.view(-1)[B:]), p(out["mc_return"].view(-1)[B:]), p(aux_weight), ALPHA, GAMMA,
                                   p(loss[o:]), p(grad[o:]), None, None, sp))
@@ -295,10 +294,9 @@ def run_ours(args):
 
         def graph_batch(i, st):
             sl, o, spx = slots[i], i * B, C.c_void_p(st.cuda_stream)
-            L.check(lib.fdql_sample_streams(h, B, T, L.GOAL_FUTURE, P_RELABEL, 1000 + 97 * rank + i, 0, p(sl["ctr"]), p(starts[o:]),
-                                            p(flags[o:]), p(goals[o:]), spx))
-            L.check(lib.fdql_sample_gather(h, B, T, rlen, p(starts[o:]), p(flags[o:]), p(goals[o:]), ring.reward_op.op, params,
-                                           n_params, GAMMA, opts, B, sl["outp"], p(sl["mask"]), p(sl["contig"]), p(sl["weight"]), spx))
+            L.check(lib.fdql_sample_gather_draw(h, B, T, L.GOAL_FUTURE, P_RELABEL, 1000 + 97 * rank + i, 0, p(sl["ctr"]), p(starts[o:]),
+                                                p(flags[o:]), p(goals[o:]), ring.reward_op.op, params, n_params, GAMMA, opts, B,
+                                                sl["outp"], p(sl["mask"]), p(sl["contig"]), p(sl["weight"]), spx))
             L.check(lib.fdql_tqc_loss(B, CQ, N_DROP, p(z[o:]), p(q[o:]), p(lp[o:]), p(sl["out"]["reward"][1:]), p(sl["mask"][1:]),
                                       p(sl["out"]["mc_return"][1:]), p(sl["weight"]), ALPHA, GAMMA, p(loss[o:]), p(grad[o:]), None,
                                       None, spx))
@@ -462,9 +460,9 @@ def run_ours(args):
                        "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
             "roofline": roofline, "gpu_launches": (3 if args.separate_streams else 2) * K, "clocks": clk,
             "single_batch_launches": {"windows_per_launch": B, "ms_per_batch": small_ms, "transitions_per_s": world * B / (small_ms * 1e-3),
-                                      "note": "3 launches per 4096-window batch from Python (streams, gather, loss), launch-latency bound",
+                                      "note": "2 launches per 4096-window batch from Python (gather with fused draw, loss), launch-latency bound",
                                       "cuda_graph_4_streams": {"ms_per_batch": graph_ms, "transitions_per_s": world * B / (graph_ms * 1e-3),
-                                                               "note": "16 batches x 3 launches captured once, round-robin over four streams"}},
+                                                               "note": "16 batches x 2 launches captured once, round-robin over four streams"}},
             "checks": {"loss_mean": float(loss.mean()), "relabel_frac": float(flags.float().mean()),
                        "violations": float(stats[2] / max(float(stats[3]), 1) / CQ)}}
     if e2e:
@@ -596,8 +594,8 @@ def cpu_reference(args, steps, warmup, quiet=False):
     line = {"metric": "sampled+relabelled+targeted transitions/s", "value": value, "unit": "transitions/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "HER(future,k=4: relabel p=0.8, full-episode-tail return recompute) + TQC 5x25 drop 10 + n-step "
-                                   "lower bound; obs64/act8/goal16; ring %d rows (L=128 episodes); batch 4096, T=2" % n_rows,
+            "config": {"workload": "HER(future,k=4: relabel p=0.8, return-to-go recomputed over the whole episode tail) + TQC 5x25 drop 10 + "
+                                   "n-step lower bound; obs64/act8/goal16; ring %d rows/GPU (L=128 episodes); batch 4096, T=2" % (n_rows + 1),
                        "batch": B, "temporal_len": T, "batches_per_step": nb},
             "cpu_baseline": base, "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
