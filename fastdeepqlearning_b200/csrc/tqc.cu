@@ -400,6 +400,30 @@ __device__ __forceinline__ void grp_half(float (&e)[E], int sl) {
   }
   if constexpr (J > 1) grp_half<E, J / 2>(e, sl);
 }
+// 60-comparator, 10-layer sorting network for 16 inputs (the bitonic network needs 80 for the same job); checked on all 2^16 0/1
+// inputs (tests/test_cabi_and_host.py::test_sort16_network_sorts_every_01_input reads this table)
+#define FDQL_SORT16_NETWORK(CE)                                                                             \
+  CE(0, 13) CE(1, 12) CE(2, 15) CE(3, 14) CE(4, 8) CE(5, 6) CE(7, 11) CE(9, 10)                           \
+  CE(0, 5) CE(1, 7) CE(2, 9) CE(3, 4) CE(6, 13) CE(8, 14) CE(10, 15) CE(11, 12)                           \
+  CE(0, 1) CE(2, 3) CE(4, 5) CE(6, 8) CE(7, 9) CE(10, 11) CE(12, 13) CE(14, 15)                           \
+  CE(0, 2) CE(1, 3) CE(4, 10) CE(5, 11) CE(6, 7) CE(8, 9) CE(12, 14) CE(13, 15)                           \
+  CE(1, 2) CE(3, 12) CE(4, 6) CE(5, 7) CE(8, 10) CE(9, 11) CE(13, 14)                                     \
+  CE(1, 4) CE(2, 6) CE(5, 8) CE(7, 10) CE(9, 13) CE(11, 14)                                               \
+  CE(2, 4) CE(3, 6) CE(9, 12) CE(11, 13)                                                                  \
+  CE(3, 5) CE(6, 8) CE(7, 9) CE(10, 12)                                                                   \
+  CE(3, 4) CE(5, 6) CE(7, 8) CE(9, 10) CE(11, 12)                                                         \
+  CE(6, 7) CE(8, 9)
+__device__ __forceinline__ void grp_sort16(float (&e)[16]) {
+#define FDQL_CE(a, b)                  \
+  {                                    \
+    const float x = e[a], y = e[b];    \
+    e[a] = fminf(x, y);                \
+    e[b] = fmaxf(x, y);                \
+  }
+  FDQL_SORT16_NETWORK(FDQL_CE)
+#undef FDQL_CE
+}
+
 template <int E, int NT, int K>
 __device__ __forceinline__ void grp_sort_from(float (&e)[E], int sl) {
   grp_flip<E, NT, K>(e, sl);
@@ -459,13 +483,14 @@ __device__ __forceinline__ void grp_stage_rows(float* dst, const float* __restri
   }
 }
 
-constexpr int kGrpLb = 1, kGrpStats = 2;  // kernel flavours: lower bound (mc_return given), summaries (stats given)
+constexpr int kGrpLb = 1, kGrpStats = 2, kGrpFull = 4;  // kernel flavours: lower bound (mc_return given), summaries (stats given),
+                                                          // every atom slot but the last one holds 32 real atoms (n_atoms > 32 * (R - 1))
 
 template <int NT, int FLAGS>
 __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
   using C = GrpCfg<NT>;
   constexpr int E = C::E, LPT = C::LPT, G = C::G, R = C::R, TP = C::TP;
-  constexpr bool LB = (FLAGS & kGrpLb) != 0, STATS = (FLAGS & kGrpStats) != 0;
+  constexpr bool LB = (FLAGS & kGrpLb) != 0, STATS = (FLAGS & kGrpStats) != 0, FULL = (FLAGS & kGrpFull) != 0;
   constexpr int NQ = STATS ? 3 : 1;  // per-transition sums reduced over the warp: loss, sum q, sum q^2
   extern __shared__ __align__(16) float grp_smem[];
   __shared__ double sm_stats[3];
@@ -538,12 +563,20 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
       const bool live = grp < rows;
       const float* zst = Zb + grp * nz;
       float e[E];
+      if (nz >= NT - LPT) {  // only the last slot can fall off the row (125 atoms: 120 + sl < 125)
 #pragma unroll
-      for (int s = 0; s < E; ++s) {
-        const int j = s * LPT + sl;  // any split of the row over the lanes will do: it is sorted next
-        float v = CUDART_INF_F;
-        if (j < nz) v = live ? zst[j] : 0.f;
-        e[s] = v;
+        for (int s = 0; s < E - 1; ++s) e[s] = zst[s * LPT + sl];  // any split of the row over the lanes will do: it is sorted next
+        e[E - 1] = (E - 1) * LPT + sl < nz ? zst[(E - 1) * LPT + sl] : CUDART_INF_F;
+      } else {
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+          const int j = s * LPT + sl;
+          e[s] = j < nz ? zst[j] : CUDART_INF_F;
+        }
+      }
+      if (!live) {  // rows past the end of the batch: harmless finite values, nothing is written for them
+#pragma unroll
+        for (int s = 0; s < E; ++s) e[s] = 0.f;
       }
       const float* in = inb + buf * C::kIn + grp;
       const float rew = (a.reward && live) ? in[0 * G] : 0.f, msk = (a.mask && live) ? in[1 * G] : 1.f;
@@ -552,7 +585,9 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
       const float gs = (a.grad_scale && live) ? in[4 * G] : 1.f;
       const float mg = __fmul_rn(msk, a.gamma);
 
-      grp_sort_from<E, NT, 2>(e, sl);  // sorted position of (sl, s) is i = sl * E + s
+      static_assert(E == 16, "the in-lane sorter is a 16-input network");
+      grp_sort16(e);                    // each lane's 16 values ascending
+      grp_sort_from<E, NT, 2 * E>(e, sl);  // bitonic merges across the lanes; sorted position of (sl, s) is i = sl * E + s
 
       // centre: a kept target near the median.  Fetched here, before any per-slot predicate is live: a shuffle inside the loop
       // has an out-of-line non-converged path, and ptxas would pack and unpack every live predicate around it.
@@ -640,7 +675,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
       float acc = 0.f, lbacc = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        const bool ok = validf[s] != 0.f;
+        const bool ok = (FULL && s < R - 1) ? true : validf[s] != 0.f;
         const float qc = ok ? qrow[32 * s] - c0 : 0.f;
         uint32_t oa = aYt, ob = aYt, oc = aYt;
         grp_search_steps<R, NT / 2, false>(oa, qc - 1.f, one);  // a = #(y < q-1)
@@ -667,10 +702,10 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
           const float lbj = fmaxf(Gc - qc, 0.f);
           const bool on = lbj > 0.f;
           gl = on ? glb : 0.f;
-          lbacc = fmaf(lbj, validf[s], lbacc);
+          lbacc = (FULL && s < R - 1) ? lbacc + lbj : fmaf(lbj, validf[s], lbacc);
           if constexpr (STATS) viol += (on && ok) ? 1 : 0;
         }
-        acc = fmaf(lj, validf[s], acc);
+        acc = (FULL && s < R - 1) ? acc + lj : fmaf(lj, validf[s], acc);
         if (grow_ != nullptr && ok) st_stream1(grow_ + 32 * s, fmaf(gj, gscale, gl));
         if constexpr (STATS) {
           s1 += qc;  // padded slots hold 0
@@ -857,12 +892,16 @@ static int launch_tqc_group_f(const TqcArgs& a, cudaStream_t st) {
 }
 template <int NT>
 static int launch_tqc_group(const TqcArgs& a, cudaStream_t st) {
-  const int flags = (a.mc_return ? kGrpLb : 0) | (a.stats ? kGrpStats : 0);
+  const int flags = (a.mc_return ? kGrpLb : 0) | (a.stats ? kGrpStats : 0) | (a.n_atoms > 32 * (NT / 32 - 1) ? kGrpFull : 0);
   switch (flags) {
     case 0: return launch_tqc_group_f<NT, 0>(a, st);
     case 1: return launch_tqc_group_f<NT, 1>(a, st);
     case 2: return launch_tqc_group_f<NT, 2>(a, st);
-    default: return launch_tqc_group_f<NT, 3>(a, st);
+    case 3: return launch_tqc_group_f<NT, 3>(a, st);
+    case 4: return launch_tqc_group_f<NT, 4>(a, st);
+    case 5: return launch_tqc_group_f<NT, 5>(a, st);
+    case 6: return launch_tqc_group_f<NT, 6>(a, st);
+    default: return launch_tqc_group_f<NT, 7>(a, st);
   }
 }
 

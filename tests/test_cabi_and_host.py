@@ -116,3 +116,19 @@ def test_hindsight_goal_pick_indexing():
     random.seed(3)
     want = [9 - 1 - random.choice(range(9)) for _ in range(50)]
     assert picks == want and set(picks) <= set(range(9))
+
+
+def test_sort16_network_sorts_every_01_input():
+    """The in-lane sorter of the TQC group kernel is a 60-comparator network written as a macro table in csrc/tqc.cu; by the
+    0-1 principle it sorts every input iff it sorts all 2^16 binary ones."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastdeepqlearning_b200", "csrc", "tqc.cu")).read()
+    body = src[src.index("#define FDQL_SORT16_NETWORK(CE)"):src.index("__device__ __forceinline__ void grp_sort16")]
+    pairs = [(int(a), int(b)) for a, b in re.findall(r"CE\((\d+), (\d+)\)", body)]
+    assert len(pairs) == 60 and all(0 <= a < b < 16 for a, b in pairs)
+    x = ((np.arange(1 << 16)[:, None] >> np.arange(16)) & 1).astype(np.int8)
+    for a, b in pairs:
+        lo, hi = np.minimum(x[:, a], x[:, b]), np.maximum(x[:, a], x[:, b])
+        x[:, a], x[:, b] = lo, hi
+    assert bool((np.diff(x, axis=1) >= 0).all())
