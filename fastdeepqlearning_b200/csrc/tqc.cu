@@ -448,6 +448,21 @@ __device__ __forceinline__ void grp_search_steps(uint32_t& addr, float x, uint32
                  : "f"(x), "r"(one), "n"(4 * kProbe), "n"(4 * kAdvance));
   if constexpr (STEP > 1) grp_search_steps<R, STEP / 2, LE>(addr, x, one);
 }
+// the first two levels of a search with their three pivots in registers (every search of a transition probes the same three
+// table entries there): compare, select the level-2 pivot, compare; both advances are predicated IMADs like in grp_search_steps
+template <int ADV1, int ADV2, bool LE>
+__device__ __forceinline__ void grp_search_top2(uint32_t& addr, float x, float piv1, float piv2lo, float piv2hi, uint32_t one) {
+  if constexpr (LE)
+    asm volatile("{\n .reg .pred p, q;\n .reg .f32 v;\n setp.le.f32 p, %2, %1;\n selp.f32 v, %4, %3, p;\n @p mad.lo.u32 %0, %5, %6, %0;\n"
+                 " setp.le.f32 q, v, %1;\n @q mad.lo.u32 %0, %5, %7, %0;\n}"
+                 : "+r"(addr)
+                 : "f"(x), "f"(piv1), "f"(piv2lo), "f"(piv2hi), "r"(one), "n"(ADV1), "n"(ADV2));
+  else
+    asm volatile("{\n .reg .pred p, q;\n .reg .f32 v;\n setp.lt.f32 p, %2, %1;\n selp.f32 v, %4, %3, p;\n @p mad.lo.u32 %0, %5, %6, %0;\n"
+                 " setp.lt.f32 q, v, %1;\n @q mad.lo.u32 %0, %5, %7, %0;\n}"
+                 : "+r"(addr)
+                 : "f"(x), "f"(piv1), "f"(piv2lo), "f"(piv2hi), "r"(one), "n"(ADV1), "n"(ADV2));
+}
 // byte offset 4*phys -> sorted index: phys = row * 32 + col, i = col * R + row
 template <int R>
 __device__ __forceinline__ float grp_count(uint32_t o) {
@@ -669,6 +684,16 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
       const float Gc = LB ? sc[t * C::kSc + 1] : 0.f;
       const uint32_t aYt = aZb + 4 * t * TP, aQt = aQ + 8 * t * TP;
       const float nT1 = lds_f32(aQt + 2 * physK4);  // -(sum of the kept centred targets)
+      // level-1 and level-2 pivots (logical indices NT/2-1, NT/4-1, 3NT/4-1) and the byte advances of these two levels
+      constexpr int kAdv1 = 4 * (NT / 2 >= R ? NT / 2 / R : NT / 2 * 32), kAdv2 = 4 * (NT / 4 >= R ? NT / 4 / R : NT / 4 * 32);
+      constexpr int kPrb1 = 4 * (NT / 2 >= R ? (R - 1) * 32 + NT / 2 / R - 1 : (NT / 2 - 1) * 32);
+      constexpr int kPrb2 = 4 * (NT / 4 >= R ? (R - 1) * 32 + NT / 4 / R - 1 : (NT / 4 - 1) * 32);
+      float piv1 = 0.f, piv2lo = 0.f, piv2hi = 0.f;
+      if constexpr (NT >= 128) {
+        piv1 = lds_f32(aYt + kPrb1);
+        piv2lo = lds_f32(aYt + kPrb2);
+        piv2hi = lds_f32(aYt + kAdv1 + kPrb2);
+      }
       const float gscale = inv_nk * gs, glb = -inv_n * gs;
       const float* qrow = qs + t * n + lane;
       float* __restrict__ grow_ = a.grad_q ? a.grad_q + (m0 + t) * n + lane : nullptr;
@@ -678,9 +703,19 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
         const bool ok = (FULL && s < R - 1) ? true : validf[s] != 0.f;
         const float qc = ok ? qrow[32 * s] - c0 : 0.f;
         uint32_t oa = aYt, ob = aYt, oc = aYt;
-        grp_search_steps<R, NT / 2, false>(oa, qc - 1.f, one);  // a = #(y < q-1)
-        grp_search_steps<R, NT / 2, false>(ob, qc, one);        // b = #(y < q)
-        grp_search_steps<R, NT / 2, true>(oc, qc + 1.f, one);   // c = #(y <= q+1)
+        if constexpr (NT >= 128) {  // levels 1-2 from the three pivots in registers, levels 3.. from the table
+          const float xa = qc - 1.f, xc = qc + 1.f;
+          grp_search_top2<kAdv1, kAdv2, false>(oa, xa, piv1, piv2lo, piv2hi, one);
+          grp_search_top2<kAdv1, kAdv2, false>(ob, qc, piv1, piv2lo, piv2hi, one);
+          grp_search_top2<kAdv1, kAdv2, true>(oc, xc, piv1, piv2lo, piv2hi, one);
+          grp_search_steps<R, NT / 8, false>(oa, xa, one);  // a = #(y < q-1)
+          grp_search_steps<R, NT / 8, false>(ob, qc, one);  // b = #(y < q)
+          grp_search_steps<R, NT / 8, true>(oc, xc, one);   // c = #(y <= q+1)
+        } else {
+          grp_search_steps<R, NT / 2, false>(oa, qc - 1.f, one);
+          grp_search_steps<R, NT / 2, false>(ob, qc, one);
+          grp_search_steps<R, NT / 2, true>(oc, qc + 1.f, one);
+        }
         oa -= aYt;
         ob -= aYt;
         oc -= aYt;
