@@ -30,6 +30,7 @@ def make(conf, **kwargs):
             for r in shards:
                 r.replay.set_reward_op(kwargs["compute_reward"], conf.gamma)
             read_heads = [wrappers.SampleTimeHindsight(r, relabel_prob=getattr(conf, "her_relabel_prob", 0.8)) for r in read_heads]
+            write_heads = [wrappers.IgnoreKeys(r) for r in write_heads]
         else:
             write_heads = [wrappers.HindsightNStepReplay(r, kwargs["compute_reward"], mode=her_mode) for r in write_heads]
     return read_heads, write_heads

@@ -3,6 +3,6 @@ from . import nstep_return as nstep_return_vmap  # the reference keeps NStepRetu
 from .wrapper_base_class import ReplayMemoryWrapper
 from .nstep_return import NStepReturn, NStepReturnVmap
 from .her_vmap import HindsightVmapWrite, HindsightVmapRead
-from .her import HindsightNStepReplay, SampleTimeHindsight
+from .her import HindsightNStepReplay, SampleTimeHindsight, IgnoreKeys
 from .squash_rewards import SquashRewards
 from .torch_dataloader import TorchDataLoader, ConfigurationError

@@ -46,6 +46,18 @@ class HindsightNStepReplay(ReplayMemoryWrapper):
             self.replay_buffer.add_hindsight_rows([begin], [L], [goal])                      # her.py:55-95
 
 
+class IgnoreKeys(ReplayMemoryWrapper):
+    """Write head of the sample-time hindsight mode: drops the keys the reference's HER wrappers ignore (`info`, her.py:13), which the
+    Runner keeps in every row whenever use_HER is on (runner.py:185-186); rows are stored once, nothing else happens at write time."""
+
+    def __init__(self, replay_buffer, ignore_keys=("info",)):
+        ReplayMemoryWrapper.__init__(self, replay_buffer)
+        self._ignored_keys = tuple(ignore_keys)
+
+    def add(self, experience):
+        self.replay_buffer.add({k: v for k, v in experience.items() if k not in self._ignored_keys})
+
+
 class SampleTimeHindsight(ReplayMemoryWrapper):
     """Read head that relabels at sample time: each sampled window is relabelled with probability `relabel_prob`
     towards the achieved goal of a later row of its episode ("future" strategy, k = p/(1-p)), with reward, task_done,

@@ -97,7 +97,8 @@ def test_sample_time_future_read_head(fdql):
                 hit = bool((ag == dg).all())
                 head.add({"obs_1d": rng.standard_normal(5).astype(np.float32), "action": rng.standard_normal(2).astype(np.float32),
                           "achieved_goal": ag, "desired_goal": dg, "reward": 0.0 if hit else -1.0, "task_done": hit,
-                          "episode_done": t == L - 1, "episode_step": t})
+                          "episode_done": t == L - 1, "episode_step": t, "info": {"is_success": hit}})  # runner.py:185-186 keeps info
+    assert "info" not in write_heads[0].keys
     xp = read_heads[0].temporal_sample()
     assert {"mask", "is_contiguous", "loss_weight"} <= set(xp)
     hit = (xp["achieved_goal"] == xp["desired_goal"]).all(-1, keepdim=True).float()
