@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
     sl.src = nullptr; sl.dst = nullptr; sl.sstride = 0; sl.dwidth = 0; sl.meta = SLOT_NONE; sl.ovr = 0;
     bool found = false;
     for (int w = 0; w < A.n_wide; ++w) {
-      const int vecs = A.wide[w].vecs;
+      const int vecs = g.out.p[A.wide[w].key] != nullptr ? A.wide[w].vecs : 0;  // keys without an output take no lanes
       if (!found && i >= 0 && i < vecs) {
         found = true;
         float* o = g.out.p[A.wide[w].key];
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
     sl.src = nullptr; sl.dst = nullptr; sl.sstride = 0; sl.dwidth = 0; sl.meta = SLOT_NONE; sl.ovr = 0;
     bool found = false;
     for (int w = 0; w < A.n_wide; ++w) {
-      const int vecs = A.wide[w].vecs;
+      const int vecs = g.out.p[A.wide[w].key] != nullptr ? A.wide[w].vecs : 0;  // keys without an output take no lanes
       if (!found && i >= 0 && i < vecs) {
         found = true;
         float* o = g.out.p[A.wide[w].key];
@@ -1206,11 +1206,11 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   FDQL_REQUIRE(smem <= 200 * 1024, "temporal_len %d too long for the per-warp window scratch", T);
   const int64_t want_blocks = (b_end - b_begin + warps_per_block - 1) / warps_per_block;
   int64_t blocks = want_blocks;
-  int row_vecs = a->dev.n_scal;  // one lane per float4 of a wide key + one lane per scalar column
-  for (int w = 0; w < a->dev.n_wide; ++w) row_vecs += a->dev.wide[w].vecs;
+  int wide_vecs = 0;  // one lane per float4 of a wide key that has an output (+ one lane per scalar column in the warp kernels)
+  for (int w = 0; w < a->dev.n_wide; ++w)
+    if (out[a->dev.wide[w].key] != nullptr) wide_vecs += a->dev.wide[w].vecs;
+  const int row_vecs = wide_vecs + a->dev.n_scal;
   const int slots = (row_vecs + 31) / 32;
-  int wide_vecs = 0;
-  for (int w = 0; w < a->dev.n_wide; ++w) wide_vecs += a->dev.wide[w].vecs;
   const int wslots = (wide_vecs + 31) / 32;
   const bool hash_ok = relabel && reward_op == FDQL_REWARD_BITFLIP && !g_force_full_vector_relabel;
   // small tail-scanning launches are latency-bound and run faster with one warp per window (measured: 4096 windows 20 us vs 29 us);
