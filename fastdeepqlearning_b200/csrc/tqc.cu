@@ -338,11 +338,11 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
 //   that the G tables of a warp start one bank apart (phase A stores are conflict free, too).
 // =================================================================================================
 constexpr int kGrpE = 16;
-constexpr int kGrpWarps = 4;
 
 template <int NT>
 struct GrpCfg {
   static constexpr int E = kGrpE;
+  static constexpr int kWarps = NT >= 128 ? 16 : NT >= 64 ? 12 : 8;  // one block per SM (shared memory and registers fill it)
   static constexpr int LPT = NT / E;    // lanes per transition in phase A
   static constexpr int G = 32 / LPT;    // transitions per warp and round
   static constexpr int R = NT / 32;     // table rows = predicted atoms per lane in phase B
@@ -353,8 +353,9 @@ struct GrpCfg {
   static constexpr int kRedPitch = 36;  // rows of 32 per-lane partial sums, 16-byte aligned, consecutive rows 4 banks apart
   static constexpr int kRed = 3 * G * kRedPitch;
   static constexpr int kIn = 8 * G;     // staged per-transition inputs {reward, mask, log_pi, mc_return, grad_scale}[G], two buffers
-  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | red | in[0] | in[1] |
-  static constexpr int kWarpFloats = 2 * kZY + 2 * kZY + G * NT + kSc * G + kRed + 2 * kIn;
+  static constexpr int kBar = 8;        // three mbarriers (next_z buffer 0 / 1, q_pred) + padding
+  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | red | in[0] | in[1] | mbarriers |
+  static constexpr int kWarpFloats = 2 * kZY + 2 * kZY + G * NT + kSc * G + kRed + 2 * kIn + kBar;
   static_assert(kZY % 4 == 0 && kWarpFloats % 4 == 0, "16-byte alignment of the staging buffers");
 };
 
@@ -480,29 +481,50 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-// rows [m0, m0 + rows) of a [M, width] matrix -> shared memory, asynchronously when the run is 16-byte aligned and whole
-// (MAXF = capacity of the destination in floats: the copy is unrolled into MAXF/128 predicated 16-byte cp.async per lane)
-template <int MAXF>
-__device__ __forceinline__ void grp_stage_rows(float* dst, const float* __restrict__ src, int64_t m0, int width, int rows, int full_rows,
-                                               bool aligned, int lane) {
-  const float* g = src + m0 * width + lane * 4;
+// ---- 1-D bulk copies (TMA engine) signalled on a per-warp mbarrier ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      "MBAR_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra MBAR_DONE;\n bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// rows [m0, m0 + rows) of a [M, width] matrix -> shared memory: one bulk copy issued by lane 0 and signalled on `bar` when the
+// run is 16-byte aligned and whole (returns true: the reader waits on the barrier), plain loads otherwise (returns false)
+__device__ __forceinline__ bool grp_stage_rows(float* dst, const float* __restrict__ src, int64_t m0, int width, int rows, int full_rows,
+                                               bool aligned, int lane, uint32_t bar) {
+  const float* g1 = src + m0 * width;
   const int nfl = rows * width;
   if (aligned && rows == full_rows) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + 16 * lane;
-#pragma unroll
-    for (int k = 0; k < (MAXF + 127) / 128; ++k)
-      if (lane * 4 + 128 * k < nfl) cp_async16(d + 512 * k, g + 128 * k);
-  } else {
-    const float* g1 = src + m0 * width;
-    for (int i = lane; i < nfl; i += 32) dst[i] = ld_stream1(g1 + i);
+    if (lane == 0) {
+      mbar_expect_tx(bar, 4u * (uint32_t)nfl);
+      bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), g1, 4u * (uint32_t)nfl, bar);
+    }
+    return true;
   }
+  for (int i = lane; i < nfl; i += 32) dst[i] = ld_stream1(g1 + i);
+  return false;
 }
 
 constexpr int kGrpLb = 1, kGrpStats = 2, kGrpFull = 4;  // kernel flavours: lower bound (mc_return given), summaries (stats given),
                                                           // every atom slot but the last one holds 32 real atoms (n_atoms > 32 * (R - 1))
 
 template <int NT, int FLAGS>
-__global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
+__global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
   using C = GrpCfg<NT>;
   constexpr int E = C::E, LPT = C::LPT, G = C::G, R = C::R, TP = C::TP;
   constexpr bool LB = (FLAGS & kGrpLb) != 0, STATS = (FLAGS & kGrpStats) != 0, FULL = (FLAGS & kGrpFull) != 0;
@@ -517,6 +539,15 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
   float* red = sc + C::kSc * G;  // [3 * G][kRedPitch]: per-lane partial sums, one row per (quantity, transition)
   float* inb = red + C::kRed;    // [2][5][G] staged per-transition inputs
   const uint32_t aW = (uint32_t)__cvta_generic_to_shared(W), aQ = aW + 8 * C::kZY;
+  const uint32_t aBar = aW + 4 * (uint32_t)(C::kWarpFloats - C::kBar);  // + 0 / 8: next_z buffers, + 16: q_pred
+  if (lane == 0) {
+    mbar_init(aBar, 1);
+    mbar_init(aBar + 8, 1);
+    mbar_init(aBar + 16, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
   const int n = a.n_atoms, nz = a.n_z, K = nz - a.n_drop;
   const uint32_t one = (uint32_t)min(n, 1);  // 1, opaque to the compiler (see grp_search_steps)
   const float Kf = (float)K;
@@ -524,8 +555,12 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
   const float inv_nk = 1.f / ((float)n * (float)K);
   const float inv_nm1 = n > 1 ? 1.f / (float)(n - 1) : 0.f;
   const float half_over_n = (float)(0.5 / (double)n);
+  // the block owns a contiguous run of groups; a warp that finishes a round takes the next unclaimed group, so the warps of
+  // an SM end within one round of each other whatever order the scheduler favours them in
+  __shared__ int sm_next;
   if (STATS && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
-  if (STATS) __syncthreads();
+  if (threadIdx.x == 0) sm_next = C::kWarps;
+  __syncthreads();
   double st_sum = 0.0, st_var = 0.0;
   int viol = 0;
   // phase B constants of this lane: :98, tau over the pooled atoms: fl32(fl32(j / n) + fl32(1/2/n)) for j = lane + 32 s
@@ -542,35 +577,43 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
   const int c_src = grp * LPT + (K / 2) / E;  // lane holding a kept target near the median in slot 0
   const uint32_t physK4 = 4u * (uint32_t)((K % R) * 32 + K / R);
   const bool zal = (reinterpret_cast<uintptr_t>(a.next_z) & 15) == 0, qal = (reinterpret_cast<uintptr_t>(a.q_pred) & 15) == 0;
-  // per-transition inputs travel with next_z, one round ahead: lane l < 5*G copies array l / G of transition l % G (4-byte cp.async)
+  // per-transition inputs travel one round ahead: lane l < 5*G copies array l / G of transition l % G (4-byte cp.async)
   // (NT = 32 has G = 16: lanes take up to three slots)
   const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
+  // (the five pointers sit side by side in TqcArgs in this order: one indexed constant load instead of a select chain)
+  static_assert(offsetof(TqcArgs, grad_scale) - offsetof(TqcArgs, next_log_pi) == 4 * sizeof(const float*), "input pointer block");
+  const float* const* in_ptrs = &a.next_log_pi;  // {next_log_pi, reward, mask, mc_return, grad_scale}
   auto stage_inputs = [&](int b, int64_t m0) {
 #pragma unroll
     for (int slot = lane; slot < 5 * G; slot += 32) {
       const int which = slot / G, t = slot % G;
-      const float* src = which == 0 ? a.reward : which == 1 ? a.mask : which == 2 ? a.next_log_pi : which == 3 ? a.mc_return : a.grad_scale;
+      const float* src = in_ptrs[which];
       if (src != nullptr && m0 + t < a.M) cp_async4(aW + 4 * (uint32_t)((inb - W) + b * C::kIn + which * G + t), src + m0 + t);
     }
   };
 
-  const int64_t n_groups = (a.M + G - 1) / G;
-  const int64_t wstride = (int64_t)gridDim.x * kGrpWarps;
-  int64_t gi = (int64_t)blockIdx.x * kGrpWarps + wib;
+  const int64_t n_groups_all = (a.M + G - 1) / G;
+  const int64_t per_block = n_groups_all / gridDim.x, extra = n_groups_all % gridDim.x;
+  const int64_t g_begin = blockIdx.x * per_block + min((int64_t)blockIdx.x, extra);
+  const int64_t n_groups = g_begin + per_block + (blockIdx.x < extra ? 1 : 0);  // end of this block's run
+  int64_t gi = g_begin + wib;
   int buf = 0;
+  uint32_t it = 0;  // round counter: the barrier of next_z buffer b completes once per use (parity (it >> 1) & 1), q_pred's every round
+  bool z_bulk = false;
   if (gi < n_groups) {
-    grp_stage_rows<G * NT>(W, a.next_z, gi * G, nz, (int)min((int64_t)G, a.M - gi * G), G, zal, lane);
+    z_bulk = grp_stage_rows(W, a.next_z, gi * G, nz, (int)min((int64_t)G, a.M - gi * G), G, zal, lane, aBar);
     stage_inputs(0, gi * G);
   }
   cp_async_commit();
-  for (; gi < n_groups; gi += wstride, buf ^= 1) {
+  int64_t gnext = 0;
+  for (; gi < n_groups; gi = gnext, buf ^= 1, ++it) {
     const int64_t m0 = gi * G;
     const int rows = (int)min((int64_t)G, a.M - m0);
     float* Zb = W + buf * C::kZY;
     const uint32_t aZb = aW + 4 * buf * C::kZY;
-    grp_stage_rows<G * NT>(qs, a.q_pred, m0, n, rows, G, qal, lane);
-    cp_async_commit();
-    cp_async_wait<1>();  // this round's next_z rows have landed
+    const bool q_bulk = grp_stage_rows(qs, a.q_pred, m0, n, rows, G, qal, lane, aBar + 16);
+    cp_async_wait<0>();  // this round's per-transition inputs have landed
+    if (z_bulk) mbar_wait(aBar + 8 * buf, (it >> 1) & 1);  // ... and its next_z rows
     __syncwarp();
 
     // ================= phase A: LPT lanes per transition =================
@@ -594,8 +637,8 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
         for (int s = 0; s < E; ++s) e[s] = 0.f;
       }
       const float* in = inb + buf * C::kIn + grp;
-      const float rew = (a.reward && live) ? in[0 * G] : 0.f, msk = (a.mask && live) ? in[1 * G] : 1.f;
-      const float ent = (a.next_log_pi && live) ? __fmul_rn(alpha, -in[2 * G]) : 0.f;
+      const float rew = (a.reward && live) ? in[1 * G] : 0.f, msk = (a.mask && live) ? in[2 * G] : 1.f;
+      const float ent = (a.next_log_pi && live) ? __fmul_rn(alpha, -in[0 * G]) : 0.f;
       const float Gv = (LB && live) ? in[3 * G] : 0.f;
       const float gs = (a.grad_scale && live) ? in[4 * G] : 1.f;
       const float mg = __fmul_rn(msk, a.gamma);
@@ -666,20 +709,27 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
         sc[grp * C::kSc + 2] = gs;
       }
     }
+    fence_proxy_async_smem();  // the tables were written through the generic proxy, the bulk copy below overwrites the older ones
     __syncwarp();
     {  // next round's next_z rows into the other buffer (its tables are dead)
-      const int64_t gnext = gi + wstride;
+      int claimed = 0;
+      if (lane == 0) claimed = atomicAdd(&sm_next, 1);
+      gnext = g_begin + __shfl_sync(kFull, claimed, 0);
+      z_bulk = false;
       if (gnext < n_groups) {
-        grp_stage_rows<G * NT>(W + (buf ^ 1) * C::kZY, a.next_z, gnext * G, nz, (int)min((int64_t)G, a.M - gnext * G), G, zal, lane);
+        z_bulk = grp_stage_rows(W + (buf ^ 1) * C::kZY, a.next_z, gnext * G, nz, (int)min((int64_t)G, a.M - gnext * G), G, zal, lane,
+                                aBar + 8 * (buf ^ 1));
         stage_inputs(buf ^ 1, gnext * G);
       }
       cp_async_commit();
     }
-    cp_async_wait<1>();  // this round's q_pred rows have landed
+    if (q_bulk) mbar_wait(aBar + 16, it & 1);  // this round's q_pred rows have landed
     __syncwarp();
 
     // ================= phase B: the warp per transition =================
-    for (int t = 0; t < rows; ++t) {
+    const bool has_grad = a.grad_q != nullptr;
+    float* __restrict__ grow_ = a.grad_q + m0 * n + lane;  // advanced by one row per transition; only dereferenced under has_grad
+    for (int t = 0; t < rows; ++t, grow_ += n) {
       const float c0 = sc[t * C::kSc + 0], gs = sc[t * C::kSc + 2];
       const float Gc = LB ? sc[t * C::kSc + 1] : 0.f;
       const uint32_t aYt = aZb + 4 * t * TP, aQt = aQ + 8 * t * TP;
@@ -696,7 +746,6 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
       }
       const float gscale = inv_nk * gs, glb = -inv_n * gs;
       const float* qrow = qs + t * n + lane;
-      float* __restrict__ grow_ = a.grad_q ? a.grad_q + (m0 + t) * n + lane : nullptr;
       float acc = 0.f, lbacc = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int s = 0; s < R; ++s) {
@@ -741,7 +790,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) tqc_loss_group_kernel(const
           if constexpr (STATS) viol += (on && ok) ? 1 : 0;
         }
         acc = (FULL && s < R - 1) ? acc + lj : fmaf(lj, validf[s], acc);
-        if (grow_ != nullptr && ok) st_stream1(grow_ + 32 * s, fmaf(gj, gscale, gl));
+        if (has_grad && ok) st_stream1(grow_ + 32 * s, fmaf(gj, gscale, gl));
         if constexpr (STATS) {
           s1 += qc;  // padded slots hold 0
           s2 = fmaf(qc, qc, s2);
@@ -910,6 +959,7 @@ int g_tqc_warp_kernel = 0;  // test hook: 1 = always the warp-per-transition ker
 template <int NT, int FLAGS>
 static int launch_tqc_group_f(const TqcArgs& a, cudaStream_t st) {
   using C = GrpCfg<NT>;
+  constexpr int kGrpWarps = C::kWarps;
   constexpr size_t smem = (size_t)kGrpWarps * C::kWarpFloats * sizeof(float);
   static int per_sm = 0;
   if (per_sm == 0) {
@@ -918,7 +968,8 @@ static int launch_tqc_group_f(const TqcArgs& a, cudaStream_t st) {
     if (per_sm < 1) per_sm = 1;
   }
   const int64_t n_groups = (a.M + C::G - 1) / C::G;
-  int64_t blocks = (n_groups + kGrpWarps - 1) / kGrpWarps;
+  // every block takes an equal run of groups and hands them to its warps one by one; small batches spread over all SMs
+  int64_t blocks = n_groups;
   const int64_t resident = (int64_t)num_sms() * per_sm;
   if (blocks > resident) blocks = resident;
   tqc_loss_group_kernel<NT, FLAGS><<<(unsigned)blocks, kGrpWarps * 32, smem, st>>>(a);
