@@ -465,9 +465,27 @@ __device__ __forceinline__ void grp_search_top2(uint32_t& addr, float x, float p
                  : "f"(x), "f"(piv1), "f"(piv2lo), "f"(piv2hi), "r"(one), "n"(ADV1), "n"(ADV2));
 }
 // byte offset 4*phys -> sorted index: phys = row * 32 + col, i = col * R + row
+// (o = 128 row + 4 col  ->  i = o R / 4 - (32 R - 1) row, written as multiply-high / multiply-add so that it runs down the FMA
+// pipe: the ALU pipe is the busier one in this kernel)
 template <int R>
 __device__ __forceinline__ float grp_count(uint32_t o) {
-  return (float)(int)((((o & 124u) * R) >> 2) + (o >> 7));
+  uint32_t row, i;
+  asm("mul.hi.u32 %0, %1, 33554432;" : "=r"(row) : "r"(o));  // o >> 7
+  if constexpr (R == 4) {
+    asm("mad.lo.u32 %0, %1, -127, %2;" : "=r"(i) : "r"(row), "r"(o));
+  } else {
+    uint32_t u;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(u) : "r"(o), "n"(R << 30));  // o R / 4
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(i) : "r"(row), "n"(-(32 * R - 1)), "r"(u));
+  }
+  return (float)(int)i;
+}
+
+// address of the {-P1, P2} entry that belongs to byte offset o of the Y table (8-byte entries), again on the FMA pipe
+__device__ __forceinline__ uint32_t grp_qaddr(uint32_t base, uint32_t o) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(o), "r"(base));
+  return r;
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -621,7 +639,25 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
       const bool live = grp < rows;
       const float* zst = Zb + grp * nz;
       float e[E];
-      if (nz >= NT - LPT) {  // only the last slot can fall off the row (125 atoms: 120 + sl < 125)
+      if constexpr (NT == 128) {
+        // lane (grp, sl) reads element 32 (s / 4) + r_k of its row, k = s % 4, r_k = (8 ((grp + k) % 4) - grp nz + sl) mod 32: at every
+        // step the four transitions of the warp read four different octants of the 32 banks, whatever nz is (rows of 125 floats
+        // start 29 banks apart: with the plain split below every load is a 3-way bank conflict)
+        const int r0 = (8 * grp - grp * nz + sl) & 31;
+        if (nz >= 96) {  // only the last four slots can fall off the row
+#pragma unroll
+          for (int s = 0; s < E; ++s) {
+            const int j = 32 * (s / 4) + ((r0 + 8 * (s % 4)) & 31);
+            e[s] = (s < 12 || j < nz) ? zst[j] : CUDART_INF_F;
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < E; ++s) {
+            const int j = 32 * (s / 4) + ((r0 + 8 * (s % 4)) & 31);
+            e[s] = j < nz ? zst[j] : CUDART_INF_F;
+          }
+        }
+      } else if (nz >= NT - LPT) {  // only the last slot can fall off the row
 #pragma unroll
         for (int s = 0; s < E - 1; ++s) e[s] = zst[s * LPT + sl];  // any split of the row over the lanes will do: it is sorted next
         e[E - 1] = (E - 1) * LPT + sl < nz ? zst[(E - 1) * LPT + sl] : CUDART_INF_F;
@@ -768,7 +804,7 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
         oa -= aYt;
         ob -= aYt;
         oc -= aYt;
-        const float2 Qa = lds2_at(aQt + 2 * oa), Qb = lds2_at(aQt + 2 * ob), Qc = lds2_at(aQt + 2 * oc);
+        const float2 Qa = lds2_at(grp_qaddr(aQt, oa)), Qb = lds2_at(grp_qaddr(aQt, ob)), Qc = lds2_at(grp_qaddr(aQt, oc));
         const float ia = grp_count<R>(oa), ib = grp_count<R>(ob), ic = grp_count<R>(oc);
         // L_i(q) = sum_{k<i} (q - y_k),  F_i(q) = sum_{k<i} (y_k - q)^2   (table: x = -P1_i, y = P2_i)
         const float La = fmaf(ia, qc, Qa.x), Lb = fmaf(ib, qc, Qb.x), Lc = fmaf(ic, qc, Qc.x);
