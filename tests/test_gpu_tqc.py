@@ -165,9 +165,33 @@ def test_autograd_drop_in(ops):
     grad_close(qp.grad.cpu().numpy(), g[p + "grad"], g[p + "grad"])
 
 
+@pytest.mark.parametrize("n,k", [(100, 10), (128, 127), (125, 97), (70, 96), (97, 95), (64, 5), (33, 64), (20, 32), (7, 3)])
+def test_quantile_huber_mismatched_widths_vs_oracle(ops, n, k):
+    """quantile_huber_loss_f with n predicted quantiles against k samples, n != k: the table capacity follows the wider of
+    the two, so the staged sample rows are shorter than the table (short rows take the fully bounds-checked row split).
+    M = 1027 is not a multiple of the group size either, so the last group runs the plain staging path."""
+    rng = np.random.default_rng(1000 * n + k)
+    M = 1027
+    q = (rng.standard_normal((M, n)) * 2).astype(np.float32)
+    s = (rng.standard_normal((M, k)) * 2 + 0.5).astype(np.float32)
+    loss, grad = ops.quantile_huber(dev(q), dev(s))
+    want = O.quantile_huber(q[:64], s[:64])
+    np.testing.assert_allclose(loss.cpu().numpy()[:64], want, rtol=1e-5, atol=1e-7)
+    wg = O.quantile_huber_grad(q[:64], s[:64])
+    grad_close(grad.cpu().numpy()[:64], wg, wg)
+    # the whole batch against the brute-force pairwise form in torch (fp64 on the device)
+    import torch
+    qd, sd = dev(q).double(), dev(s).double()
+    d = sd[:, None, :] - qd[:, :, None]
+    tau = ((torch.arange(n, device="cuda", dtype=torch.float32) / n + 1 / 2 / n).double())[None, :, None]
+    hub = torch.where(d.abs() > 1, d.abs() - 0.5, 0.5 * d * d)
+    ref = ((tau - (d < 0).double()).abs() * hub).mean((-1, -2))
+    np.testing.assert_allclose(loss.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("n,n_drop", [(125, 10), (50, 10), (30, 3)])
 def test_unaligned_rows_take_the_plain_staging_path(ops, n, n_drop):
-    """The group kernel stages rows with 16-byte cp.async when the row run is aligned; views that start in the middle of an
+    """The group kernel stages rows with one bulk copy per group when the row run is 16-byte aligned; views that start in the middle of an
     allocation (row stride 4n bytes: 500 B for 125 atoms) use plain loads.  Same results bit for bit, stats included."""
     import torch
     g = torch.Generator(device="cuda").manual_seed(n)
