@@ -412,8 +412,8 @@ def run_ours(args):
                                  "limiter": "HBM latency on random 32-256 B segments (ncu r1: long-scoreboard stalls dominate, DRAM traffic = algorithmic bytes)",
                                  "relabelled_returns": "tail scan (16 B per tail row)" if args.tail_scan else
                                  "link records: chain of equal achieved goals + goal-agnostic return, O(hits) per window"},
-        "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC, "symbol": "fdql::tqc_loss_group_kernel<128, 3>",
-                            "limiter": "instruction issue (72% active, ALU pipe 61%) and shared-memory wavefronts (72% of peak): 128-value sort "
+        "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC, "symbol": "fdql::tqc_loss_group_kernel<128, 7>",
+                            "limiter": "instruction issue (80% active, ALU pipe 58%) and shared-memory wavefronts (81% of peak): 128-value sort "
                                        "network + 375 seven-level searches per transition; not HBM (ncu r1, profiles/r1_ncu_summary.md)"},
     }
     if args.separate_streams:
