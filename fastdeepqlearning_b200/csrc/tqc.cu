@@ -326,14 +326,14 @@ __global__ void __launch_bounds__(kTqcWarps * 32, VPL <= 4 ? 3 : 2) tqc_loss_ker
 // =================================================================================================
 // Group kernel (n_atoms, n_z <= 128): a warp owns G = 32/LPT transitions per round and works in two layouts.
 //   phase A, LPT lanes per transition, E = 16 values per lane: the pooled target atoms come out of a shared-memory staging
-//     copy (filled one round ahead with 16-byte cp.async), are sorted by a bitonic network that is in registers except for
+//     copy (filled one round ahead by a 1-D bulk copy on a per-warp mbarrier), are sorted by a bitonic network that is in registers except for
 //     log2(LPT) partner exchanges per merge phase, turned into the soft target, centred, prefix-summed (serial walk per lane +
 //     a log2(LPT)-step scan) and written as G search tables.
 //   phase B, the whole warp per transition: lane l handles predicted atoms l, l+32, ...; all 32 lanes search the SAME table,
 //     whose layout makes every search level bank-conflict free, and read {-P1, P2} at the three split points.
 // Against the warp-per-transition kernel above this removes most of the cross-lane sort traffic (6 instead of 15 exchange
 // stages of 128 values), all scans/reductions/bounds checks that were paid per transition by 32 lanes, and the global-load
-// address arithmetic (rows arrive by cp.async).
+// address arithmetic (rows arrive by bulk copies).  One 16-warp block per SM; its warps pull groups from a shared counter.
 //   table layout: sorted index i lives at phys(i) = (i % R) * 32 + i / R, R = NT / 32 rows, table pitch NT + 1 entries so
 //   that the G tables of a warp start one bank apart (phase A stores are conflict free, too).
 // =================================================================================================
@@ -488,9 +488,6 @@ __device__ __forceinline__ uint32_t grp_qaddr(uint32_t base, uint32_t o) {
   return r;
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
