@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the T=50 figure (reference default temporal_len, SURVEY 8)")
     ap.add_argument("--no-updates", action="store_true")
     ap.add_argument("--exact-episode-step", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="learner step launched eagerly instead of as one CUDA graph")
@@ -327,6 +328,56 @@ def run_ours(args):
         assert not torch.equal(first, starts[:B]), "graph replays must draw fresh windows"
         graph_ms = e0.elapsed_time(e1) / (reps * G)
 
+    # ---- secondary figure: the reference's default temporal_len = 50 (conf.py:38): 49 TD pairs per sampled window ------
+    secondary = None
+    if not args.no_secondary:
+        T2, n2 = 50, 4 * B
+        M2 = (T2 - 1) * n2
+        out2 = {k: torch.empty((T2, n2, w), device=device) for k, w in zip(keys, ring._widths)}
+        outp2 = L.ptr_array([out2[k].data_ptr() for k in keys])
+        mask2, contig2, weight2 = (torch.empty(T2, n2, device=device), torch.empty(T2 - 1, n2, device=device),
+                                   torch.empty(T2 - 1, n2, device=device))
+        st2, fl2, go2 = (torch.empty(n2, dtype=torch.int64, device=device), torch.empty(n2, dtype=torch.uint8, device=device),
+                         torch.empty(n2, dtype=torch.int64, device=device))
+        z2 = torch.randn(M2, CQ, device=device, generator=gen) * 3
+        q2 = torch.randn(M2, CQ, device=device, generator=gen) * 3
+        lp2 = torch.randn(M2, device=device, generator=gen)
+        loss2, grad2 = torch.empty(M2, device=device), torch.empty(M2, CQ, device=device)
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+        def step50(i, ev=None):
+            if ev:
+                ev[0].record(stream)
+            L.check(lib.fdql_sample_streams(h, n2, T2, L.GOAL_FUTURE, P_RELABEL, 31 + rank, 50_000 + i, None, p(st2), p(fl2), p(go2), sp))
+            L.check(lib.fdql_sample_gather(h, n2, T2, rlen, p(st2), p(fl2), p(go2), ring.reward_op.op, params, n_params, GAMMA,
+                                           opts, B, outp2, p(mask2), p(contig2), p(weight2), sp))
+            if ev:
+                ev[1].record(stream)
+            L.check(lib.fdql_tqc_loss(M2, CQ, N_DROP, p(z2), p(q2), p(lp2), p(out2["reward"][1:]), p(mask2[1:]),
+                                      p(out2["mc_return"][1:]), p(weight2), ALPHA, GAMMA, p(loss2), p(grad2), None, None, sp))
+            if ev:
+                ev[2].record(stream)
+        for i in range(3):
+            step50(i)
+        torch.cuda.synchronize(device)
+        reps2, acc2 = 10, np.zeros(2)
+        for i in range(reps2):
+            step50(3 + i, ev2)
+            torch.cuda.synchronize(device)
+            acc2 += [ev2[0].elapsed_time(ev2[1]), ev2[1].elapsed_time(ev2[2])]
+        ms2 = float(acc2.sum() / reps2)
+        if dist:
+            tm = torch.tensor([ms2], device=device)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms2 = float(tm.item())
+        secondary = {"temporal_len": T2, "windows_per_step": n2, "transitions_per_step_per_gpu": M2, "ms_per_step": ms2,
+                     "transitions_per_s": world * M2 / (ms2 * 1e-3), "rows_gathered_per_s": world * T2 * n2 / (acc2[0] / reps2 * 1e-3),
+                     "gather_ms": float(acc2[0] / reps2), "tqc_ms": float(acc2[1] / reps2), "loss_mean": float(loss2.mean()),
+                     "note": "reference default temporal_len (conf.py:38): one window gives 49 TD pairs, so the gather is amortised and "
+                             "the loss kernel is the step; streams drawn by fdql_sample_streams, relabelled returns by the tail scan "
+                             "(link records serve T <= 32)"}
+        del out2, z2, q2, grad2, loss2, lp2
+
     # ---- e2e: the host-buffer C-ABI call, pinned host inputs, host outputs ---------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -465,6 +516,8 @@ def run_ours(args):
                                                                "note": "16 batches x 2 launches captured once, round-robin over four streams"}},
             "checks": {"loss_mean": float(loss.mean()), "relabel_frac": float(flags.float().mean()),
                        "violations": float(stats[2] / max(float(stats[3]), 1) / CQ)}}
+    if secondary:
+        line["secondary_T50"] = secondary
     if e2e:
         line["e2e"] = e2e
     if updates:
