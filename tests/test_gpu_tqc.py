@@ -229,3 +229,29 @@ def test_group_kernel_vs_warp_per_transition_kernel(ops, fdql, n, n_drop):
     torch.testing.assert_close(a["loss"], b["loss"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(a["grad"], b["grad"], rtol=1e-4, atol=1e-5 * float(b["grad"].abs().max()))
     torch.testing.assert_close(a["stats"], b["stats"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("M", [1, 3, 4, 5, 63, 64, 2368, 9473, 70001])
+def test_group_kernel_many_batch_sizes_repeatable(ops, fdql, M):
+    """The staging pipeline of the group kernel (bulk copies on per-warp mbarriers whose parity flips every round, groups
+    claimed from a per-block counter) over batch sizes from a single partial group to several rounds per warp: two runs are
+    bit-identical, and equal to the warp-per-transition kernel (identical td_target, losses / gradients to rounding)."""
+    import torch
+    n, n_drop = 125, 10
+    g = torch.Generator(device="cuda").manual_seed(M)
+    z, q = torch.randn(M, n, device="cuda", generator=g) * 3, torch.randn(M, n, device="cuda", generator=g) * 3 + 1
+    lp, rw, mc = (torch.randn(M, 1, device="cuda", generator=g) for _ in range(3))
+    mk = (torch.rand(M, 1, device="cuda", generator=g) > 0.1).float()
+    a = ops.tqc_loss(q, z, lp, rw, mk, mc, 0.7, 0.99, n_drop, want_target=True)
+    b = ops.tqc_loss(q, z, lp, rw, mk, mc, 0.7, 0.99, n_drop, want_target=True)
+    for k in ("loss", "grad", "td_target"):
+        assert torch.equal(a[k], b[k]), k
+    lib = fdql.lib()
+    old = lib.fdql_debug_tqc_warp_kernel(1)
+    try:
+        c = ops.tqc_loss(q, z, lp, rw, mk, mc, 0.7, 0.99, n_drop, want_target=True)
+    finally:
+        lib.fdql_debug_tqc_warp_kernel(old)
+    assert torch.equal(a["td_target"], c["td_target"])
+    torch.testing.assert_close(a["loss"], c["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(a["grad"], c["grad"], rtol=1e-4, atol=1e-5 * float(c["grad"].abs().max()))
