@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
   // other whatever order the scheduler favours them in
   __shared__ int sm_next;
   if (STATS && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
-  if (threadIdx.x == 0) sm_next = C::kWarps;
+  if (threadIdx.x == 0) sm_next = (int)(blockDim.x >> 5);
   __syncthreads();
   double st_sum = 0.0, st_var = 0.0;
   int viol = 0;
@@ -992,17 +992,23 @@ int g_tqc_warp_kernel = 0;  // test hook: 1 = always the warp-per-transition ker
 template <int NT, int FLAGS>
 static int launch_tqc_group_f(const TqcArgs& a, cudaStream_t st) {
   using C = GrpCfg<NT>;
-  constexpr int kGrpWarps = C::kWarps;
-  constexpr size_t smem = (size_t)kGrpWarps * C::kWarpFloats * sizeof(float);
-  static int per_sm = 0;
+  const int64_t n_groups = (a.M + C::G - 1) / C::G;
+  // large batches: one block per SM (its warps share a work counter, see the kernel); batches of at most two rounds per warp: the
+  // same kernel in 4-warp blocks, which leave room on an SM for kernels of other streams (the learner's prefetch pattern)
+  const bool small = n_groups <= (int64_t)2 * C::kWarps * num_sms();
+  const int kGrpWarps = small ? 4 : C::kWarps;
+  const size_t smem = (size_t)kGrpWarps * C::kWarpFloats * sizeof(float);
+  static int per_sm_cached[2] = {0, 0};
+  int& per_sm = per_sm_cached[small ? 1 : 0];
   if (per_sm == 0) {
-    FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (per_sm_cached[0] == 0 && per_sm_cached[1] == 0)
+      FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)C::kWarps * C::kWarpFloats * sizeof(float))));
     FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tqc_loss_group_kernel<NT, FLAGS>, kGrpWarps * 32, smem));
     if (per_sm < 1) per_sm = 1;
   }
-  const int64_t n_groups = (a.M + C::G - 1) / C::G;
   // block b takes groups b, b + blocks, b + 2 blocks, ... and hands them to its warps one by one; small batches spread over all SMs
-  int64_t blocks = n_groups;
+  int64_t blocks = small ? (n_groups + kGrpWarps - 1) / kGrpWarps : n_groups;
   const int64_t resident = (int64_t)num_sms() * per_sm;
   if (blocks > resident) blocks = resident;
   tqc_loss_group_kernel<NT, FLAGS><<<(unsigned)blocks, kGrpWarps * 32, smem, st>>>(a);
