@@ -359,7 +359,8 @@ struct GrpCfg {
   static_assert(kZY % 4 == 0 && kWarpFloats % 4 == 0, "16-byte alignment of the staging buffers");
 };
 
-template <int E, int NT, int K>
+// (LS = lane stride of a transition's lanes: sub-lane sl of transition grp is lane sl * LS + grp)
+template <int E, int NT, int K, int LS>
 __device__ __forceinline__ void grp_flip(float (&e)[E], int sl) {
   if constexpr (K <= E) {
 #pragma unroll
@@ -375,19 +376,19 @@ __device__ __forceinline__ void grp_flip(float (&e)[E], int sl) {
     const bool lower = (sl & (K / 2 / E)) == 0;
     float o[E];
 #pragma unroll
-    for (int s = 0; s < E; ++s) o[s] = __shfl_xor_sync(kFull, e[E - 1 - s], LM);
+    for (int s = 0; s < E; ++s) o[s] = __shfl_xor_sync(kFull, e[E - 1 - s], LM * LS);
 #pragma unroll
     for (int s = 0; s < E; ++s) e[s] = lower ? fminf(e[s], o[s]) : fmaxf(e[s], o[s]);
   }
 }
-template <int E, int J>
+template <int E, int J, int LS>
 __device__ __forceinline__ void grp_half(float (&e)[E], int sl) {
   if constexpr (J >= E) {
     constexpr int LM = J / E;
     const bool lower = (sl & LM) == 0;
 #pragma unroll
     for (int s = 0; s < E; ++s) {
-      const float o = __shfl_xor_sync(kFull, e[s], LM);
+      const float o = __shfl_xor_sync(kFull, e[s], LM * LS);
       e[s] = lower ? fminf(e[s], o) : fmaxf(e[s], o);
     }
   } else {
@@ -399,7 +400,7 @@ __device__ __forceinline__ void grp_half(float (&e)[E], int sl) {
         e[s | J] = fmaxf(x, y);
       }
   }
-  if constexpr (J > 1) grp_half<E, J / 2>(e, sl);
+  if constexpr (J > 1) grp_half<E, J / 2, LS>(e, sl);
 }
 // 60-comparator, 10-layer sorting network for 16 inputs (the bitonic network needs 80 for the same job); checked on all 2^16 0/1
 // inputs (tests/test_cabi_and_host.py::test_sort16_network_sorts_every_01_input reads this table)
@@ -425,11 +426,11 @@ __device__ __forceinline__ void grp_sort16(float (&e)[16]) {
 #undef FDQL_CE
 }
 
-template <int E, int NT, int K>
+template <int E, int NT, int K, int LS>
 __device__ __forceinline__ void grp_sort_from(float (&e)[E], int sl) {
-  grp_flip<E, NT, K>(e, sl);
-  if constexpr (K >= 4) grp_half<E, K / 4>(e, sl);
-  if constexpr (K < NT) grp_sort_from<E, NT, K * 2>(e, sl);
+  grp_flip<E, NT, K, LS>(e, sl);
+  if constexpr (K >= 4) grp_half<E, K / 4, LS>(e, sl);
+  if constexpr (K < NT) grp_sort_from<E, NT, K * 2, LS>(e, sl);
 }
 
 // one level of the branch-free search in the pitch-32 layout: lo is a multiple of 2*STEP, probe logical lo + STEP - 1.
@@ -587,9 +588,11 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
     validf[s] = lane + 32 * s < n ? 1.f : 0.f;
   }
   // phase A constants
-  const int grp = lane / LPT, sl = lane % LPT;
+  // the lanes of a transition are G apart (lane = sl * G + grp): a half-warp then holds every transition with half of its
+  // sub-lanes, which makes the 64-bit stores of the {-P1, P2} tables conflict free (bank pair = grp + 4 sl + const mod 16)
+  const int grp = lane % G, sl = lane / G;
   const int kk = K - sl * E;                  // kept slots of this lane: s < kk
-  const int c_src = grp * LPT + (K / 2) / E;  // lane holding a kept target near the median in slot 0
+  const int c_src = ((K / 2) / E) * G + grp;  // lane holding a kept target near the median in slot 0
   const uint32_t physK4 = 4u * (uint32_t)((K % R) * 32 + K / R);
   const bool zal = (reinterpret_cast<uintptr_t>(a.next_z) & 15) == 0, qal = (reinterpret_cast<uintptr_t>(a.q_pred) & 15) == 0;
   // per-transition inputs travel one round ahead: lane l < 5*G copies array l / G of transition l % G (4-byte cp.async)
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
 
       static_assert(E == 16, "the in-lane sorter is a 16-input network");
       grp_sort16(e);                    // each lane's 16 values ascending
-      grp_sort_from<E, NT, 2 * E>(e, sl);  // bitonic merges across the lanes; sorted position of (sl, s) is i = sl * E + s
+      grp_sort_from<E, NT, 2 * E, G>(e, sl);  // bitonic merges across the lanes; sorted position of (sl, s) is i = sl * E + s
 
       // centre: a kept target near the median.  Fetched here, before any per-slot predicate is live: a shuffle inside the loop
       // has an out-of-line non-converged path, and ptxas would pack and unpack every live predicate around it.
@@ -716,13 +719,13 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
       float x1 = l1, x2 = l2;  // inclusive scan over the LPT lanes of the transition
 #pragma unroll
       for (int d = 1; d < LPT; d <<= 1) {
-        const float o1 = __shfl_up_sync(kFull, x1, d, LPT), o2 = __shfl_up_sync(kFull, x2, d, LPT);
+        const float o1 = __shfl_up_sync(kFull, x1, d * G), o2 = __shfl_up_sync(kFull, x2, d * G);
         if (sl >= d) {
           x1 += o1;
           x2 += o2;
         }
       }
-      float p1 = __shfl_up_sync(kFull, x1, 1, LPT), p2 = __shfl_up_sync(kFull, x2, 1, LPT);  // exclusive
+      float p1 = __shfl_up_sync(kFull, x1, G), p2 = __shfl_up_sync(kFull, x2, G);  // exclusive
       if (sl == 0) p1 = p2 = 0.f;
       p1 = -p1;
       __syncwarp();  // every lane has read its staged row: the buffer becomes the tables
