@@ -464,7 +464,7 @@ def run_ours(args):
                                  "relabelled_returns": "tail scan (16 B per tail row)" if args.tail_scan else
                                  "link records: chain of equal achieved goals + goal-agnostic return, O(hits) per window"},
         "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC, "symbol": "fdql::tqc_loss_group_kernel<128, 7>",
-                            "limiter": "instruction issue (80% active, ALU pipe 58%) and shared-memory wavefronts (81% of peak): 128-value sort "
+                            "limiter": "instruction issue (81% active, ALU pipe 60%) and shared-memory wavefronts (79% of peak): 128-value sort "
                                        "network + 375 seven-level searches per transition; not HBM (ncu r1, profiles/r1_ncu_summary.md)"},
     }
     if args.separate_streams:
