@@ -132,3 +132,33 @@ def test_sort16_network_sorts_every_01_input():
         lo, hi = np.minimum(x[:, a], x[:, b]), np.maximum(x[:, a], x[:, b])
         x[:, a], x[:, b] = lo, hi
     assert bool((np.diff(x, axis=1) >= 0).all())
+
+
+def test_group_kernel_row_split_is_a_conflict_free_bijection():
+    """Phase A of the TQC group kernel (csrc/tqc.cu, NT = 128) lets lane (grp, sl) read element
+    j = 32 (s / 4) + ((8 grp - grp nz + sl + 8 (s % 4)) mod 32) of its staged row at step s.  For every row length nz this must
+    (a) visit each of the 128 slots of a row exactly once and (b) put the 32 lanes of a step on 32 different banks
+    (row grp starts at float offset grp * nz); the Y / {-P1, P2} table stores of the same lanes (float offset
+    grp * 129 + 4 sl + 32 (s % 4) + s / 4) must be conflict free too, the 8-byte ones per half-warp of lanes sl * 4 + grp."""
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastdeepqlearning_b200", "csrc", "tqc.cu")).read()
+    assert "const int r0 = (8 * grp - grp * nz + sl) & 31;" in src and "32 * (s / 4) + ((r0 + 8 * (s % 4)) & 31)" in src
+    assert "const int grp = lane % G, sl = lane / G;" in src
+    grp, sl = np.meshgrid(np.arange(4), np.arange(8), indexing="ij")
+    for nz in range(1, 129):
+        r0 = (8 * grp - grp * nz + sl) & 31
+        seen = np.zeros((4, 128), np.int32)
+        for s in range(16):
+            j = 32 * (s // 4) + ((r0 + 8 * (s % 4)) & 31)
+            for g in range(4):
+                seen[g, j[g]] += 1
+            banks = (grp * nz + j) % 32
+            assert len(set(banks.ravel().tolist())) == 32, (nz, s)
+        assert (seen == 1).all(), nz
+    lane = np.arange(32)
+    g, l = lane % 4, lane // 4
+    for s in range(16):
+        ph = g * 129 + 4 * l + 32 * (s % 4) + s // 4
+        assert len(set((ph % 32).tolist())) == 32                     # 4-byte Y table stores: 32 banks
+        for half in (slice(0, 16), slice(16, 32)):
+            assert len(set((ph[half] % 16).tolist())) == 16           # 8-byte table stores: 16 bank pairs per half-warp
