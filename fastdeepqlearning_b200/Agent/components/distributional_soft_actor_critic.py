@@ -6,7 +6,7 @@ lower bound, summaries, and d loss/d q_pred) is ONE launch of fdql_tqc_loss.  `q
 the reference's free function."""
 import torch
 
-from .soft_actor_critic import SoftActorCritic, _LossWithStats, _summaries_from_stats
+from .soft_actor_critic import SoftActorCritic, _LossWithStats, _ReducedLossWithStats, _summaries_from_stats
 from ... import ops
 
 quantile_huber_loss_f = ops.quantile_huber_loss_f
@@ -25,10 +25,9 @@ class DistributionalSoftActorCritic(SoftActorCritic):
         q_pred, next_z, next_log_pi = self._critic_io(curr_xp, next_xp)
         lb = next_xp["mc_return"] if conf.use_nStep_lowerbounds else None
         lp = next_log_pi if conf.use_max_entropy_q else None
-        alpha, n_drop = self.curr_alpha, self.n_drop(q_pred.shape[-1])  # alpha stays on the device
-
-        def fused(q):
-            return ops.tqc_loss(q, next_z, lp, next_xp["reward"], next_xp["mask"], lb, alpha, conf.gamma, n_drop,
-                                grad_scale=grad_scale, want_stats=True)
-        loss, stats = _LossWithStats.apply(q_pred, fused)
+        loss, stats = _LossWithStats.apply(q_pred, lambda q: self._q_loss_fused(q, next_z, lp, next_xp, lb, grad_scale))
         return loss, None, _summaries_from_stats(stats, q_pred.shape[-1], lb is not None)
+
+    def _q_loss_fused(self, q_pred, next_z, lp, next_xp, lb, grad_scale):
+        return ops.tqc_loss(q_pred, next_z, lp, next_xp["reward"], next_xp["mask"], lb, self.curr_alpha, self.conf.gamma,
+                            self.n_drop(q_pred.shape[-1]), grad_scale=grad_scale, want_stats=True)

@@ -25,6 +25,42 @@ class SkipHeadMLP(nn.Module):
             feats.append(x)
         return self.head(torch.cat(feats, dim=-1))
 
+    @torch.no_grad()
+    def load_reference_state_dict(self, sd, prefix=""):
+        """Weights saved by franQ's SkipHeadMLP (models/mlp.py:62-90: `feature_extractor.{i}.0.{weight,bias}`, `head.{weight,bias}`)."""
+        for i, lin in enumerate(self.hidden):
+            lin.weight.copy_(torch.as_tensor(sd[f"{prefix}feature_extractor.{i}.0.weight"]))
+            lin.bias.copy_(torch.as_tensor(sd[f"{prefix}feature_extractor.{i}.0.bias"]))
+        self.head.weight.copy_(torch.as_tensor(sd[f"{prefix}head.weight"]))
+        self.head.bias.copy_(torch.as_tensor(sd[f"{prefix}head.bias"]))
+
+    def reference_state_dict(self, prefix=""):
+        out = {}
+        for i, lin in enumerate(self.hidden):
+            out[f"{prefix}feature_extractor.{i}.0.weight"] = lin.weight.detach().clone()
+            out[f"{prefix}feature_extractor.{i}.0.bias"] = lin.bias.detach().clone()
+        out[f"{prefix}head.weight"], out[f"{prefix}head.bias"] = self.head.weight.detach().clone(), self.head.bias.detach().clone()
+        return out
+
+
+class FeedForwardEncoder(nn.Module):
+    """franQ/Agent/components/encoder.py:13-58 in its feed-forward mode for 1-D observations: cat(obs_1d, achieved_goal,
+    desired_goal) -> MLP(hidden_features) -> joiner MLP(out_features).  Ordinary torch (BASELINE.json north_star)."""
+
+    def __init__(self, in_features, out_features, hidden_features=256, obs_1d_hidden_dims=(256,), joint_hidden_dims=(256,),
+                 keys=("obs_1d", "achieved_goal", "desired_goal")):
+        super().__init__()
+        self.keys = tuple(keys)
+        self.obs_1d = SkipHeadMLP(in_features, hidden_features, obs_1d_hidden_dims)
+        self.joiner = SkipHeadMLP(hidden_features, out_features, joint_hidden_dims)
+
+    def forward_train(self, xp):
+        return self.joiner(self.obs_1d(torch.cat([xp[k] for k in self.keys if k in xp], dim=-1)))
+
+    def load_reference_state_dict(self, sd, prefix=""):
+        self.obs_1d.load_reference_state_dict(sd, prefix + "visible_layer_encoders.obs_1d.")
+        self.joiner.load_reference_state_dict(sd, prefix + "joiner.")
+
 
 class MLPEnsemble(nn.Module):
     def __init__(self, in_features, out_features, hidden_sizes, ensemble_size):
@@ -33,6 +69,10 @@ class MLPEnsemble(nn.Module):
 
     def forward(self, x):
         return torch.cat([net(x) for net in self.nets], dim=-1)
+
+    def load_reference_state_dict(self, sd, prefix=""):
+        for e, net in enumerate(self.nets):
+            net.load_reference_state_dict(sd, f"{prefix}nets.{e}.")
 
 
 class BatchedMLPEnsemble(nn.Module):
@@ -80,6 +120,19 @@ class BatchedMLPEnsemble(nn.Module):
                 self.hidden_b[l][e, 0].copy_(sd[f"hidden.{l}.bias"])
             self.head_w[e].copy_(sd["head.weight"].t())
             self.head_b[e, 0].copy_(sd["head.bias"])
+
+    def load_reference_state_dict(self, sd, prefix=""):
+        """Weights saved by franQ's MLPEnsemble (models/mlp.py:95-104: `nets.{e}.feature_extractor.{l}.0.weight`, `nets.{e}.head.weight`)."""
+        members = []
+        for e in range(self.E):
+            m = {}
+            for l in range(len(self.hidden_w)):
+                m[f"hidden.{l}.weight"] = torch.as_tensor(sd[f"{prefix}nets.{e}.feature_extractor.{l}.0.weight"])
+                m[f"hidden.{l}.bias"] = torch.as_tensor(sd[f"{prefix}nets.{e}.feature_extractor.{l}.0.bias"])
+            m["head.weight"] = torch.as_tensor(sd[f"{prefix}nets.{e}.head.weight"])
+            m["head.bias"] = torch.as_tensor(sd[f"{prefix}nets.{e}.head.bias"])
+            members.append(m)
+        self.load_member_state_dicts(members)
 
     def member_state_dicts(self):
         out = []

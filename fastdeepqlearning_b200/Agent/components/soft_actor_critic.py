@@ -51,6 +51,22 @@ class _LossWithStats(torch.autograd.Function):
         return grad * g_loss, None
 
 
+class _ReducedLossWithStats(torch.autograd.Function):
+    """sum_m weight[m] * loss[m] as one scalar; the kernel applied `weight` to d loss / d q_pred itself (grad_scale)."""
+
+    @staticmethod
+    def forward(ctx, q_pred, fn, weight):
+        r = fn(q_pred)
+        ctx.save_for_backward(r["grad"])
+        ctx.mark_non_differentiable(r["stats"])
+        return (r["loss"] * weight).sum(), r["stats"]
+
+    @staticmethod
+    def backward(ctx, g_total, _g_stats):
+        (grad,) = ctx.saved_tensors
+        return grad * g_total, None, None
+
+
 class SoftActorCritic(nn.Module):
     def __init__(self, conf, input_dim, actor_factory=make_actor, critic_factory=make_critic):
         super().__init__()
@@ -96,26 +112,62 @@ class SoftActorCritic(nn.Module):
         q_pred = self.critic(torch.cat((curr_xp["state"], action), dim=-1))
         return q_pred, next_z, next_log_pi
 
-    def q_loss(self, curr_xp, next_xp):
+    def _bootstrap_bound(self, q_pred, next_z, next_log_pi, next_xp):
+        """soft_actor_critic.py:102-132: the n-step return over the whole sampled window, bootstrapped from the target network at its
+        last row, as a lower bound on the prediction at t = 0; zero for windows that cross a terminal.  [B, CQ] like the reference
+        (plain torch: off in every reference preset, a handful of [B]-sized ops)."""
         conf = self.conf
-        if getattr(conf, "use_bootstrap_minibatch_nstep", False):
-            raise NotImplementedError("use_bootstrap_minibatch_nstep (soft_actor_critic.py:102-132) is outside the hot path")
+        Tm1 = q_pred.shape[0]
+        with torch.no_grad():
+            tz = next_z[-1]
+            if next_log_pi is not None:
+                tz = tz + self.curr_alpha * (-next_log_pi[-1])
+            td_last = next_xp["reward"][-1] + next_xp["mask"][-1] * conf.gamma * tz.min(-1, keepdim=True)[0]
+            g = conf.gamma ** torch.arange(Tm1, device=q_pred.device, dtype=q_pred.dtype).view(-1, *[1] * (next_xp["reward"].dim() - 1))
+            ret = (next_xp["reward"] * g).sum(0)
+            valid = next_xp["mask"].to(q_pred.dtype).prod(0)
+        return valid * ((ret + (conf.gamma ** Tm1) * td_last) - q_pred[0]).relu()
+
+    def q_loss(self, curr_xp, next_xp, grad_scale=None):
+        conf = self.conf
         q_pred, next_z, next_log_pi = self._critic_io(curr_xp, next_xp)
         lb = next_xp["mc_return"] if conf.use_nStep_lowerbounds else None
         lp = next_log_pi if conf.use_max_entropy_q else None
-        alpha = float(self.curr_alpha)  # (host read: the non-distributional kernel takes alpha by value)
+        loss, stats = _LossWithStats.apply(q_pred, lambda q: self._q_loss_fused(q, next_z, lp, next_xp, lb, grad_scale))
+        summ = _summaries_from_stats(stats, q_pred.shape[-1], lb is not None)
+        bound = None
+        if conf.use_nStep_lowerbounds and getattr(conf, "use_bootstrap_minibatch_nstep", False):
+            bound = self._bootstrap_bound(q_pred, next_z, lp, next_xp)
+            summ["bootstrap_minibatch_nstep_violations"] = (bound.detach() != 0).float().mean()
+        return loss, bound, summ
 
-        def fused(q):
-            return ops.sac_min_target_loss(q, next_z, lp, next_xp["reward"], next_xp["mask"], lb, alpha, conf.gamma, want_stats=True)
-        loss, stats = _LossWithStats.apply(q_pred, fused)
-        return loss, None, _summaries_from_stats(stats, q_pred.shape[-1], lb is not None)
+    def _q_loss_fused(self, q_pred, next_z, lp, next_xp, lb, grad_scale):
+        return ops.sac_min_target_loss(q_pred, next_z, lp, next_xp["reward"], next_xp["mask"], lb, self.curr_alpha, self.conf.gamma,
+                                       grad_scale=grad_scale, want_stats=True)
+
+    def q_loss_reduced(self, curr_xp, next_xp, weight):
+        """(sum over the [T-1, B] transitions of weight * q_loss, summaries): q_loss followed by the learner's loss reduce
+        (deepQlearning.py:222-225,249) with the reduce weights folded into the kernel's backward pass."""
+        conf = self.conf
+        q_pred, next_z, next_log_pi = self._critic_io(curr_xp, next_xp)
+        lb = next_xp["mc_return"] if conf.use_nStep_lowerbounds else None
+        lp = next_log_pi if conf.use_max_entropy_q else None
+        total, stats = _ReducedLossWithStats.apply(q_pred, lambda q: self._q_loss_fused(q, next_z, lp, next_xp, lb, weight), weight)
+        return total, _summaries_from_stats(stats, q_pred.shape[-1], lb is not None)
+
+    def _alias_frozen_critic(self):
+        """soft_actor_critic.py:142 copies critic -> critic_frozen before every actor update so that the policy gradient flows through
+        the critic's function but not into its weights.  Here critic_frozen's parameters (requires_grad False) SHARE the critic's
+        storage: always equal, nothing to copy per step, and the optimizer's in-place updates are seen at once."""
+        for pf, p in zip(self.critic_frozen.parameters(), self.critic.parameters()):
+            if pf.data_ptr() != p.data_ptr():
+                pf.data = p.data
 
     def actor_loss(self, xp):
         """soft_actor_critic.py:136-154 (ordinary torch: it differentiates through the critic MLP)."""
         pi, log_pi, _ = self.actor(xp["state"])
         entropy = -log_pi
-        with torch.no_grad():  # hard_update(critic_frozen, critic) (soft_actor_critic.py:142) as one multi-tensor copy
-            torch._foreach_copy_(list(self.critic_frozen.parameters()), list(self.critic.parameters()))
+        self._alias_frozen_critic()
         qpi = self.critic_frozen(torch.cat((xp["state"].detach(), pi), dim=-1)).mean(-1, keepdim=True)
         alpha_now = self.curr_alpha.detach().clone()  # the buffer is refreshed in place below
         policy_loss = -(alpha_now * entropy) - qpi

@@ -86,17 +86,28 @@ class Learner:
             step = xp["episode_step"]
             xp["is_contiguous"] = ((step[1:] == step[:-1] + 1) & (xp["mask"][:-1] != 0)).to(step.dtype)
         is_contiguous = xp.pop("is_contiguous")
-        xp.pop("loss_weight", None)
+        weight = xp.pop("loss_weight", None)
         if getattr(conf, "discrete", False):  # :206-210 one-hot of the stored action index (fdql_action_onehot)
             from .. import ops
             xp["action_onehot"] = ops.action_onehot(xp["action"], conf.action_space.n)
         xp["state"] = self.encoder.forward_train(xp)
         curr, nxt = self._temporal_difference_shift(xp)
-        q_loss, _, summ = self.actor_critic.q_loss(curr, nxt)
+        bootstrap = getattr(conf, "use_bootstrap_minibatch_nstep", False) and conf.use_nStep_lowerbounds
+        if weight is not None and not bootstrap and getattr(conf, "fold_loss_reduce", True):
+            # :222-225,249 folded into the loss kernel: the gather kernel's aux weight contig / ((sum_t contig + 1e-4) B T) goes in as
+            # grad_scale, so d loss / d q_pred leaves the kernel already reduced and the scalar is sum(weight * per-transition loss)
+            q_sum, summ = self.actor_critic.q_loss_reduced(curr, nxt, weight)
+            pi_loss, alpha_loss, asumm = self.actor_critic.actor_loss(curr)
+            self.last_summaries = {**summ, **asumm, "Valid_Portion": is_contiguous.mean()}
+            return q_sum + ((pi_loss + alpha_loss) * weight).sum()
+        q_loss, bound, summ = self.actor_critic.q_loss(curr, nxt)
         pi_loss, alpha_loss, asumm = self.actor_critic.actor_loss(curr)
         loss = ((q_loss + pi_loss + alpha_loss) * is_contiguous).sum(0) / (is_contiguous.sum(0) + 1e-4)   # :222-225
+        loss = loss.mean()
+        if bootstrap:                                                                                   # :226-228
+            loss = loss + (bound * is_contiguous.prod(0)).mean()
         self.last_summaries = {**summ, **asumm, "Valid_Portion": is_contiguous.mean()}
-        return loss.mean() / conf.temporal_len                                                         # :249
+        return loss / conf.temporal_len                                                                # :249
 
     def _allreduce_grads(self):
         import torch.distributed as dist

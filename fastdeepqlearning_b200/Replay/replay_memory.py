@@ -48,7 +48,7 @@ class ReplayMemory:
         self._widths: T.List[int] = []
         self._shapes: T.Dict[str, tuple] = {}
         self._role_override = dict(roles or {})
-        self._stage_rows = int(stage_rows)
+        self._stage_rows = max(1, min(int(stage_rows), self._maxlen))  # a flush never carries more rows than the ring holds
         self._stage = None
         self._stage_np = None
         self._n_staged = 0

@@ -48,7 +48,9 @@ class NStepReturn(ReplayMemoryWrapper):
 
     def _add_rows_q3(self, cols, lens):
         """Episode by episode: an episode longer than n_step is preceded by the duplicate of its oldest row (the reference
-        emits it while the episode is still running, so it lands in the ring before the episode's own rows)."""
+        emits it while the episode is still running, so it lands in the ring before the episode's own rows).
+        Returns the row of the first episode's own first row -- NOT the duplicate's: the hindsight wrapper copies from it and
+        counts its goal pick from it (her.py:36-46 sees the episode, never the duplicate)."""
         n = next(iter(cols.values())).shape[0]
         cols = dict(cols)
         if self.return_name not in cols:
@@ -61,7 +63,7 @@ class NStepReturn(ReplayMemoryWrapper):
             begin = self.replay_buffer.add_rows(sub, episode_lengths=[L], with_returns=True, gamma=self.discount)
             if dup is not None:
                 self.replay_buffer.q3_duplicate(begin, self.n_step, dup, self.discount)
-            first = (dup if dup is not None else begin) if first is None else first
+            first = begin if first is None else first
             off += L
         return first
 
@@ -98,10 +100,27 @@ class NStepReturnVmap(ReplayMemoryWrapper):
     def _reset(self):
         self.rows = []
 
-    def _check_len(self, L):
+    def _write_episode(self, cols, L, picks=None):
+        """One finished episode -> ring.  An episode longer than n_step is preceded by the duplicate of its oldest row carrying the
+        per-column return truncated after n_step rows: the reference's `_pop` (nstep_return_vmap.py:50-57) emits it when the deque
+        reaches n_step rows and, like NStepReturn._pop, never removes the row (quirk Q3), so it lands in the ring before the
+        episode's own rows.  The truncated recurrence runs over the first n_step rows (mode 2 of fdql_vmap_flush_episodes), the
+        oldest row is copied to the reserved slot, then the whole-episode recurrence overwrites the returns of the episode's rows."""
+        ring = self.replay_buffer
+        dup = None
         if L > self.n_step:
-            raise NotImplementedError("vmap mode: episodes longer than nStep_return_steps (the reference's _pop duplicate, "
-                                      "nstep_return_vmap.py:50-57) are not supported")
+            ring.ensure_schema(cols)
+            dup = ring.reserve_rows(1)
+        begin = ring.add_rows(cols, episode_lengths=[L])
+        kw = dict(gamma=self.discount, done_quirk=self.reference_done_quirk)
+        if picks is not None:
+            rows = (begin + np.asarray(picks, dtype=np.int64)) % self._maxlen
+            ring.vmap_flush([begin], [L], pick_rows=rows, fill=True, returns=False, **kw)
+        if dup is not None:
+            ring.vmap_flush([begin], [self.n_step], fill=False, returns=True, **kw)
+            ring.q3_duplicate(begin, 1, dup, self.discount)
+        ring.vmap_flush([begin], [L], fill=False, returns=True, **kw)
+        return begin
 
     def add(self, experience):
         """Rows that already carry virtual_rewards / virtual_dones (nstep_return_vmap.py:23-35)."""
@@ -109,22 +128,13 @@ class NStepReturnVmap(ReplayMemoryWrapper):
         if experience[self.done_name]:
             rows = self.rows
             self._reset()
-            L = len(rows)
-            self._check_len(L)
             cols = stack_rows(rows)
             cols[self.return_name] = np.zeros_like(cols[self.reward_name])
-            begin = self.replay_buffer.add_rows(cols, episode_lengths=[L])
-            self.replay_buffer.vmap_flush([begin], [L], fill=False, returns=True, gamma=self.discount,
-                                          done_quirk=self.reference_done_quirk)
+            self._write_episode(cols, len(rows))
 
     def add_vmap_rows(self, cols, L, picks):
         """Episode-batched protocol used by HindsightVmapWrite: goals / rewards / dones and the returns in one device pass."""
         import torch
-        self._check_len(L)
         cols = dict(cols)
         cols[self.return_name] = torch.zeros_like(cols[self.reward_name])
-        begin = self.replay_buffer.add_rows(cols, episode_lengths=[L])
-        rows = (begin + np.asarray(picks, dtype=np.int64)) % self._maxlen
-        self.replay_buffer.vmap_flush([begin], [L], pick_rows=rows, fill=True, returns=True, gamma=self.discount,
-                                      done_quirk=self.reference_done_quirk)
-        return begin
+        return self._write_episode(cols, L, picks)

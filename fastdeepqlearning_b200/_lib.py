@@ -70,6 +70,7 @@ _SIGNATURES = {
     "fdql_tqc_loss_dev_alpha": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "fdql_quantile_huber": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "fdql_sac_min_target_loss": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p]),
+    "fdql_sac_min_target_loss_dev_alpha": (C.c_int, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _p, _p]),
     "fdql_hotpath_step_host": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _u32, _pp,
                                          _i32, _i32, _p, _p, _p, _f32, _p, _p, _p]),
 }

@@ -138,7 +138,7 @@ __device__ void build_link_records(const ArenaDev& A, int64_t s, int L, double g
     if (chain_ok && !nan) {
       for (int k = j + 1; k < L; ++k) {
         const int64_t rk = ring_row(s, k, A.capacity);
-        const float4 o = __ldg(A.scan + rk);
+        const float4 o = A.scan[rk];  // written earlier in this launch: a coherent load, not ld.global.nc
         if (__float_as_uint(o.x) == __float_as_uint(me.x) && __float_as_uint(o.y) == __float_as_uint(me.y) &&
             rows_equal(A, row, rk)) {
           next = k - j;
@@ -314,6 +314,53 @@ __global__ void __launch_bounds__(32) q3_duplicate_kernel(ArenaDev A, int64_t sr
   if (lane == 0) A.rec[dst * (int64_t)A.rec_stride + A.col_mc_return] = g0;
 }
 
+// The ring head has just moved over the rows before `r`.  If row r belongs to a committed episode that began before it, that
+// episode has lost its first rows: the survivors r .. ep_end still carry the old extents, whose start now lies in a newer
+// episode.  They become uncommitted (extents -1): never relabelled at sample time, gathered verbatim -- which is all the
+// reference can do with the rows of an episode it has partly overwritten.  One block.
+__global__ void __launch_bounds__(256) invalidate_survivors_kernel(ArenaDev A, int64_t r) {
+  __shared__ int sh[2];
+  if (threadIdx.x == 0) {
+    const float* rec = A.rec + r * (int64_t)A.rec_stride;
+    sh[0] = __float_as_int(rec[A.col_ep_start]);
+    sh[1] = __float_as_int(rec[A.col_ep_end]);
+  }
+  __syncthreads();
+  const int es = sh[0], ee = sh[1];
+  if (es < 0 || ee < 0 || es == (int)r) return;
+  const int64_t n = (int64_t)ee - r + (ee < r ? A.capacity : 0) + 1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float* rec = A.rec + ring_row(r, i, A.capacity) * (int64_t)A.rec_stride;
+    rec[A.col_ep_start] = __int_as_float(-1);
+    rec[A.col_ep_end] = __int_as_float(-1);
+  }
+}
+
+// called with the range [a->top, a->top + n) that is about to be (over)written, before the cursor advances
+static void note_overwrite(Arena* a, int64_t n) {
+  const int64_t cap = a->dev.capacity;
+  if (n <= 0 || n >= cap) {
+    a->pending_inval_row = -1;
+    if (n >= cap) a->rows_written = cap;
+    return;
+  }
+  const int64_t end = a->top + n;  // one past the last written row, before the modulo
+  const int64_t r = end % cap;
+  // row r holds data only if the ring has been written that far before
+  a->pending_inval_row = (a->rows_written >= cap || r < a->rows_written) ? r : -1;
+  if (end >= cap) a->rows_written = cap;
+  else if (end > a->rows_written) a->rows_written = end;
+}
+
+int flush_pending_invalidation(const Arena* ca, cudaStream_t st) {
+  Arena* a = const_cast<Arena*>(ca);
+  if (a->pending_inval_row < 0) return FDQL_OK;
+  invalidate_survivors_kernel<<<1, 256, 0, st>>>(a->dev, a->pending_inval_row);
+  a->pending_inval_row = -1;
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
+}
+
 static void advance_cursor(Arena* a, int64_t n) {
   const int64_t cap = a->dev.capacity, top = a->top;
   int64_t mx;
@@ -343,6 +390,7 @@ int fdql_arena_create(int64_t capacity, int32_t n_keys, const int32_t* widths, c
   memset(static_cast<Arena*>(a), 0, sizeof(Arena));
   a->n_keys = n_keys;
   a->device = device;
+  a->pending_inval_row = -1;
   ArenaDev& D = a->dev;
   D.capacity = capacity;
   D.col_reward = D.col_task_done = D.col_ep_done = D.col_ep_step = D.col_mc_return = -1;
@@ -447,6 +495,8 @@ int fdql_arena_set_cursor(fdql_arena* a, int64_t top, int64_t len) {
   FDQL_REQUIRE(top >= 0 && top < a->dev.capacity && len >= 0 && len <= a->dev.capacity, "cursor out of range");
   a->top = top;
   a->len = len;
+  a->pending_inval_row = -1;
+  if (len + 1 > a->rows_written) a->rows_written = len + 1 > a->dev.capacity ? a->dev.capacity : len + 1;
   return FDQL_OK;
 }
 
@@ -510,6 +560,8 @@ int fdql_arena_append(fdql_arena* a, int64_t n_rows, const float* const* src, vo
   int64_t blocks = (n_rows * widest + 255) / 256;
   const int64_t cap_blocks = (int64_t)a->num_sms * 8;
   if (blocks > cap_blocks) blocks = cap_blocks;
+  note_overwrite(a, n_rows);
+  { int rc = flush_pending_invalidation(a, (cudaStream_t)stream); if (rc) return rc; }
   append_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a->dev, sp, n_rows, a->top);
   FDQL_CUDA(cudaGetLastError());
   advance_cursor(a, n_rows);
@@ -546,6 +598,7 @@ int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t ds
   FDQL_REQUIRE(a != nullptr, "null arena");
   FDQL_REQUIRE(src_row >= 0 && src_row < a->dev.capacity && dst_row >= 0 && dst_row < a->dev.capacity, "row out of range");
   FDQL_REQUIRE(n_step >= 1 && n_step <= a->dev.capacity, "bad n_step");
+  { int rc = flush_pending_invalidation(a, (cudaStream_t)stream); if (rc) return rc; }
   q3_duplicate_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->dev, src_row, n_step, dst_row, gamma);
   FDQL_CUDA(cudaGetLastError());
   return FDQL_OK;
@@ -554,6 +607,7 @@ int fdql_q3_duplicate(fdql_arena* a, int64_t src_row, int32_t n_step, int64_t ds
 int fdql_arena_reserve(fdql_arena* a, int64_t n_rows, int64_t* first_row) {
   FDQL_REQUIRE(a != nullptr && n_rows >= 0 && n_rows <= a->dev.capacity, "bad reserve");
   if (first_row) *first_row = a->top;
+  note_overwrite(a, n_rows);  // no stream here: the survivors are invalidated by the next call that has one
   advance_cursor(a, n_rows);
   return FDQL_OK;
 }
@@ -576,6 +630,8 @@ int fdql_commit_episodes(fdql_arena* a, int32_t n_eps, const int64_t* ep_begin, 
   FDQL_REQUIRE(ep_begin != nullptr && ep_len != nullptr, "null episode table");
   RewardSpec rs;
   int rc = upload_reward_spec(a, reward_op, reward_params_host, n_params, (cudaStream_t)stream, &rs);
+  if (rc) return rc;
+  rc = flush_pending_invalidation(a, (cudaStream_t)stream);
   if (rc) return rc;
   int lpr = 1;
   if (a->dev.wide_ag >= 0) {
@@ -607,6 +663,8 @@ int fdql_her_flush_episodes(fdql_arena* a, int32_t n_eps, const int64_t* src_beg
   FDQL_REQUIRE(a->dev.wide[a->dev.wide_ag].vecs <= 32, "goal wider than 128 floats is not supported");
   RewardSpec rs;
   int rc = upload_reward_spec(a, reward_op, reward_params_host, n_params, (cudaStream_t)stream, &rs);
+  if (rc) return rc;
+  rc = flush_pending_invalidation(a, (cudaStream_t)stream);
   if (rc) return rc;
   const int lpr = lanes_per_row(a->dev.wide[a->dev.wide_ag].vecs);
   const unsigned blocks = (unsigned)(((int64_t)n_eps * 32 + 255) / 256);

@@ -169,7 +169,11 @@ struct Arena {
   double link_gamma;    // discount the link records were built with
   int link_state;       // 0: none yet, 1: link_gamma valid, 2: episodes were committed with different discounts (links unusable)
   int num_sms;
+  int64_t rows_written;        // rows [0, rows_written) of the ring have held data (capacity once it has wrapped)
+  int64_t pending_inval_row;   // first row behind the write head whose episode may have lost its beginning (-1: none); see arena.cu
 };
+
+int flush_pending_invalidation(const Arena* a, cudaStream_t st);
 
 int upload_reward_spec(const Arena* a, int32_t op, const float* params_host, int32_t n_params, cudaStream_t st,
                        RewardSpec* out);

@@ -76,10 +76,12 @@ __device__ __forceinline__ void eval_chunk(const ArenaDev& A, const RewardSpec& 
         if (vok) {
           const float* w = rs.params + 2 + 4 * v;
           const int n = min(4, ag.width - 4 * v);
-          const float da[4] = {a[q].x - g[q].x, a[q].y - g[q].y, a[q].z - g[q].z, a[q].w - g[q].w};
+          // the reference evaluates the functor on float64 goals (eleurent_parking.py:53): difference, weighting and sum in fp64
+          const double da[4] = {(double)a[q].x - (double)g[q].x, (double)a[q].y - (double)g[q].y, (double)a[q].z - (double)g[q].z,
+                                (double)a[q].w - (double)g[q].w};
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            if (c < n) acc += (double)fabsf(da[c]) * (double)w[c];
+            if (c < n) acc += fabs(da[c]) * (double)w[c];
         }
 #pragma unroll
         for (int m = LPR / 2; m >= 1; m >>= 1) acc += shfl_xor_f64(acc, m);

@@ -1161,6 +1161,10 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
                          const int64_t* goal_rows, int32_t reward_op, const float* reward_params_host, int32_t n_params,
                          double gamma, uint32_t opts, int32_t batch_for_weight, float* const* out, float* aux_mask,
                          float* aux_contig, float* aux_weight, cudaStream_t st, const DrawSpec* draw) {
+  {
+    const int rc = flush_pending_invalidation(a, st);
+    if (rc) return rc;
+  }
   GatherArgs g;
   memset(&g, 0, sizeof(g));
   if (draw != nullptr) {
@@ -1356,6 +1360,10 @@ int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_
   if (n == 0) return FDQL_OK;
   const int64_t range = a->len - T;  // T==0: flat sample() over [0, len)
   FDQL_REQUIRE(range > 0, "empty start range");
+  {
+    const int rc = flush_pending_invalidation(a, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   sample_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->dev, n, range, goal_mode, relabel_prob,
                                                                                        seed, counter,
                                                                                        reinterpret_cast<unsigned long long*>(counter_dev),

@@ -32,6 +32,7 @@ struct TqcArgs {
   float* td_target;
   double* stats;
   const float* alpha_dev;  // when set, overrides alpha
+  int32_t grp_red_alias;   // group kernel: the per-lane partial sums live in the dead rows of the q_pred staging (see GrpCfg)
 };
 
 // ---- warp-level bitonic sort of 32*VPL values; sorted position of (lane, slot) is i = lane*VPL + slot ----------------
@@ -342,21 +343,26 @@ constexpr int kGrpE = 16;
 template <int NT>
 struct GrpCfg {
   static constexpr int E = kGrpE;
-  static constexpr int kWarps = NT >= 128 ? 16 : NT >= 64 ? 12 : 8;  // one block per SM (shared memory and registers fill it)
   static constexpr int LPT = NT / E;    // lanes per transition in phase A
   static constexpr int G = 32 / LPT;    // transitions per warp and round
   static constexpr int R = NT / 32;     // table rows = predicted atoms per lane in phase B
   static constexpr int TP = NT + 1;     // table pitch in entries
   static constexpr int kZY = G * TP;    // floats: staged rows of next_z, later the G sorted tables (two buffers)
   static constexpr int kSc = 8;         // per-transition scalars
-  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars |
   static constexpr int kRedPitch = 36;  // rows of 32 per-lane partial sums, 16-byte aligned, consecutive rows 4 banks apart
-  static constexpr int kRed = 3 * G * kRedPitch;
+  static constexpr int kRed = 3 * G * kRedPitch;  // [G][3] rows: {loss, sum q, sum q^2} of transition t at row 3 t + quantity
   static constexpr int kIn = 8 * G;     // staged per-transition inputs {reward, mask, log_pi, mc_return, grad_scale}[G], two buffers
   static constexpr int kBar = 8;        // three mbarriers (next_z buffer 0 / 1, q_pred) + padding
-  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | red | in[0] | in[1] | mbarriers |
-  static constexpr int kWarpFloats = 2 * kZY + 2 * kZY + G * NT + kSc * G + kRed + 2 * kIn + kBar;
-  static_assert(kZY % 4 == 0 && kWarpFloats % 4 == 0, "16-byte alignment of the staging buffers");
+  // | zy[0] | zy[1] | QT float2[G*TP] | q_pred rows | scalars | in[0] | in[1] | mbarriers | (red) |
+  // The per-lane partial sums of transition t are parked when its phase B ends; by then rows 0..t of the q_pred staging are dead, so
+  // with at least 3 * kRedPitch predicted atoms per row `red` lives there (rows 3 t .. 3 t + 2 end before row t + 1 begins) and the
+  // block holds a fifth warp per scheduler in the shared memory that frees; narrower rows keep a separate `red`.
+  static constexpr int kWarpFloatsAlias = 2 * kZY + 2 * kZY + G * NT + kSc * G + 2 * kIn + kBar;
+  static constexpr int kWarpFloats = kWarpFloatsAlias + kRed;
+  static constexpr int kWarps = NT >= 128 ? 16 : NT >= 64 ? 12 : 8;       // one block per SM (shared memory fills it)
+  static constexpr int kWarpsAlias = NT >= 128 ? 20 : NT >= 64 ? 12 : 8;
+  static constexpr int kMaxWarps = kWarpsAlias;
+  static_assert(kZY % 4 == 0 && kWarpFloats % 4 == 0 && kWarpFloatsAlias % 4 == 0, "16-byte alignment of the staging buffers");
 };
 
 // (LS = lane stride of a transition's lanes: sub-lane sl of transition grp is lane sl * LS + grp)
@@ -540,7 +546,7 @@ constexpr int kGrpLb = 1, kGrpStats = 2, kGrpFull = 4;  // kernel flavours: lowe
                                                           // every atom slot but the last one holds 32 real atoms (n_atoms > 32 * (R - 1))
 
 template <int NT, int FLAGS>
-__global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
+__global__ void __launch_bounds__(GrpCfg<NT>::kMaxWarps * 32, 1) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
   using C = GrpCfg<NT>;
   constexpr int E = C::E, LPT = C::LPT, G = C::G, R = C::R, TP = C::TP;
   constexpr bool LB = (FLAGS & kGrpLb) != 0, STATS = (FLAGS & kGrpStats) != 0, FULL = (FLAGS & kGrpFull) != 0;
@@ -548,14 +554,15 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
   extern __shared__ __align__(16) float grp_smem[];
   __shared__ double sm_stats[3];
   const int lane = lane_id(), wib = threadIdx.x >> 5;
-  float* W = grp_smem + wib * C::kWarpFloats;
+  const bool red_alias = a.grp_red_alias != 0;
+  float* W = grp_smem + wib * (red_alias ? C::kWarpFloatsAlias : C::kWarpFloats);
   float2* QT = reinterpret_cast<float2*>(W + 2 * C::kZY);
   float* qs = W + 4 * C::kZY;
   float* sc = qs + G * NT;
-  float* red = sc + C::kSc * G;  // [3 * G][kRedPitch]: per-lane partial sums, one row per (quantity, transition)
-  float* inb = red + C::kRed;    // [2][5][G] staged per-transition inputs
+  float* inb = sc + C::kSc * G;  // [2][5][G] staged per-transition inputs
+  float* red = red_alias ? qs : W + C::kWarpFloatsAlias;  // [G][3][kRedPitch]: per-lane partial sums, one row per (transition, quantity)
   const uint32_t aW = (uint32_t)__cvta_generic_to_shared(W), aQ = aW + 8 * C::kZY;
-  const uint32_t aBar = aW + 4 * (uint32_t)(C::kWarpFloats - C::kBar);  // + 0 / 8: next_z buffers, + 16: q_pred
+  const uint32_t aBar = aW + 4 * (uint32_t)(C::kWarpFloatsAlias - C::kBar);  // + 0 / 8: next_z buffers, + 16: q_pred
   if (lane == 0) {
     mbar_init(aBar, 1);
     mbar_init(aBar + 8, 1);
@@ -832,10 +839,11 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
           s2 = fmaf(qc, qc, s2);
         }
       }
-      red[(0 * G + t) * C::kRedPitch + lane] = fmaf(acc, inv_nk, lbacc * inv_n);
+      __syncwarp();  // every lane has read row t of the q_pred staging (aliased layout: `red` overwrites its head)
+      red[(3 * t + 0) * C::kRedPitch + lane] = fmaf(acc, inv_nk, lbacc * inv_n);
       if constexpr (STATS) {
-        red[(1 * G + t) * C::kRedPitch + lane] = s1;
-        red[(2 * G + t) * C::kRedPitch + lane] = s2;
+        red[(3 * t + 1) * C::kRedPitch + lane] = s1;
+        red[(3 * t + 2) * C::kRedPitch + lane] = s2;
       }
     }
     __syncwarp();
@@ -847,7 +855,7 @@ __global__ void __launch_bounds__(GrpCfg<NT>::kWarps * 32, 1) tqc_loss_group_ker
       float sums[NQ];
 #pragma unroll
       for (int qn = 0; qn < NQ; ++qn) {
-        const float4* rrow = reinterpret_cast<const float4*>(red + (qn * G + t) * C::kRedPitch + part * G);
+        const float4* rrow = reinterpret_cast<const float4*>(red + (3 * t + qn) * C::kRedPitch + part * G);
         float sacc = 0.f;
 #pragma unroll
         for (int k = 0; k < G / 4; ++k) {
@@ -903,6 +911,7 @@ struct SacArgs {
   float* loss;
   float* grad_q;
   double* stats;
+  const float* alpha_dev;  // when set, overrides alpha
 };
 
 __global__ void __launch_bounds__(256) sac_min_target_kernel(const __grid_constant__ SacArgs a) {
@@ -913,11 +922,12 @@ __global__ void __launch_bounds__(256) sac_min_target_kernel(const __grid_consta
   if (a.stats && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
   if (a.stats) __syncthreads();
   double st_sum = 0.0, st_var = 0.0, st_viol = 0.0;
+  const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
   for (int64_t m = (int64_t)blockIdx.x * 8 + wib; m < a.M; m += nwarps) {
     const float* __restrict__ zrow = a.target_z + m * n;
     const float* __restrict__ qrow = a.q_pred + m * n;
-    const float ent = a.next_log_pi ? __fmul_rn(a.alpha, -__ldg(a.next_log_pi + m)) : 0.f;
+    const float ent = a.next_log_pi ? __fmul_rn(alpha, -__ldg(a.next_log_pi + m)) : 0.f;
     float zmin = CUDART_INF_F;
     for (int j = lane; j < n; j += 32) {
       float z = ld_stream1(zrow + j);
@@ -992,21 +1002,35 @@ static int num_sms() {
 
 int g_tqc_warp_kernel = 0;  // test hook: 1 = always the warp-per-transition kernel
 
+int g_tqc_grp_warps = 0;  // test / tuning hook: warps per block of the group kernel (0 = automatic)
+
 template <int NT, int FLAGS>
-static int launch_tqc_group_f(const TqcArgs& a, cudaStream_t st) {
+static int launch_tqc_group_f(const TqcArgs& a0, cudaStream_t st) {
   using C = GrpCfg<NT>;
+  TqcArgs a = a0;
   const int64_t n_groups = (a.M + C::G - 1) / C::G;
+  // the per-lane sums of transition t (three rows) fit into the dead q_pred rows 0..t when a row is at least as long as they are
+  a.grp_red_alias = a.n_atoms >= 3 * C::kRedPitch ? 1 : 0;
+  const int auto_warps = a.grp_red_alias ? C::kWarpsAlias : C::kWarps;
+  const int full_warps = g_tqc_grp_warps > 0 && g_tqc_grp_warps < auto_warps ? g_tqc_grp_warps : auto_warps;
+  const int warp_floats = a.grp_red_alias ? C::kWarpFloatsAlias : C::kWarpFloats;
   // large batches: one block per SM (its warps share a work counter, see the kernel); batches of at most two rounds per warp: the
   // same kernel in 4-warp blocks, which leave room on an SM for kernels of other streams (the learner's prefetch pattern)
-  const bool small = n_groups <= (int64_t)2 * C::kWarps * num_sms();
-  const int kGrpWarps = small ? 4 : C::kWarps;
-  const size_t smem = (size_t)kGrpWarps * C::kWarpFloats * sizeof(float);
-  static int per_sm_cached[2] = {0, 0};
-  int& per_sm = per_sm_cached[small ? 1 : 0];
+  const bool small = n_groups <= (int64_t)2 * full_warps * num_sms();
+  const int kGrpWarps = small ? 4 : full_warps;
+  const size_t smem = (size_t)kGrpWarps * warp_floats * sizeof(float);
+  static int per_sm_cached[2][2] = {{0, 0}, {0, 0}};
+  static int warps_cached = 0;
+  if (warps_cached != full_warps) {
+    per_sm_cached[0][0] = per_sm_cached[0][1] = per_sm_cached[1][0] = per_sm_cached[1][1] = 0;
+    warps_cached = full_warps;
+    constexpr size_t kNeed = sizeof(float) * (C::kWarps * C::kWarpFloats > C::kWarpsAlias * C::kWarpFloatsAlias
+                                                  ? C::kWarps * C::kWarpFloats
+                                                  : C::kWarpsAlias * C::kWarpFloatsAlias);
+    FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeed));
+  }
+  int& per_sm = per_sm_cached[small ? 1 : 0][a.grp_red_alias];
   if (per_sm == 0) {
-    if (per_sm_cached[0] == 0 && per_sm_cached[1] == 0)
-      FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)C::kWarps * C::kWarpFloats * sizeof(float))));
     FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tqc_loss_group_kernel<NT, FLAGS>, kGrpWarps * 32, smem));
     if (per_sm < 1) per_sm = 1;
   }
@@ -1060,8 +1084,9 @@ using namespace fdql;
 extern "C" {
 
 int fdql_debug_tqc_warp_kernel(int on) {
-  const int old = g_tqc_warp_kernel;
-  g_tqc_warp_kernel = on;
+  const int old = g_tqc_warp_kernel | (g_tqc_grp_warps << 8);
+  g_tqc_warp_kernel = on & 1;
+  g_tqc_grp_warps = (on >> 8) & 0xff;  // bits 8..15: warps per block of the group kernel (0 = automatic)
   return old;
 }
 
@@ -1077,7 +1102,7 @@ int fdql_tqc_loss(int64_t M, int32_t n_atoms, int32_t n_drop, const float* next_
   if (M == 0) return FDQL_OK;
   FDQL_REQUIRE(next_z && q_pred && reward && mask, "null input");
   TqcArgs a{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q,
-            td_target, stats, nullptr};
+            td_target, stats, nullptr, 0};
   return launch_tqc(a, (cudaStream_t)stream);
 }
 
@@ -1092,7 +1117,7 @@ int fdql_tqc_loss_dev_alpha(int64_t M, int32_t n_atoms, int32_t n_drop, const fl
   if (M == 0) return FDQL_OK;
   FDQL_REQUIRE(next_z && q_pred && reward && mask && alpha_dev, "null input");
   TqcArgs a{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, 0.f, gamma, loss, grad_q,
-            td_target, stats, alpha_dev};
+            td_target, stats, alpha_dev, 0};
   return launch_tqc(a, (cudaStream_t)stream);
 }
 
@@ -1104,8 +1129,17 @@ int fdql_quantile_huber(int64_t M, int32_t n_quantiles, int32_t n_samples, const
   if (M == 0) return FDQL_OK;
   FDQL_REQUIRE(quantiles && samples, "null input");
   TqcArgs a{M, n_quantiles, n_samples, 0, samples, quantiles, nullptr, nullptr, nullptr, nullptr, grad_scale, 1.f, 1.f,
-            loss, grad_q, nullptr, nullptr, nullptr};
+            loss, grad_q, nullptr, nullptr, nullptr, 0};
   return launch_tqc(a, (cudaStream_t)stream);
+}
+
+static int launch_sac(const SacArgs& a, cudaStream_t st) {
+  int64_t blocks = (a.M + 7) / 8;
+  const int64_t max_blocks = (int64_t)num_sms() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  sac_min_target_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  FDQL_CUDA(cudaGetLastError());
+  return FDQL_OK;
 }
 
 int fdql_sac_min_target_loss(int64_t M, int32_t n_atoms, const float* target_z, const float* q_pred, const float* next_log_pi,
@@ -1114,13 +1148,19 @@ int fdql_sac_min_target_loss(int64_t M, int32_t n_atoms, const float* target_z, 
   FDQL_REQUIRE(M >= 0 && n_atoms >= 1, "bad sizes");
   if (M == 0) return FDQL_OK;
   FDQL_REQUIRE(target_z && q_pred && reward && mask, "null input");
-  SacArgs a{M, n_atoms, target_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q, stats};
-  int64_t blocks = (M + 7) / 8;
-  const int64_t max_blocks = (int64_t)num_sms() * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
-  sac_min_target_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
-  FDQL_CUDA(cudaGetLastError());
-  return FDQL_OK;
+  SacArgs a{M, n_atoms, target_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, gamma, loss, grad_q, stats, nullptr};
+  return launch_sac(a, (cudaStream_t)stream);
+}
+
+int fdql_sac_min_target_loss_dev_alpha(int64_t M, int32_t n_atoms, const float* target_z, const float* q_pred,
+                                       const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,
+                                       const float* grad_scale, const float* alpha_dev, float gamma, float* loss, float* grad_q,
+                                       double* stats, void* stream) {
+  FDQL_REQUIRE(M >= 0 && n_atoms >= 1, "bad sizes");
+  if (M == 0) return FDQL_OK;
+  FDQL_REQUIRE(target_z && q_pred && reward && mask && alpha_dev, "null input");
+  SacArgs a{M, n_atoms, target_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, 0.f, gamma, loss, grad_q, stats, alpha_dev};
+  return launch_sac(a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -22,7 +22,7 @@ __device__ __forceinline__ void eval_row_thread(const RewardSpec& rs, const floa
                                                 float& reward, bool& done) {
   if (rs.op == FDQL_REWARD_WEIGHTED_PNORM) {
     double acc = 0.0;
-    for (int c = 0; c < G; ++c) acc += (double)fabsf(a[c] - g[c]) * (double)rs.params[2 + c];
+    for (int c = 0; c < G; ++c) acc += fabs((double)a[c] - (double)g[c]) * (double)rs.params[2 + c];
     const double r = -pow(acc, (double)rs.params[0]);
     reward = (float)r;
     done = r > -(double)rs.params[1];

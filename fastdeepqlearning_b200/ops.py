@@ -101,9 +101,15 @@ def sac_min_target_loss(q_pred, target_z, next_log_pi, reward, mask, mc_return, 
         loss = torch.empty(M, dtype=torch.float32, device=q.device)
         grad = torch.empty_like(q)
         stats = torch.zeros(4, dtype=torch.float64, device=q.device) if want_stats else None
-        L.check(L.lib().fdql_sac_min_target_loss(M, n, _p(z), _p(q), _p(_flat(next_log_pi)), _p(_flat(reward)), _p(_flat(mask)),
-                                                 _p(_flat(mc_return)), _p(_flat(grad_scale)), float(alpha), float(gamma),
-                                                 _p(loss), _p(grad), _p(stats), _stream(q)))
+        if torch.is_tensor(alpha):  # temperature kept on the device (no host sync; CUDA-graph safe)
+            a_dev = alpha.detach().to(device=q.device, dtype=torch.float32).reshape(-1)
+            L.check(L.lib().fdql_sac_min_target_loss_dev_alpha(M, n, _p(z), _p(q), _p(_flat(next_log_pi)), _p(_flat(reward)),
+                                                               _p(_flat(mask)), _p(_flat(mc_return)), _p(_flat(grad_scale)), _p(a_dev),
+                                                               float(gamma), _p(loss), _p(grad), _p(stats), _stream(q)))
+        else:
+            L.check(L.lib().fdql_sac_min_target_loss(M, n, _p(z), _p(q), _p(_flat(next_log_pi)), _p(_flat(reward)), _p(_flat(mask)),
+                                                     _p(_flat(mc_return)), _p(_flat(grad_scale)), float(alpha), float(gamma),
+                                                     _p(loss), _p(grad), _p(stats), _stream(q)))
     out = {"loss": loss.reshape(lead + (1,)), "grad": grad.reshape(lead + (n,))}
     if want_stats:
         out["stats"] = stats

@@ -222,6 +222,13 @@ int fdql_sac_min_target_loss(int64_t M, int32_t n_atoms, const float* target_z, 
                              const float* grad_scale, float alpha, float gamma, float* loss, float* grad_q,
                              double* stats, void* stream);
 
+/* same, with the entropy temperature read from device memory (alpha_dev[0]) at kernel time: no host read of curr_alpha in the
+ * learner step (soft_actor_critic.py:40,151 keeps it as a Python float), CUDA-graph capturable */
+int fdql_sac_min_target_loss_dev_alpha(int64_t M, int32_t n_atoms, const float* target_z, const float* q_pred,
+                                       const float* next_log_pi, const float* reward, const float* mask, const float* mc_return,
+                                       const float* grad_scale, const float* alpha_dev, float gamma, float* loss, float* grad_q,
+                                       double* stats, void* stream);
+
 /* Host-buffer form of one whole pass (what a non-CUDA caller binds): streams and critic outputs come from host
  * memory (pinned for the copies to overlap), loss [ (T-1)*n ] and grad_q [ (T-1)*n, n_atoms ] go back to host memory;
  * the gathered batch stays in HBM in out[] for the device-side MLPs.  Transition m = t*n + b pairs row t (q_pred) with

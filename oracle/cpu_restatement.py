@@ -325,6 +325,13 @@ def vmap_write_episode(cols, picks_chrono, reward_fn, gamma=None, reference_done
     return out
 
 
+def vmap_pop_returns(virtual_rewards, virtual_dones, n_step, gamma, reference_done_quirk=True):
+    """NStepReturnVmap._pop (nstep_return_vmap.py:50-57): when the episode buffer reaches n_step rows the oldest row is emitted with
+    the recurrence evaluated over those n_step rows only -- and is not removed (quirk Q3), so it is stored again at the flush.
+    Returns the [V+1] truncated returns of the oldest row (chronological inputs [L, V+1], L > n_step)."""
+    return vmap_returns(np.asarray(virtual_rewards)[:n_step], np.asarray(virtual_dones)[:n_step], gamma, reference_done_quirk)[0]
+
+
 def vmap_read_select(batch, column):
     """HindsightVmapRead.temporal_sample + cleanup (her_vmap.py:104-123) on a gathered [T, B, ...] batch."""
     out = {k: v for k, v in batch.items() if not k.startswith("virtual_")}
@@ -497,6 +504,20 @@ def sac_min_target_loss(q_pred, target_z, next_log_pi, reward, mask, mc_return, 
         summaries["mc_constraint_violations"] = float((~inactive).sum()) / lb.size
     n = q.shape[-1]
     return l1.mean(-1, keepdims=True), g / n, summaries
+
+
+def sac_bootstrap_bound(q_pred, target_z, next_log_pi, reward, mask, alpha, gamma, use_max_entropy_q=True, dtype=np.float64):
+    """soft_actor_critic.py:102-132: minibatch n-step bootstrap bound.  Inputs [T-1, B, .]; returns ([B, CQ] bound, d sum(bound*w)/d q_pred
+    is -w where the bound is active, on q_pred[0] only).  bound = prod_t mask * relu(sum_t gamma^t r_t + gamma^(T-1) td_target[-1] - q_pred[0])."""
+    z = np.asarray(target_z, dtype)
+    if use_max_entropy_q:
+        z = z + dtype(alpha) * (-np.asarray(next_log_pi, dtype))
+    td = np.asarray(reward, dtype) + np.asarray(mask, dtype) * dtype(gamma) * z.min(-1, keepdims=True)
+    Tm1 = z.shape[0]
+    g = (dtype(gamma) ** np.arange(Tm1)).reshape(-1, 1, 1)
+    ret = (np.asarray(reward, dtype) * g).sum(0)
+    valid = np.asarray(mask, dtype).prod(0)
+    return valid * np.maximum((ret + dtype(gamma) ** Tm1 * td[-1]) - np.asarray(q_pred, dtype)[0], 0)
 
 
 # torch-CPU forms used as the timed CPU baseline (same operator sequence as the reference) -------

@@ -1,0 +1,445 @@
+"""GPU parity added in round 2, every case against outputs of the unmodified reference (tests/golden/{her_q3,pnorm,vmap_pop,
+learner_step,sac_bootstrap}.npz, oracle/make_goldens_r2.py) or against the pinned oracle:
+  * hindsight over an NStepReturn shorter than the episode (quirk Q3 under HER), through Replay.make, one dict at a time;
+  * the parking reward functor (weighted p-norm) at write time, in the vmap chain and at sample time;
+  * vmap episodes longer than nStep_return_steps (NStepReturnVmap._pop);
+  * one whole learner update (loss, every gradient, Adam step, target update) on recorded weights, batch and policy noise;
+  * the minibatch n-step bootstrap bound of SoftActorCritic.q_loss;
+  * link records on episodes of 1000 and of more than 32767 rows; small rings; partly overwritten episodes."""
+import random
+import types
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import cpu_restatement as O
+
+pytestmark = pytest.mark.gpu
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def _feed(head, g, name, gdt):
+    off = 0
+    for L in g[f"{name}_lengths"]:
+        for t in range(L):
+            i = off + t
+            head.add({"obs_1d": g[f"{name}_in_obs"][i], "action": g[f"{name}_in_action"][i],
+                      "achieved_goal": g[f"{name}_in_ag"][i].astype(gdt), "desired_goal": g[f"{name}_in_dg"][i].astype(gdt),
+                      "reward": float(g[f"{name}_in_reward"][i]), "task_done": bool(g[f"{name}_in_task_done"][i]),
+                      "episode_done": t == L - 1, "episode_step": t, "info": {}})
+        off += L
+
+
+def _make(fdql, mode, op, n_step, gamma, replay_size=4096):
+    from fastdeepqlearning_b200 import Replay
+    conf = types.SimpleNamespace(replay_size=replay_size, batch_size=8, temporal_len=2, num_instances=1, use_nStep_lowerbounds=True,
+                                 nStep_return_steps=n_step, gamma=gamma, use_squashed_rewards=False, use_HER=True, her_mode=mode,
+                                 training_device="cuda:0")
+    return Replay.make(conf, compute_reward=op)
+
+
+# ------------------------------------------------------------------------------------------------ quirk Q3 under hindsight
+@pytest.mark.parametrize("mode", ["final", "random"])
+def test_her_over_short_nstep_reference_row_stream(fdql, mode, monkeypatch):
+    """her.py:36-46 over nstep_return.py:33-34,50-57 with n_step = 4 < episode length: the ring must hold, per long episode,
+    dup, the real rows, dup', the hindsight rows -- copied from and counted from the episode's own first row, not the duplicate's."""
+    g = load_golden("her_q3")
+    read, write = _make(fdql, mode, fdql.RewardOp.bitflip(), int(g["n_step"]), float(g["gamma"]))
+    it = iter(list(g["bitflip_picks"]))
+    monkeypatch.setattr(random, "choice", lambda seq: seq[len(seq) - 1 - next(it)])
+    _feed(write[0], g, "bitflip", np.int64)
+    ring = read[0]
+    n = len(ring)
+    lengths = g["bitflip_lengths"]
+    assert n == 2 * lengths.sum() + 2 * int((lengths > int(g["n_step"])).sum())
+    mem = {k: npy(v)[:n] for k, v in ring.memory.items()}
+    for k in ("obs_1d", "action", "achieved_goal", "desired_goal", "task_done", "episode_done", "episode_step", "reward", "mc_return"):
+        np.testing.assert_array_equal(mem[k], g[f"bitflip_{mode}_{k}"].astype(np.float32), err_msg=k)
+
+
+# ------------------------------------------------------------------------------------------------ parking functor
+def _parking_op(fdql, g):
+    return fdql.RewardOp.weighted_pnorm(list(g["weights"]), float(g["success"]), float(g["p"]))
+
+
+@pytest.mark.parametrize("mode", ["final", "random"])
+def test_parking_functor_write_time_reference_rows(fdql, mode, monkeypatch):
+    """Env/eleurent_parking.py:42-55 as FDQL_REWARD_WEIGHTED_PNORM through fdql_her_flush_episodes vs the reference's stored rows:
+    goals, dones and re-based steps bit for bit, rewards and returns to 1e-6 (fp64 functor, fp32 store on both sides)."""
+    g = load_golden("pnorm")
+    read, write = _make(fdql, mode, _parking_op(fdql, g), 1000, float(g["gamma"]))
+    it = iter(list(g["parking_picks"]))
+    monkeypatch.setattr(random, "choice", lambda seq: seq[len(seq) - 1 - next(it)])
+    _feed(write[0], g, "parking", np.float64)
+    ring = read[0]
+    n = len(ring)
+    assert n == 2 * g["parking_lengths"].sum()
+    mem = {k: npy(v)[:n] for k, v in ring.memory.items()}
+    for k in ("obs_1d", "action", "achieved_goal", "desired_goal", "task_done", "episode_done", "episode_step"):
+        np.testing.assert_array_equal(mem[k], g[f"parking_{mode}_{k}"].astype(np.float32), err_msg=k)
+    assert mem["task_done"].sum() > 0
+    np.testing.assert_allclose(mem["reward"], g[f"parking_{mode}_reward"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mem["mc_return"], g[f"parking_{mode}_mc_return"], rtol=1e-5, atol=1e-6)
+
+
+def test_parking_functor_vmap_chain_reference_rows(fdql, monkeypatch):
+    from fastdeepqlearning_b200 import Replay
+    from fastdeepqlearning_b200.Replay import wrappers as W
+    g = load_golden("pnorm")
+    V = int(g["V"])
+    lengths = g["vmap_lengths"]
+    picks = iter(g["vmap_picks_deque"].reshape(len(lengths), V))
+    shard = Replay.AsyncReplayMemory(4096, 8, 2)
+    her = W.HindsightVmapWrite(W.NStepReturnVmap(shard, 1000, float(g["gamma"]), reference_done_quirk=True), _parking_op(fdql, g),
+                               num_virtual_goals=V)
+    monkeypatch.setattr(np.random, "randint", lambda low, high=None, size=None: np.asarray(next(picks)))
+    _feed(her, g, "vmap", np.float32)
+    monkeypatch.undo()
+    n = int(lengths.sum())
+    assert len(shard) == n
+    mem = {k: npy(v)[:n] for k, v in shard.replay.memory.items()}
+    np.testing.assert_array_equal(mem["virtual_goals"].reshape(n, -1), g["vmap_virtual_goals"].reshape(n, -1).astype(np.float32))
+    np.testing.assert_array_equal(mem["virtual_dones"], g["vmap_virtual_dones"].astype(np.float32))
+    np.testing.assert_allclose(mem["virtual_rewards"], g["vmap_virtual_rewards"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mem["virtual_mc_return"], g["vmap_virtual_mc_return"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("T", [1, 3])
+def test_parking_functor_sample_time_vs_oracle(fdql, T):
+    """Sample-time relabelling with a non-equality functor (the full-vector relabel path) vs oracle.sample_time_relabel."""
+    from fastdeepqlearning_b200 import Replay
+    g = load_golden("pnorm")
+    fn = O.make_reward_weighted_pnorm(g["weights"], float(g["success"]), float(g["p"]))
+    gamma = float(g["gamma"])
+    lengths = g["parking_lengths"]
+    N = int(lengths.sum())
+    ends = np.cumsum(lengths) - 1
+    starts_ep = ends - lengths + 1
+    ep_of = np.repeat(np.arange(len(lengths)), lengths)
+    real_mc = O.segmented_returns(g["parking_in_reward"], np.isin(np.arange(N), ends), gamma)
+    cols = {"obs_1d": g["parking_in_obs"], "achieved_goal": g["parking_in_ag"].astype(np.float32),
+            "desired_goal": g["parking_in_dg"].astype(np.float32), "reward": g["parking_in_reward"].reshape(-1, 1).astype(np.float32),
+            "task_done": g["parking_in_task_done"].reshape(-1, 1).astype(np.float32),
+            "episode_done": np.isin(np.arange(N), ends).reshape(-1, 1).astype(np.float32),
+            "episode_step": (np.arange(N) - starts_ep[ep_of]).reshape(-1, 1).astype(np.float32), "mc_return": real_mc.reshape(-1, 1)}
+    ring = Replay.ReplayMemory(N + 3, 16, T)
+    ring.set_reward_op(_parking_op(fdql, g), gamma)
+    ring.add_rows(cols, episode_lengths=lengths)
+    rng = np.random.default_rng(3)
+    B = 300
+    starts = rng.integers(0, N - T, B)
+    flags = rng.random(B) < 0.8
+    goal_rows = np.array([rng.integers(s, ends[ep_of[s]] + 1) for s in starts])
+    want = O.sample_time_relabel(cols, starts, T, flags, goal_rows, starts_ep[ep_of], ends[ep_of], fn, gamma)
+    got = ring.temporal_sample(starts=starts, flags=flags.astype(np.uint8), goal_rows=goal_rows, exact_episode_step=True, length=N)
+    for k in ("desired_goal", "task_done", "episode_step", "achieved_goal", "obs_1d"):
+        np.testing.assert_array_equal(npy(got[k]), want[k], err_msg=k)
+    assert want["task_done"].sum() > 0
+    np.testing.assert_allclose(npy(got["reward"]), want["reward"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(got["mc_return"]), want["mc_return"], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ vmap _pop
+def test_vmap_pop_duplicate_reference_rows(fdql, monkeypatch):
+    """nstep_return_vmap.py:50-57 through HindsightVmapWrite -> NStepReturnVmap(n_step = 3): bit for bit (reference arithmetic, Q7)."""
+    from fastdeepqlearning_b200 import Replay
+    from fastdeepqlearning_b200.Replay import wrappers as W
+    g = load_golden("vmap_pop")
+    V, n_step, gamma = int(g["V"]), int(g["n_step"]), float(g["gamma"])
+    lengths = g["bitflip_lengths"]
+    picks = iter(g["bitflip_picks_deque"].reshape(len(lengths), V))
+    shard = Replay.AsyncReplayMemory(4096, 8, 2)
+    her = W.HindsightVmapWrite(W.NStepReturnVmap(shard, n_step, gamma, reference_done_quirk=True), fdql.RewardOp.bitflip(),
+                               num_virtual_goals=V)
+    monkeypatch.setattr(np.random, "randint", lambda low, high=None, size=None: np.asarray(next(picks)))
+    _feed(her, g, "bitflip", np.float32)
+    monkeypatch.undo()
+    n = int(g["n_rows"])
+    assert len(shard) == n == lengths.sum() + int((lengths > n_step).sum())
+    mem = shard.replay.memory
+    want_keys = [k[len("stored_"):] for k in g.files if k.startswith("stored_")]
+    assert set(want_keys) == set(mem)
+    for k in want_keys:
+        np.testing.assert_array_equal(npy(mem[k])[:n].reshape(n, -1), g[f"stored_{k}"].reshape(n, -1).astype(np.float32), err_msg=k)
+
+
+def test_vmap_pop_sane_mode_vs_oracle(fdql):
+    """Default (1 - done) recurrence with episodes longer than n_step, rows that already carry the virtual columns (add())."""
+    from fastdeepqlearning_b200 import Replay
+    from fastdeepqlearning_b200.Replay import wrappers as W
+    rng = np.random.default_rng(9)
+    V1, n_step, gamma = 4, 5, 0.93
+    shard = Replay.AsyncReplayMemory(512, 8, 2)
+    head = W.NStepReturnVmap(shard, n_step, gamma)
+    want = []
+    for L in (3, 9, 5, 12):
+        vr = rng.standard_normal((L, V1)).astype(np.float32)
+        vd = rng.random((L, V1)) < 0.25
+        for t in range(L):
+            head.add({"x": float(t), "virtual_goals": np.zeros((V1, 2), np.float32), "virtual_rewards": vr[t],
+                      "virtual_dones": vd[t].astype(np.float32), "episode_done": t == L - 1})
+        full = O.vmap_returns(vr, vd, gamma, reference_done_quirk=False)
+        if L > n_step:
+            want.append(O.vmap_pop_returns(vr, vd, n_step, gamma, reference_done_quirk=False)[None])
+        want.append(full)
+    want = np.concatenate(want)
+    np.testing.assert_array_equal(npy(shard.replay.memory["virtual_mc_return"])[:len(want)], want)
+
+
+# ------------------------------------------------------------------------------------------------ one whole learner update
+def _strip(g, prefix):
+    return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
+
+
+def _mlp_grads(mlp, prefix):
+    out = {}
+    for i, lin in enumerate(mlp.hidden):
+        out[f"{prefix}feature_extractor.{i}.0.weight"], out[f"{prefix}feature_extractor.{i}.0.bias"] = lin.weight.grad, lin.bias.grad
+    out[f"{prefix}head.weight"], out[f"{prefix}head.bias"] = mlp.head.weight.grad, mlp.head.bias.grad
+    return out
+
+
+def _ensemble_tensors(critic, prefix, grad):
+    """per-member tensors of a critic ensemble under the reference's parameter names (values or gradients)"""
+    from fastdeepqlearning_b200.Agent.components import models
+    pick = (lambda p: p.grad) if grad else (lambda p: p.detach())
+    out = {}
+    if isinstance(critic, models.BatchedMLPEnsemble):
+        for e in range(critic.E):
+            for l in range(len(critic.hidden_w)):
+                out[f"{prefix}nets.{e}.feature_extractor.{l}.0.weight"] = pick(critic.hidden_w[l])[e].t()
+                out[f"{prefix}nets.{e}.feature_extractor.{l}.0.bias"] = pick(critic.hidden_b[l])[e, 0]
+            out[f"{prefix}nets.{e}.head.weight"], out[f"{prefix}nets.{e}.head.bias"] = pick(critic.head_w)[e].t(), pick(critic.head_b)[e, 0]
+    else:
+        for e, net in enumerate(critic.nets):
+            for i, lin in enumerate(net.hidden):
+                out[f"{prefix}nets.{e}.feature_extractor.{i}.0.weight"], out[f"{prefix}nets.{e}.feature_extractor.{i}.0.bias"] = \
+                    pick(lin.weight), pick(lin.bias)
+            out[f"{prefix}nets.{e}.head.weight"], out[f"{prefix}nets.{e}.head.bias"] = pick(net.head.weight), pick(net.head.bias)
+    return out
+
+
+def _mlp_values(mlp, prefix):
+    return {k: v for k, v in mlp.reference_state_dict(prefix).items()}
+
+
+@pytest.mark.parametrize("case", [0, 1])
+@pytest.mark.parametrize("batched", [True, False])
+@pytest.mark.parametrize("fold", [False, True])
+def test_learner_update_matches_reference(fdql, case, batched, fold, monkeypatch):
+    """deepQlearning.py:105-127,198-249: the reference's weights, one injected [T, B] batch and its policy noise go into the mirror;
+    loss, every gradient, the Adam step and the target update must come out the same (<= 1e-5 of each tensor's scale).
+    `fold`: the loss-reduce weights enter the loss kernel as grad_scale (what the gather kernel's aux output feeds)."""
+    import torch
+    from fastdeepqlearning_b200 import Agent
+    from fastdeepqlearning_b200.Agent.components import models
+    g = load_golden("learner_step")
+    tag = f"ls{case}"
+    T, B, C, Q = int(g[f"{tag}_T"]), int(g[f"{tag}_B"]), int(g[f"{tag}_C"]), int(g[f"{tag}_Q"])
+    latent = int(g[f"{tag}_latent"])
+    conf = Agent.LearnerConf(training_device="cuda:0", obs_space={"obs_1d": 6, "achieved_goal": 3, "desired_goal": 3},
+                             action_space=types.SimpleNamespace(shape=(2,)), num_critics=C, num_q_predictions=Q,
+                             top_quantiles_to_drop=float(g[f"{tag}_drop"]), batch_size=B, temporal_len=T, pi_hidden_dims=(16,),
+                             critic_hidden_dims=(16, 16), init_log_alpha=-0.3, learning_rate=float(g[f"{tag}_lr"]), tau=float(g[f"{tag}_tau"]),
+                             gamma=float(g[f"{tag}_gamma"]), use_distributional_sac=bool(g[f"{tag}_distributional"]), batched_critics=batched,
+                             fold_loss_reduce=fold)
+    enc = models.FeedForwardEncoder(12, latent, hidden_features=10, obs_1d_hidden_dims=(8,), joint_hidden_dims=(8,)).to("cuda")
+    learner = Agent.Learner(conf, encoder=enc, state_dim=latent)
+    ac = learner.actor_critic
+    w0 = _strip(g, f"{tag}_w0_")
+    enc.load_reference_state_dict(w0, "encoder.")
+    ac.actor.load_reference_state_dict(w0, "actor.")
+    ac.actor_target.load_reference_state_dict(w0, "actor_target.")
+    ac.critic.load_reference_state_dict(w0, "critic.")
+    ac.critic_target.load_reference_state_dict(w0, "critic_target.")
+    with torch.no_grad():
+        ac.log_alpha.copy_(torch.as_tensor(w0["log_alpha"]))
+        ac.curr_alpha.fill_(float(np.exp(w0["log_alpha"])))
+    xp = {k: torch.as_tensor(v, dtype=torch.float32, device="cuda") for k, v in _strip(g, f"{tag}_xp_").items()}
+    if fold:  # what the gather kernel emits with FDQL_OPT_EMIT_LEARNER_AUX (checked against the oracle in test_gpu_replay.py)
+        mask, contig = O.learner_preprocess(npy(xp["task_done"]), npy(xp["episode_step"]))
+        xp["mask"] = torch.as_tensor(mask.astype(np.float32), device="cuda")
+        xp["is_contiguous"] = torch.as_tensor(contig.astype(np.float32), device="cuda")
+        xp["loss_weight"] = torch.as_tensor(O.upstream_weight(contig, T), device="cuda")
+    eps = [torch.as_tensor(g[f"{tag}_eps{i}"], device="cuda") for i in range(2)]  # actor_target(next state), actor(curr state)
+    tape = iter(eps)
+    monkeypatch.setattr(torch, "randn_like", lambda t, **kw: next(tape))
+    learner.optimizer.zero_grad(set_to_none=True)
+    loss = learner.get_losses(xp)
+    monkeypatch.undo()
+    loss.backward()
+    np.testing.assert_allclose(float(loss), float(g[f"{tag}_loss"]), rtol=1e-5)
+    got = {}
+    got.update(_mlp_grads(enc.obs_1d, "encoder.visible_layer_encoders.obs_1d."))
+    got.update(_mlp_grads(enc.joiner, "encoder.joiner."))
+    got.update(_mlp_grads(ac.actor, "actor_critic.actor."))
+    got.update(_ensemble_tensors(ac.critic, "actor_critic.critic.", grad=True))
+    got["actor_critic.log_alpha"] = ac.log_alpha.grad
+    want = _strip(g, f"{tag}_grad_")
+    assert set(want) == set(got)
+    for k, w in want.items():
+        scale = max(np.abs(w).max(), 1e-12)
+        np.testing.assert_allclose(npy(got[k]), w, rtol=1e-4, atol=1e-5 * scale, err_msg=k)
+    # Adam step + target update (deepQlearning.py:123-124, soft_actor_critic.py:53-60)
+    learner.optimizer.step()
+    ac.update_target()
+    w1 = _strip(g, f"{tag}_w1_")
+    after = {}
+    after.update(_mlp_values(enc.obs_1d, "encoder.visible_layer_encoders.obs_1d."))
+    after.update(_mlp_values(enc.joiner, "encoder.joiner."))
+    after.update(_mlp_values(ac.actor, "actor."))
+    after.update(_mlp_values(ac.actor_target, "actor_target."))
+    after.update(_ensemble_tensors(ac.critic, "critic.", grad=False))
+    after.update(_ensemble_tensors(ac.critic_target, "critic_target.", grad=False))
+    after["log_alpha"] = ac.log_alpha.detach()
+    assert set(w1) == set(after)
+    lr = float(g[f"{tag}_lr"])
+    for k, w in w1.items():
+        gk = k if k.startswith("encoder.") else "actor_critic." + k
+        # Adam's first step moves a weight by lr * g / (|g| + 1e-8): where the reference's gradient is round-off noise around zero
+        # (|g| < 1e-6) the step is noise of up to lr, on both sides; everywhere else the weights must agree
+        atol = np.where(np.abs(want[gk]) < 1e-6, 1.01 * lr, 2e-5) if gk in want else 2e-5
+        assert (np.abs(npy(after[k]) - w) <= atol + 1e-4 * np.abs(w)).all(), k
+    np.testing.assert_allclose(float(ac.curr_alpha), float(g[f"{tag}_curr_alpha_after"]), rtol=1e-6)
+    # critic_frozen aliases the critic's storage: equal after the optimizer step without any copy (soft_actor_critic.py:142)
+    for pf, p in zip(ac.critic_frozen.parameters(), ac.critic.parameters()):
+        assert pf.data_ptr() == p.data_ptr() and not pf.requires_grad
+
+
+# ------------------------------------------------------------------------------------------------ bootstrap bound
+class _Fixed:
+    def __init__(self, value):
+        self.value = value
+
+    def __call__(self, *_):
+        return self.value
+
+
+def test_sac_bootstrap_bound_matches_reference(fdql):
+    """soft_actor_critic.py:102-132: q_loss returns the bound as its second value; loss, bound and d/d q_pred vs the reference."""
+    import torch
+    from fastdeepqlearning_b200 import Agent
+    g = load_golden("sac_bootstrap")
+    for i in range(int(g["cases"])):
+        p = f"sb{i}_"
+        CQ = g[p + "q_pred"].shape[-1]
+        conf = Agent.LearnerConf(training_device="cuda:0", obs_space={"obs_1d": 4}, obs_keys=("obs_1d",),
+                                 action_space=types.SimpleNamespace(shape=(2,)), num_critics=CQ, num_q_predictions=1,
+                                 use_distributional_sac=False, use_bootstrap_minibatch_nstep=True, use_max_entropy_q=bool(g[p + "ment"]),
+                                 gamma=float(g[p + "gamma"]), temporal_len=int(g[p + "T"]), pi_hidden_dims=(8,), critic_hidden_dims=(8,))
+        ac = Agent.SoftActorCritic(conf, 4).to("cuda")
+        t = lambda k: torch.as_tensor(g[p + k].astype(np.float32), device="cuda")
+        q_pred = t("q_pred").requires_grad_(True)
+        ac._critic_io = lambda c, n: (q_pred, t("target_z"), t("log_pi"))  # the three MLPs replaced by the golden's fixed outputs
+        ac.curr_alpha.fill_(float(g[p + "alpha"]))
+        nxt = {"state": None, "reward": t("reward"), "mask": t("mask"), "mc_return": t("mc_return")}
+        loss, bound, summ = ac.q_loss({"state": None}, nxt)
+        np.testing.assert_allclose(npy(loss), g[p + "loss"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(npy(bound), g[p + "bound"], rtol=1e-5, atol=1e-6)
+        ((loss * t("up_q")).sum() + (bound * t("up_b")).sum()).backward()
+        want = g[p + "grad"]
+        np.testing.assert_allclose(npy(q_pred.grad), want, rtol=1e-4, atol=1e-5 * np.abs(want).max())
+        np.testing.assert_allclose(float(summ["bootstrap_minibatch_nstep_violations"]), float(g[p + "viol"]), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ long episodes / link records
+@pytest.mark.parametrize("L,tile", [(1000, 0), (1000, 64), (40000, 64)])
+def test_link_records_on_long_episodes(fdql, L, tile):
+    """Reference default nStep_return_steps = 1000 (conf.py:46): episodes of 1000 rows keep a chain of equal achieved goals; above
+    32767 rows the chain is not built (bit 31 of the link record) and the tile kernel falls back to the verified tail scan.
+    Both must equal oracle.sample_time_relabel (goals, dones, exact episode_step bit for bit; returns to 1e-5)."""
+    from fastdeepqlearning_b200 import Replay
+    rng = np.random.default_rng(L)
+    G, gamma, T = 3, 0.999, 2
+    ag = rng.integers(0, 2, (L, G)).astype(np.float32)       # 8 distinct goals: every row has many equal successors
+    dg = np.tile(rng.integers(0, 2, G).astype(np.float32), (L, 1))
+    hit = (ag == dg).all(-1)
+    step = np.arange(L, dtype=np.float32).reshape(-1, 1)
+    cols = {"obs_1d": rng.standard_normal((L, 5)).astype(np.float32), "achieved_goal": ag, "desired_goal": dg,
+            "reward": (hit.astype(np.float32) - 1).reshape(-1, 1), "task_done": hit.astype(np.float32).reshape(-1, 1),
+            "episode_done": (step == L - 1).astype(np.float32), "episode_step": step, "mc_return": np.zeros((L, 1), np.float32)}
+    cols["reward"][0] = 0.0
+    ring = Replay.ReplayMemory(L + 8, 16, T)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), gamma)
+    ring.add_rows(cols, episode_lengths=[L], with_returns=True)
+    cols["mc_return"] = npy(ring.memory["mc_return"])[:L]
+    B = 48 if L > 5000 else 160
+    starts = rng.integers(0, L - T, B)
+    starts[:4] = [0, 1, L - T - 1, L // 2]
+    goal_rows = np.array([rng.integers(s, L) for s in starts])
+    flags = np.ones(B, bool)
+    flags[::5] = False
+    want = O.sample_time_relabel(cols, starts, T, flags, goal_rows, np.zeros(L, int), np.full(L, L - 1), O.reward_bitflip, gamma)
+    lib = fdql.lib()
+    old = lib.fdql_debug_force_generic_gather(tile << 8)
+    try:
+        got = ring.temporal_sample(starts=starts, flags=flags.astype(np.uint8), goal_rows=goal_rows, exact_episode_step=True, aux=True,
+                                   length=L)
+    finally:
+        lib.fdql_debug_force_generic_gather(old)
+    for k in ("desired_goal", "task_done", "episode_step", "reward", "obs_1d"):
+        np.testing.assert_array_equal(npy(got[k]), want[k], err_msg=k)
+    np.testing.assert_allclose(npy(got["mc_return"]), want["mc_return"], rtol=1e-5, atol=1e-5)
+    mask, contig = O.learner_preprocess(want["task_done"], want["episode_step"])
+    np.testing.assert_array_equal(npy(got["is_contiguous"]), contig.astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ small rings, overwritten episodes
+def test_small_ring_survives_more_adds_than_rows(fdql):
+    """replay_memory.py:38-46 overwrites the ring in place for any maxlen: a ring smaller than the staging block must take more
+    than maxlen add() calls between two reads (the staged rows are flushed in blocks of at most maxlen rows)."""
+    from fastdeepqlearning_b200 import Replay
+    ring = Replay.AsyncReplayMemory(50, 4, 2)
+    ref = O.RingOracle(50, 4, 2)
+    for i in range(120):
+        row = {"x": float(i), "v": np.array([i, -i], np.float32)}
+        ring.add(row)
+        ref.add(row)
+    starts = np.array([0, 10, 30, 47])
+    got = ring.replay.temporal_sample(starts=starts)
+    want = ref.temporal_sample(starts=starts)
+    for k in ("x", "v"):
+        np.testing.assert_array_equal(npy(got[k]), want[k].astype(np.float32), err_msg=k)
+    np.testing.assert_array_equal(npy(ring.replay.memory["x"]).reshape(-1), ref.memory["x"].reshape(-1))
+
+
+def test_partly_overwritten_episode_is_not_relabelled(fdql):
+    """Once the write head has entered an episode, its surviving rows still name the old first row -- which now belongs to a
+    newer episode.  They become uncommitted: never relabelled (flags ignored), gathered verbatim; intact episodes are untouched."""
+    from fastdeepqlearning_b200 import Replay, _lib as L
+    rng = np.random.default_rng(4)
+    cap, Lep, G = 100, 20, 4
+
+    def episode():
+        ag = rng.integers(0, 2, (Lep, G)).astype(np.float32)
+        step = np.arange(Lep, dtype=np.float32).reshape(-1, 1)
+        return {"achieved_goal": ag, "desired_goal": np.ones((Lep, G), np.float32), "reward": -np.ones((Lep, 1), np.float32),
+                "task_done": np.zeros((Lep, 1), np.float32), "episode_done": (step == Lep - 1).astype(np.float32), "episode_step": step,
+                "mc_return": np.zeros((Lep, 1), np.float32)}
+    ring = Replay.ReplayMemory(cap, 4, 2)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.9)
+    for _ in range(5):
+        ring.add_rows(episode(), episode_lengths=[Lep], with_returns=True)   # rows 0..99: five whole episodes
+    short = {k: v[:7] for k, v in episode().items()}
+    short["episode_done"][-1] = 1.0
+    ring.add_rows(short, episode_lengths=[7], with_returns=True)              # overwrites rows 0..6 of the first episode
+    es, ee = (npy(t) for t in ring.episode_extents())
+    assert (es[:7] == 0).all() and (ee[:7] == 6).all()
+    assert (es[7:20] == -1).all() and (ee[7:20] == -1).all()                 # survivors of the first episode: uncommitted
+    assert (es[20:40] == 20).all() and (ee[20:40] == 39).all()               # the next episode is intact
+    mem = {k: npy(v) for k, v in ring.memory.items()}
+    starts = np.array([8, 12, 25])
+    got = ring.temporal_sample(starts=starts, flags=np.ones(3, np.uint8), goal_rows=np.array([15, 19, 30]), exact_episode_step=True,
+                               length=cap - 1)
+    for k in ("desired_goal", "reward", "task_done", "episode_step", "mc_return"):
+        np.testing.assert_array_equal(npy(got[k])[:, :2], mem[k][np.arange(2)[:, None] + starts[None, :2]], err_msg=k)
+    np.testing.assert_array_equal(npy(got["desired_goal"])[0, 2], mem["achieved_goal"][30])  # the intact episode is relabelled
+    # device-drawn streams never flag a survivor (RANDOM mode used to draw goal rows from the overwritten part)
+    for _ in range(20):
+        s, f, gr = ring.draw_streams(256, 2, goal_mode=L.GOAL_RANDOM, relabel_prob=1.0)
+        s, f = npy(s), npy(f)
+        assert not f[(s >= 7) & (s < 20)].any() and f[(s >= 20) & (s < 98)].all()
