@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- sampled+relabelled+targeted transitions/s of the B200 learner hot path (BASELINE.json metric).
 
-One step = one pass of the hot path over `batches_per_step` batches of 4096 sampled windows (T=2, one TD pair per window):
+One pass of the hot path = `batches_per_step` batches of 4096 sampled windows (T=2, one TD pair per window):
   fdql_sample_gather_draw  (uniform starts, hindsight flag p=0.8 = "future, k=4", goal row drawn in the kernel   [sampled]
                             + window gather + sample-time HER relabel + reward and return recompute;            [relabelled]
                             --separate-streams: fdql_sample_streams + fdql_sample_gather, two launches)
   fdql_tqc_loss        (pool 5x25 target atoms, sort, drop 10, soft target, quantile-Huber fwd+bwd,
                         n-step lower bound) on synthetic critic outputs resident in HBM             [targeted]
-on a 1e7-row ring (obs 64, act 8, goal 16+16, 5 scalars; fp32).  `value` is device-timed with everything resident in
-HBM; `e2e` is the same pass through the host-buffer C-ABI call fdql_hotpath_step_host (index streams and critic outputs
-from pinned host memory, loss and dloss/dq back to host memory).  `--impl reference` times the CPU restatement of the
-reference path (oracle/, numpy + torch-CPU, all host cores) on a bounded sample of the same workload.
+on a 1e7-row ring (obs 64, act 8, goal 16+16, 5 scalars; fp32).  One step = `passes_per_step` such passes, so that the timed
+region of a 20-step run is about half a second.  By default the passes are pipelined the way the reference pipelines sampling
+and training (torch_dataloader.py:22-39: a prefetch thread keeps one sampled batch ahead of the learner): the gather of pass
+k+1 runs on a second stream, as two small co-resident blocks per SM (FDQL_OPT_CORESIDENT), under the loss of pass k; every pass
+is complete inside the timed region (K gathers and K losses).  --serial runs the two kernels back to back on one stream.
+`value` is device-timed with everything resident in HBM; `e2e` is the same pass through the host-buffer C-ABI call
+fdql_hotpath_step_host (index streams and critic outputs from pinned host memory, loss and dloss/dq back to host memory).
+`--impl reference` times the CPU restatement of the reference path (oracle/, numpy + torch-CPU, all host cores) on a bounded
+sample of the same workload.
 
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under torchrun (one rank per GPU, no data-path
 collective: the replay shards by actor stream, scaling = weak)."""
@@ -67,7 +72,12 @@ def parse():
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the T=50 figure (reference default temporal_len, SURVEY 8)")
     ap.add_argument("--no-updates", action="store_true")
-    ap.add_argument("--exact-episode-step", action="store_true")
+    ap.add_argument("--fast-episode-step", action="store_true",
+                    help="episode_step of relabelled rows re-based inside the window only (mask / is_contiguous stay exact); default: "
+                         "the reference's value (her.py:72-83), bit for bit")
+    ap.add_argument("--serial", action="store_true", help="gather and loss back to back on one stream instead of pipelined on two")
+    ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="learner step launched eagerly instead of as one CUDA graph")
     ap.add_argument("--separate-streams", action="store_true", help="draw the index / goal streams in their own launch (fdql_sample_streams)")
     ap.add_argument("--tail-scan", action="store_true", help="relabelled returns by scanning the episode tail instead of the link records")
@@ -85,7 +95,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("FDQL_BENCH_CLOCK_MS", "200"),
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -181,56 +191,131 @@ def run_ours(args):
     z = torch.randn(M, CQ, device=device, generator=gen) * 3
     q = torch.randn(M, CQ, device=device, generator=gen) * 3
     lp = torch.randn(M, device=device, generator=gen)
-    out = {k: torch.empty((T, n, w), device=device) for k, w in zip(keys, ring._widths)}
-    outp = L.ptr_array([out[k].data_ptr() for k in keys])
-    aux_mask = torch.empty(T, n, device=device)
-    aux_contig = torch.empty(T - 1, n, device=device)
-    aux_weight = torch.empty(T - 1, n, device=device)
-    starts = torch.empty(n, dtype=torch.int64, device=device)
-    flags = torch.empty(n, dtype=torch.uint8, device=device)
-    goals = torch.empty(n, dtype=torch.int64, device=device)
+    def make_buf():
+        o = {k: torch.empty((T, n, w), device=device) for k, w in zip(keys, ring._widths)}
+        return {"out": o, "outp": L.ptr_array([o[k].data_ptr() for k in keys]), "mask": torch.empty(T, n, device=device),
+                "contig": torch.empty(T - 1, n, device=device), "weight": torch.empty(T - 1, n, device=device),
+                "starts": torch.empty(n, dtype=torch.int64, device=device), "flags": torch.empty(n, dtype=torch.uint8, device=device),
+                "goals": torch.empty(n, dtype=torch.int64, device=device)}
+    bufs = [make_buf(), make_buf()]  # the pipelined schedule samples pass k+1 into one while pass k's loss reads the other
+    out, outp, aux_mask, aux_contig, aux_weight = (bufs[0][k] for k in ("out", "outp", "mask", "contig", "weight"))
+    starts, flags, goals = bufs[0]["starts"], bufs[0]["flags"], bufs[0]["goals"]
     loss = torch.empty(M, device=device)
     grad = torch.empty(M, CQ, device=device)
     stats = torch.zeros(4, dtype=torch.float64, device=device)
     params, n_params = ring.reward_op.c_params()
-    opts = L.OPT_EMIT_LEARNER_AUX | (L.OPT_EXACT_EPISODE_STEP if args.exact_episode_step else 0)
+    exact = not args.fast_episode_step
+    opts = L.OPT_EMIT_LEARNER_AUX | (L.OPT_EXACT_EPISODE_STEP if exact else 0)
     if args.tail_scan:
         lib.fdql_debug_force_generic_gather(16)  # tile kernel without the link records
     bytes_relabel = BYTES_RELABEL_SCAN if args.tail_scan else BYTES_RELABEL
     stream = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device)
     sp = C.c_void_p(stream.cuda_stream)
     p = lambda t: C.c_void_p(t.data_ptr())
     rlen = len(ring)
     counter = [0]
+    pipelined = not args.serial and not args.separate_streams
+    P = args.passes_per_step or 64
 
-    def step(ev=None):
-        if ev:
-            ev[0].record(stream)
+    # argument tuples are built once per (buffer, stream): the pipelined schedule needs ~6000 launches per second from this loop
+    _args = {}
+
+    def gather(b, st, extra=0):
+        key = ("g", id(b), st.cuda_stream, extra)
+        a = _args.get(key)
+        if a is None:
+            spx = C.c_void_p(st.cuda_stream)
+            a = _args[key] = {
+                "draw_head": (h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank),
+                "draw_tail": (None, p(b["starts"]), p(b["flags"]), p(b["goals"]), ring.reward_op.op, params, n_params, GAMMA, opts | extra, B,
+                              b["outp"], p(b["mask"]), p(b["contig"]), p(b["weight"]), spx),
+                "streams_tail": (None, p(b["starts"]), p(b["flags"]), p(b["goals"]), spx),
+                "gather": (h, n, T, rlen, p(b["starts"]), p(b["flags"]), p(b["goals"]), ring.reward_op.op, params, n_params, GAMMA,
+                           opts | extra, B, b["outp"], p(b["mask"]), p(b["contig"]), p(b["weight"]), spx)}
         if args.separate_streams:
-            L.check(lib.fdql_sample_streams(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], None, p(starts), p(flags), p(goals), sp))
-        if ev:
-            ev[1].record(stream)
-        if args.separate_streams:
-            L.check(lib.fdql_sample_gather(h, n, T, rlen, p(starts), p(flags), p(goals), ring.reward_op.op, params, n_params, GAMMA,
-                                           opts, B, outp, p(aux_mask), p(aux_contig), p(aux_weight), sp))
+            L.check(lib.fdql_sample_streams(*a["draw_head"], counter[0], *a["streams_tail"]))
+            L.check(lib.fdql_sample_gather(*a["gather"]))
         else:  # streams drawn inside the gather kernel: one launch
-            L.check(lib.fdql_sample_gather_draw(h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, counter[0], None, p(starts), p(flags), p(goals),
-                                                ring.reward_op.op, params, n_params, GAMMA, opts, B, outp, p(aux_mask), p(aux_contig),
-                                                p(aux_weight), sp))
+            L.check(lib.fdql_sample_gather_draw(*a["draw_head"], counter[0], *a["draw_tail"]))
         counter[0] += 1
-        if ev:
-            ev[2].record(stream)
-        # the target reads reward / mask / mc_return of the NEXT row (t=1), quirk Q10
-        L.check(lib.fdql_tqc_loss(M, CQ, N_DROP, p(z), p(q), p(lp), p(out["reward"][1:]), p(aux_mask[1:]),
-                                  p(out["mc_return"][1:]), p(aux_weight), ALPHA, GAMMA, p(loss), p(grad), None, p(stats), sp))
-        if ev:
-            ev[3].record(stream)
 
+    def tqc(b, st):
+        key = ("t", id(b), st.cuda_stream)
+        a = _args.get(key)
+        if a is None:
+            # the target reads reward / mask / mc_return of the NEXT row (t=1), quirk Q10
+            a = _args[key] = (M, CQ, N_DROP, p(z), p(q), p(lp), p(b["out"]["reward"][1:]), p(b["mask"][1:]), p(b["out"]["mc_return"][1:]),
+                              p(b["weight"]), ALPHA, GAMMA, p(loss), p(grad), None, p(stats), C.c_void_p(st.cuda_stream))
+        L.check(lib.fdql_tqc_loss(*a))
+
+    def run_serial(n_pass, evs=None):
+        for i in range(n_pass):
+            e = evs[i] if evs is not None and i < len(evs) else None
+            if e:
+                e[0].record(stream)
+            gather(bufs[0], stream)
+            if e:
+                e[1].record(stream)
+            tqc(bufs[0], stream)
+            if e:
+                e[2].record(stream)
+
+    last_buf = [0]
+
+    loss_stream = torch.cuda.Stream(device)
+
+    def run_pipelined(n_pass, evs=None, every=16):
+        """loss stream: loss(k); side stream: gather(k+1).  loss(k) waits for gather(k); gather(k+2) waits for loss(k), whose
+        inputs it overwrites.  Starts and ends with nothing in flight: n_pass gathers and n_pass losses, all inside the call
+        (both streams fork from and join back into the caller's stream)."""
+        t0 = torch.cuda.Event()
+        t0.record(stream)
+        side.wait_event(t0)
+        loss_stream.wait_event(t0)
+        done_g, done_t = [None, None], [None, None]
+        gather(bufs[0], side, L.OPT_CORESIDENT)
+        done_g[0] = torch.cuda.Event()
+        done_g[0].record(side)
+        for k in range(n_pass):
+            cur, nxt = k & 1, (k + 1) & 1
+            e = evs[k // every] if evs is not None and k % every == every // 2 and k // every < len(evs) else None
+            if k + 1 < n_pass:
+                if done_t[nxt] is not None:
+                    side.wait_event(done_t[nxt])
+                if e:
+                    e[0].record(side)
+                gather(bufs[nxt], side, L.OPT_CORESIDENT)
+                done_g[nxt] = e[1] if e else torch.cuda.Event()
+                done_g[nxt].record(side)
+            loss_stream.wait_event(done_g[cur])
+            if e:
+                e[2].record(loss_stream)
+            tqc(bufs[cur], loss_stream)
+            done_t[cur] = e[3] if e else torch.cuda.Event()
+            done_t[cur].record(loss_stream)
+        stream.wait_event(done_t[(n_pass - 1) & 1])
+        stream.wait_event(done_g[(n_pass - 1) & 1])
+        last_buf[0] = (n_pass - 1) & 1
+
+    # ---- the two kernels alone, back to back on one stream (kernel-level figures; also the --serial headline) ----
+    lib.fdql_set_coresident(0)
+    run_serial(3)
+    torch.cuda.synchronize(device)
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(20)]
+    run_serial(20, sev)
+    torch.cuda.synchronize(device)
+    alone_ms = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(2)] for e in sev]).mean(0)  # gather, tqc
+
+    if pipelined:
+        lib.fdql_set_coresident(1)  # the loss kernel leaves room on every SM for the co-resident gather blocks
+    run = run_pipelined if pipelined else run_serial
     for _ in range(max(args.warmup, 3)):
-        step()
+        run(P)
     torch.cuda.synchronize(device)
     K = args.steps
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    n_ev = 8
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K * n_ev)]
     clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.25)
@@ -241,7 +326,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(K):
-        step(evs[i])
+        if pipelined:
+            run_pipelined(P, evs[i * n_ev:(i + 1) * n_ev], every=max(P // n_ev, 1))
+        else:
+            run_serial(P, [[a, b_, c] for a, b_, c, _ in evs[i * n_ev:(i + 1) * n_ev]])
     e1.record(stream)
     torch.cuda.synchronize(device)
     t1 = time.time()
@@ -249,13 +337,25 @@ def run_ours(args):
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop(t0, t1)
-    k_ms = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in evs]).mean(0)  # streams, gather, tqc
+
+    def _el(a, b_):
+        try:
+            return a.elapsed_time(b_)
+        except Exception:  # an event that was never recorded (P < 8 passes per step)
+            return float("nan")
+    if pipelined:
+        k_ms = np.nanmean(np.array([[float("nan"), _el(e[0], e[1]), _el(e[2], e[3])] for e in evs]), 0)  # -, gather, tqc (overlapped)
+    else:
+        k_ms = np.nanmean(np.array([[float("nan"), _el(e[0], e[1]), _el(e[1], e[2])] for e in evs]), 0)
+    lib.fdql_set_coresident(0)
     if dist:
         tmax = torch.tensor([ms_total], device=device)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_total = float(tmax.item())
     ms_step = ms_total / K
-    value = world * M / (ms_step * 1e-3)
+    ms_pass = ms_step / P
+    value = world * M * P / (ms_step * 1e-3)
+    chk = bufs[last_buf[0]] if pipelined else bufs[0]  # the batch of the last timed pass: spot-checked against the oracle below
 
     # ---- single-batch launches (B=4096 windows per launch): latency-bound figure, reported beside the headline ----
     def small_step(i):
@@ -455,32 +555,50 @@ def run_ours(args):
                    "note": "policy/critic MLPs are ordinary PyTorch fp32 modules; sample/relabel/target/loss are this repo's CUDA kernels; "
                            "the whole step (kernels + MLP fwd/bwd + gradient all-reduce + Adam + target update) is one captured CUDA graph"}
 
+    # ---- spot check of the last timed pass against the oracle (outside the timed region; oracle/ is the checker only) ----------------
+    parity = None
+    if not args.no_parity_check and rank == 0:
+        parity = oracle_spot_check(torch, ring, chk, z, q, lp, loss, grad, n, exact)
+
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()
+    gname = "sample_gather_lean_kernel" if pipelined else "sample_gather_tile_kernel"
     kernels = {
-        "sample_gather_kernel": {"ms": float(k_ms[1]), "bytes_per_transition": BYTES_GATHER + bytes_relabel + (0 if args.separate_streams else 17),
-                                 "symbol": "fdql::sample_gather_tile_kernel<1, true>" + ("" if args.separate_streams else " (draws its own index / goal streams)"),
-                                 "limiter": "HBM latency on random 32-256 B segments (ncu r1: long-scoreboard stalls dominate, DRAM traffic = algorithmic bytes)",
+        "sample_gather_kernel": {"ms": float(k_ms[1]), "ms_alone": float(alone_ms[0]),
+                                 "bytes_per_transition": BYTES_GATHER + bytes_relabel + (0 if args.separate_streams else 17),
+                                 "symbol": f"fdql::{gname}" + ("" if args.separate_streams else " (draws its own index / goal streams)"),
+                                 "limiter": ("co-resident: two 4-warp blocks per SM under the loss kernel, wide keys through cp.async staging + "
+                                             "bulk shared->global write-back (LDGSTS / UBLKCP); its duration is set by the issue slots the loss "
+                                             "kernel leaves" if pipelined else
+                                             "HBM latency on random 32-256 B segments (ncu: long-scoreboard stalls dominate)"),
                                  "relabelled_returns": "tail scan (16 B per tail row)" if args.tail_scan else
                                  "link records: chain of equal achieved goals + goal-agnostic return, O(hits) per window"},
-        "tqc_loss_kernel": {"ms": float(k_ms[2]), "bytes_per_transition": BYTES_TQC, "symbol": "fdql::tqc_loss_group_kernel<128, 7>",
-                            "limiter": "instruction issue (81% active, ALU pipe 60%) and shared-memory wavefronts (79% of peak): 128-value sort "
-                                       "network + 375 seven-level searches per transition; not HBM (ncu r1, profiles/r1_ncu_summary.md)"},
+        "tqc_loss_kernel": {"ms": float(k_ms[2]), "ms_alone": float(alone_ms[1]), "bytes_per_transition": BYTES_TQC,
+                            "symbol": "fdql::tqc_loss_group_kernel<128, 7>",
+                            "limiter": "instruction issue (81% active alone, ALU pipe 60%) and shared-memory wavefronts (79% of peak): 128-value "
+                                       "sort network + 375 seven-level searches per transition; not HBM (ncu, profiles/)"},
     }
+    for kd in kernels.values():
+        kd["note"] = ("ms = average launch duration inside the timed region, where the two kernels share every SM; ms_alone = the same "
+                      "launch with the GPU to itself") if pipelined else "ms = average launch duration inside the timed region"
     if args.separate_streams:
         kernels["sample_streams_kernel"] = {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS, "symbol": "fdql::sample_streams_kernel"}
     for kd in kernels.values():
         kd["achieved_gbs"] = kd["bytes_per_transition"] * M / (kd["ms"] * 1e-3) / 1e9
         kd["frac"] = kd["achieved_gbs"] / peak
-    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        if "ms_alone" in kd:
+            kd["frac_alone"] = kd["bytes_per_transition"] * M / (kd["ms_alone"] * 1e-3) / 1e9 / peak
+    dom = max(kernels, key=lambda k: kernels[k].get("ms_alone", kernels[k]["ms"]))
     total_bytes = sum(kd["bytes_per_transition"] for kd in kernels.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["bytes_per_transition"] * M, "launch_ms": kernels[dom]["ms"],
                 "survey_bytes_per_transition": {"sample_gather_kernel": BYTES_GATHER + BYTES_RELABEL_SURVEY, "tqc_loss_kernel": BYTES_TQC},
                 "kernels": kernels,
-                "whole_step": {"bytes_per_transition": total_bytes, "achieved_gbs": total_bytes * M / (ms_step * 1e-3) / 1e9,
-                               "frac": total_bytes * M / (ms_step * 1e-3) / 1e9 / peak}}
+                "whole_step": {"bytes_per_transition": total_bytes, "achieved_gbs": total_bytes * M / (ms_pass * 1e-3) / 1e9,
+                               "frac": total_bytes * M / (ms_pass * 1e-3) / 1e9 / peak, "ms_per_pass": ms_pass,
+                               "note": "both kernels' algorithmic bytes over the time of one pass of the pipelined schedule"},
+                "traffic_source": "dram__bytes per launch from the ncu --set full capture summarised in profiles/ (constant, not measured in-run)"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -503,19 +621,24 @@ def run_ours(args):
             "config": {"workload": "HER(future,k=4: relabel p=0.8, return-to-go recomputed over the whole episode tail) + TQC 5x25 drop 10 + "
                                    "n-step lower bound; obs64/act8/goal16; ring %d rows/GPU (L=128 episodes); batch 4096, T=2"
                                    % (len(ring) + 1),
-                       "batch": B, "temporal_len": T, "batches_per_step": D, "transitions_per_step_per_gpu": M,
+                       "batch": B, "temporal_len": T, "batches_per_step": D, "passes_per_step": P, "transitions_per_step_per_gpu": M * P,
+                       "transitions_per_pass_per_gpu": M,
+                       "schedule": ("pipelined on two streams: gather of pass k+1 (FDQL_OPT_CORESIDENT, two 4-warp blocks per SM) under the "
+                                    "loss of pass k, as the reference's prefetch thread does (torch_dataloader.py:22-39); every pass complete "
+                                    "inside the timed region") if pipelined else "gather and loss back to back on one stream",
                        "ring_rows_per_gpu": len(ring) + 1,
                        "l2": "inputs larger than L2 (random rows of a %.1f GB arena; %d MB of critic outputs per step)"
                              % ((len(ring) + 1) * (ROW_BYTES + 16) / 1e9, M * CQ * 8 // 2 ** 20),
-                       "exact_episode_step": bool(args.exact_episode_step), "parallelism": f"replay shards x{world}, no data-path collective",
+                       "exact_episode_step": bool(exact), "parallelism": f"replay shards x{world}, no data-path collective",
                        "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
-            "roofline": roofline, "gpu_launches": (3 if args.separate_streams else 2) * K, "clocks": clk,
+            "roofline": roofline, "gpu_launches": (3 if args.separate_streams else 2) * K * P, "clocks": clk,
+            "ms_per_pass": ms_pass,
             "single_batch_launches": {"windows_per_launch": B, "ms_per_batch": small_ms, "transitions_per_s": world * B / (small_ms * 1e-3),
                                       "note": "2 launches per 4096-window batch from Python (gather with fused draw, loss), launch-latency bound",
                                       "cuda_graph_4_streams": {"ms_per_batch": graph_ms, "transitions_per_s": world * B / (graph_ms * 1e-3),
                                                                "note": "16 batches x 2 launches captured once, round-robin over four streams"}},
             "checks": {"loss_mean": float(loss.mean()), "relabel_frac": float(flags.float().mean()),
-                       "violations": float(stats[2] / max(float(stats[3]), 1) / CQ)}}
+                       "violations": float(stats[2] / max(float(stats[3]), 1) / CQ), "parity_vs_oracle": parity}}
     if secondary:
         line["secondary_T50"] = secondary
     if e2e:
@@ -543,17 +666,90 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def oracle_spot_check(torch, ring, b, z, q, lp, loss, grad, n, exact, n_check=1024):
+    """The first `n_check` windows of the last timed pass against the CPU oracle (outside the timed region): the sampled and
+    relabelled batch vs oracle.sample_time_relabel on the same drawn streams, then loss and d loss / d q_pred of those transitions vs
+    oracle.tqc_q_loss.  Returns mismatch counts for the bit-exact outputs and maximum relative errors for the fp32 ones."""
+    from oracle import cpu_restatement as O
+    w = min(n_check, n)
+    s_np = b["starts"][:w].cpu().numpy()
+    f_np = b["flags"][:w].cpu().numpy().astype(bool)
+    g_np = b["goals"][:w].cpu().numpy()
+    eps = np.unique(np.concatenate([s_np // LEP, (s_np + T - 1) // LEP]))  # fixed-length episodes laid end to end from row 0
+    rows = (eps[:, None] * LEP + np.arange(LEP)[None]).reshape(-1)
+    pos = {int(e): i * LEP for i, e in enumerate(eps)}
+    rows_t = torch.as_tensor(rows, device=b["starts"].device)
+    mem = ring.memory
+    cols = {k: mem[k][rows_t].cpu().numpy() for k in ring.keys}
+    remap = lambda r: np.array([pos[int(x) // LEP] + int(x) % LEP for x in r])
+    cs, cg = remap(s_np), remap(g_np)
+    es = (np.arange(len(rows)) // LEP) * LEP
+    want = O.sample_time_relabel(cols, cs, T, f_np, cg, es, es + LEP - 1, O.reward_bitflip, GAMMA)
+    got = {k: v[:, :w].cpu().numpy() for k, v in b["out"].items()}
+    exact_keys = [k for k in cols if k not in ("reward", "mc_return") and (exact or k != "episode_step")]
+    mism = {k: int((got[k] != want[k]).sum()) for k in exact_keys}
+    rel = lambda a, c: float(np.max(np.abs(a - c) / np.maximum(np.abs(c), 1.0)))
+    mask, contig = O.learner_preprocess(want["task_done"], want["episode_step"])
+    mism["mask"] = int((b["mask"][:, :w].cpu().numpy() != mask[..., 0]).sum())
+    mism["is_contiguous"] = int((b["contig"][:, :w].cpu().numpy() != contig[..., 0]).sum())
+    wgt = O.upstream_weight(contig, T)[..., 0] * (w / B)  # the kernel normalises by the configured batch size B
+    zq = lambda t: t[:w].cpu().numpy().astype(np.float64)
+    ol, og, _ = O.tqc_q_loss(zq(q), zq(z), zq(lp).reshape(-1, 1), want["reward"][1].astype(np.float64), mask[1].astype(np.float64),
+                             want["mc_return"][1].astype(np.float64), ALPHA, GAMMA, N_DROP)
+    og = og * wgt[0][:, None]
+    gl, gg = loss[:w].cpu().numpy(), grad[:w].cpu().numpy()
+    return {"windows": int(w), "exact_mismatches": mism, "relabelled": int(f_np.sum()),
+            "max_rel_err": {"reward": rel(got["reward"], want["reward"]), "mc_return": rel(got["mc_return"], want["mc_return"]),
+                            "loss": rel(gl, ol[:, 0]), "grad_q_over_its_scale": float(np.max(np.abs(gg - og)) / max(np.abs(og).max(), 1e-30))},
+            "tolerance": "bit-exact for indices, goals, done masks, steps; 1e-5 relative for returns, targets and losses",
+            "ok": bool(sum(mism.values()) == 0 and rel(got["mc_return"], want["mc_return"]) < 1e-5 and rel(gl, ol[:, 0]) < 1e-5)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 _CPU = {}
 
 
 def _cpu_window_chunk(job):
     """One worker: window gather (numpy fancy index, replay_memory.py:62-70) + hindsight relabel + return recompute for a
-    slice of the batch, by the oracle's restatement of her.py:55-95 / nstep_return.py:60-72."""
+    slice of the batch, by the oracle's restatement of her.py:55-95 / nstep_return.py:60-72.  The ring is inherited from the parent
+    (copy-on-write); the slice of the index / goal streams travels in the job."""
     from oracle import cpu_restatement as O
-    lo, hi = job
+    t, s, f, g = job
     c = _CPU
-    return O.sample_time_relabel(c["cols"], c["starts"][lo:hi], T, c["flags"][lo:hi], c["goals"][lo:hi], c["ep_start"],
-                                 c["ep_end"], O.reward_bitflip, GAMMA)
+    return O.sample_time_relabel(c["cols"], s, t, f, g, c["ep_start"], c["ep_end"], O.reward_bitflip, GAMMA)
+
+
+def _cpu_gather_only(job):
+    """ReplayMemory.temporal_sample (replay_memory.py:54-70) of one independent shard process: randint + fancy index of every key."""
+    t, seed, reps = job
+    rng = np.random.default_rng(seed)
+    cols = _CPU["cols"]
+    n_rows = len(cols["reward"])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        idx = (np.arange(t)[:, None] + rng.integers(0, n_rows - t, B)[None, :]) % n_rows
+        out = {k: v[idx] for k, v in cols.items()}
+    return time.perf_counter() - t0, out["reward"].shape
+
+
+def _cpu_write_path(job):
+    """HindsightNStepReplay(random) -> NStepReturn(1000) -> ReplayMemory row by row (her.py:24-95, nstep_return.py:23-72), one core."""
+    from oracle import cpu_restatement as O
+    n_eps, seed = job
+    rng = np.random.default_rng(seed)
+    sink = O.RingOracle(4 * n_eps * LEP, B, T)
+    picks = iter(rng.integers(0, LEP, n_eps).tolist())
+    her = O.HindsightOracle(O.NStepOracle(sink, 1000, GAMMA), O.reward_bitflip, mode="random", goal_picker=lambda L_: next(picks))
+    ag = (rng.random((n_eps * LEP, GOAL)) < 0.5).astype(np.float32)
+    dg = np.repeat((rng.random((n_eps, GOAL)) < 0.5).astype(np.float32), LEP, 0)
+    obs = rng.standard_normal((n_eps * LEP, OBS)).astype(np.float32)
+    act = rng.standard_normal((n_eps * LEP, ACT)).astype(np.float32)
+    t0 = time.perf_counter()
+    for i in range(n_eps * LEP):
+        hit = bool((ag[i] == dg[i]).all())
+        her.add({"obs_1d": obs[i], "action": act[i], "achieved_goal": ag[i], "desired_goal": dg[i], "reward": 0.0 if hit else -1.0,
+                 "task_done": hit, "episode_done": i % LEP == LEP - 1, "episode_step": i % LEP, "info": {}})
+    return time.perf_counter() - t0, len(sink)
 
 
 class _LazyExtent:
@@ -567,7 +763,7 @@ class _LazyExtent:
         return base + LEP - 1 if self.last else base
 
 
-def cpu_reference(args, steps, warmup, quiet=False):
+def cpu_reference(args, steps, warmup, quiet=False, stages=True):
     """The reference's CPU replay-and-target path (oracle port) on the host cores, same workload, bounded sample."""
     import multiprocessing as mp
     import torch
@@ -594,56 +790,80 @@ def cpu_reference(args, steps, warmup, quiet=False):
     z = torch.randn(n, CQ) * 3
     q = torch.randn(n, CQ) * 3
     lp = torch.randn(n, 1)
-    workers = min(cores, 32)
-    ctx = mp.get_context("fork")
+    workers = min(cores, 64)
+    # ONE pool for the whole run, forked after the ring exists (shared copy-on-write); each step's streams travel in the jobs
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    stage_t = {"gather_relabel": 0.0, "tqc": 0.0}
 
-    def one_step(pool):
+    def tqc_stage(xp, n_):
+        mask = 1.0 - xp["task_done"]
+        qp = q[:n_].clone().requires_grad_(True)
+        loss = O.tqc_q_loss_torch(qp.view(T - 1, n_, CQ), z[:n_].view(T - 1, n_, CQ), lp[:n_].view(T - 1, n_, 1), xp["reward"][1:], mask[1:],
+                                  xp["mc_return"][1:], ALPHA, GAMMA, N_DROP)
+        loss.mean().backward()
+        return float(loss.mean())
+
+    def one_step():
+        t0 = time.perf_counter()
         s = rng.integers(0, n_rows - T, n)
         tail = (LEP - 1) - (s % LEP)
         g = s + np.where(tail > 0, 1 + (rng.random(n) * tail).astype(np.int64), 0)
         g = np.minimum(g, s - s % LEP + LEP - 1)
         f = rng.random(n) < P_RELABEL
-        _CPU.update(starts=s, flags=f, goals=g)
         per = (n + workers - 1) // workers
-        jobs = [(i, min(i + per, n)) for i in range(0, n, per)]
+        jobs = [(T, s[i:i + per], f[i:i + per], g[i:i + per]) for i in range(0, n, per)]
         parts = pool.map(_cpu_window_chunk, jobs) if pool else [_cpu_window_chunk(j) for j in jobs]
-        batch = {k: np.concatenate([p[k] for p in parts], axis=1) for k in parts[0]}
+        batch = {k: np.concatenate([p_[k] for p_ in parts], axis=1) for k in parts[0]}
         xp = {k: torch.from_numpy(v) for k, v in batch.items()}  # TorchDataLoader cast (already fp32)
-        mask = 1.0 - xp["task_done"]
-        qp = q.clone().requires_grad_(True)
-        loss = O.tqc_q_loss_torch(qp.view(T - 1, n, CQ), z.view(T - 1, n, CQ), lp.view(T - 1, n, 1), xp["reward"][1:], mask[1:],
-                                  xp["mc_return"][1:], ALPHA, GAMMA, N_DROP)
-        loss.mean().backward()
-        return float(loss.mean())
+        t1 = time.perf_counter()
+        out = tqc_stage(xp, n)
+        t2 = time.perf_counter()
+        stage_t["gather_relabel"] += t1 - t0
+        stage_t["tqc"] += t2 - t1
+        return out
 
-    # fork per step so the workers see this step's streams (the ring itself is shared copy-on-write)
-    def timed(k):
-        t = 0.0
-        for _ in range(k):
-            t0 = time.perf_counter()
-            if workers > 1:
-                # streams must exist before the fork: draw them inside one_step, so fork a fresh pool per step
-                one_step_pool(one_step, ctx, workers)
-            else:
-                one_step(None)
-            t += time.perf_counter() - t0
-        return t
-
-    def one_step_pool(fn, ctx_, w):
-        class _P:
-            def map(self, f, jobs):
-                with ctx_.Pool(w) as pool:
-                    return pool.map(f, jobs)
-        return fn(_P())
-
-    timed(warmup)
-    tt = timed(steps)
+    for _ in range(warmup):
+        one_step()
+    stage_t.update(gather_relabel=0.0, tqc=0.0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    tt = time.perf_counter() - t0
     ms_step = tt / steps * 1e3
     value = (T - 1) * n / (ms_step * 1e-3)
     base = {"value": value, "unit": "transitions/s", "cores": cores, "kind": "port",
             "sample": f"{steps} step(s) of {nb} batch(es) x {B} windows (T={T}) on a {n_rows}-row numpy ring: fancy-index gather + "
-                      f"oracle HER relabel/return recompute over {workers} forked workers, then the reference's torch-CPU TQC "
-                      f"sort/target/[CQ x K] pairwise quantile-Huber fwd+bwd on {cores} threads"}
+                      f"oracle HER relabel/return recompute over one persistent pool of {workers} forked workers, then the reference's "
+                      f"torch-CPU TQC sort/target/[CQ x K] pairwise quantile-Huber fwd+bwd on {cores} threads",
+            "stage_ms_per_step": {"gather_relabel_return": stage_t["gather_relabel"] / steps * 1e3, "tqc_target_loss_fwd_bwd": stage_t["tqc"] / steps * 1e3}}
+    if stages:  # per-stage figures of record, each a bounded sample on these host cores
+        st = {}
+        for t_len, reps in ((2, 20), (50, 4)):
+            el, _ = _cpu_gather_only((t_len, 1, reps))
+            st[f"temporal_sample_T{t_len}_1proc"] = {"ms_per_call": el / reps * 1e3, "rows_per_s": reps * t_len * B / el}
+            if pool:
+                res = pool.map(_cpu_gather_only, [(t_len, 10 + i, reps) for i in range(workers)])
+                el_max = max(r[0] for r in res)
+                st[f"temporal_sample_T{t_len}_{workers}proc"] = {"ms_per_call": el_max / reps * 1e3, "rows_per_s": workers * reps * t_len * B / el_max,
+                                                                  "note": "independent shard processes, the reference's own scaling model"}
+        el, stored = _cpu_write_path((6, 3))
+        st["write_path_her_random_nstep_1core"] = {"env_rows_per_s": 6 * LEP / el, "stored_rows_per_s": stored / el,
+                                                   "note": "HindsightNStepReplay(random) -> NStepReturn(1000) -> ring, 128-step episodes, row by row"}
+        xp1 = {k: torch.from_numpy(cols[k][:2 * B].reshape(T, B, -1)) for k in ("reward", "task_done", "mc_return")}
+        tqc_stage(xp1, B)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            tqc_stage(xp1, B)
+        el = (time.perf_counter() - t0) / 3
+        st["tqc_target_loss_fwd_bwd"] = {"ms_per_batch": el * 1e3, "transitions_per_s": B / el, "threads": torch.get_num_threads()}
+        try:
+            st["full_update"] = _cpu_full_update(torch)
+        except Exception as e:  # the learner mirror needs the CUDA library even for its plain-torch modules' import
+            st["full_update"] = {"unavailable": repr(e)[:200]}
+        base["stages"] = st
+    if pool:
+        pool.close()
+        pool.join()
     line = {"metric": "sampled+relabelled+targeted transitions/s", "value": value, "unit": "transitions/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -653,6 +873,70 @@ def cpu_reference(args, steps, warmup, quiet=False):
             "cpu_baseline": base, "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     return line
+
+
+def _cpu_full_update(torch):
+    """get_losses + backward + Adam step + update_targets on CPU torch with the reference's network shapes (deepQlearning.py:105-127,
+    198-249: encoder MLPs 96 -> 256 -> 256, actor [256], 5 critics [256, 256] x 25 atoms), B = 4096, T = 2: updates/s."""
+    from torch import nn
+
+    def mlp(i, o, hs):  # models/mlp.py:62-90: the head sees the input and every hidden layer
+        class M(nn.Module):
+            def __init__(self):
+                super().__init__()
+                d = [i] + list(hs)
+                self.h = nn.ModuleList([nn.Linear(a, b) for a, b in zip(d[:-1], d[1:])])
+                self.o = nn.Linear(sum(d), o)
+
+            def forward(self, x):
+                f = [x]
+                for l_ in self.h:
+                    x = nn.functional.leaky_relu(l_(x))
+                    f.append(x)
+                return self.o(torch.cat(f, -1))
+        return M()
+    from oracle import cpu_restatement as O
+    S = 256
+    enc = nn.Sequential(mlp(OBS + 2 * GOAL, 256, (256,)), mlp(256, S, (256,)))
+    actor, actor_t = mlp(S, 2 * ACT, (256,)), mlp(S, 2 * ACT, (256,))
+    crit = nn.ModuleList([mlp(S + ACT, Q_ATOMS, (256, 256)) for _ in range(C_CRIT)])
+    crit_t = nn.ModuleList([mlp(S + ACT, Q_ATOMS, (256, 256)) for _ in range(C_CRIT)])
+    params = list(enc.parameters()) + list(actor.parameters()) + list(crit.parameters())
+    opt = torch.optim.Adam(params, lr=3e-4)
+    xp = {"obs": torch.randn(T, B, OBS + 2 * GOAL), "action": torch.rand(T, B, ACT) * 2 - 1, "reward": -torch.ones(T, B, 1),
+          "mask": torch.ones(T, B, 1), "mc_return": -torch.ones(T, B, 1) * 5}
+
+    def pi(net, st):
+        mu, ls = net(st).chunk(2, -1)
+        ls = ls.clamp(-20, 2)
+        eps = torch.randn_like(mu)
+        a = torch.tanh(mu + ls.exp() * eps)
+        return a, (-0.5 * eps ** 2 - ls - 0.9189385 - torch.log(1 - a ** 2 + 1e-4)).sum(-1, keepdim=True)
+
+    def update():
+        st = enc(xp["obs"])
+        cur, nxt = st[:-1], st[1:]
+        with torch.no_grad():
+            na, nlp = pi(actor_t, nxt)
+            nz = torch.cat([c(torch.cat((nxt, na), -1)) for c in crit_t], -1)
+        qp = torch.cat([c(torch.cat((cur, xp["action"][:-1]), -1)) for c in crit], -1)
+        ql = O.tqc_q_loss_torch(qp, nz, nlp, xp["reward"][1:], xp["mask"][1:], xp["mc_return"][1:], ALPHA, GAMMA, N_DROP)
+        a, lpi = pi(actor, cur)
+        qpi = torch.cat([c(torch.cat((cur.detach(), a), -1)) for c in crit], -1).mean(-1, keepdim=True)
+        loss = (ql + (lpi - qpi)).mean() / T
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            for t_, s_ in zip(list(crit_t.parameters()) + list(actor_t.parameters()), list(crit.parameters()) + list(actor.parameters())):
+                t_.lerp_(s_, 5e-3)
+    update()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        update()
+    el = (time.perf_counter() - t0) / 2
+    return {"ms_per_update": el * 1e3, "updates_per_s": 1 / el, "transitions_per_s": B / el, "threads": torch.get_num_threads(),
+            "params": int(sum(p_.numel() for p_ in params))}
 
 
 def main():

@@ -21,7 +21,7 @@ ROLE_BY_NAME = {"reward": ROLE_REWARD, "task_done": ROLE_TASK_DONE, "episode_don
                 "desired_goal": ROLE_DESIRED_GOAL}
 REWARD_NONE, REWARD_BITFLIP, REWARD_ALL_GEQ, REWARD_FIRST_GEQ, REWARD_WEIGHTED_PNORM = range(5)
 GOAL_FINAL, GOAL_RANDOM, GOAL_FUTURE = range(3)
-OPT_EXACT_EPISODE_STEP, OPT_EMIT_LEARNER_AUX = 1, 2
+OPT_EXACT_EPISODE_STEP, OPT_EMIT_LEARNER_AUX, OPT_CORESIDENT = 1, 2, 4
 
 
 class FdqlError(RuntimeError):
@@ -65,6 +65,7 @@ _SIGNATURES = {
     "fdql_sample_gather_draw": (C.c_int, [_p, _i64, _i32, _i32, _f32, _u64, _u64, _p, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _u32, _i32,
                                           _pp, _p, _p, _p, _p]),
     "fdql_debug_force_generic_gather": (C.c_int, [C.c_int]),
+    "fdql_set_coresident": (C.c_int, [C.c_int]),
     "fdql_debug_tqc_warp_kernel": (C.c_int, [C.c_int]),
     "fdql_tqc_loss": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p]),
     "fdql_tqc_loss_dev_alpha": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),

@@ -129,6 +129,7 @@ struct GatherArgs {
   int64_t* starts_out;
   uint8_t* flags_out;
   int64_t* goal_out;
+  int32_t dbg;       // probe switches of the lean kernel (1: no wide-key phase, 2: no scalar phase)
   int32_t use_link;  // tile kernel, equality rewards: link records are valid for this gamma -> O(hits) relabelled returns
   double log2_gamma, inv_gamma;
 };
@@ -822,16 +823,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   }
 }
 
-// =================================================================================================
-// Tile kernel (plain gather and equality-reward hindsight): a block owns a tile of 256 sampled windows.
-//   phase 1, one THREAD per window -- everything scalar: index / goal streams, episode extents, the hindsight scan over
-//     the tail's 16-byte scan records (hash match -> verified), the return recurrence in the reference's own order
-//     (fp64 step, fp32 store: bit-exact mc_return), task_done / episode_step re-basing, every scalar key of the row and
-//     the learner aux.  All 32 lanes of a warp work on different windows, stores are coalesced over the batch index.
-//   phase 2, one WARP per window -- the wide keys: each lane owns <= S float4 of a row (row plan in registers), loads of four
-//     windows are in flight before their stores; the desired_goal lanes read the hindsight goal row instead.
-// The two phases meet in 12 bytes of shared memory per window (start row, goal row, last in-episode window row).
-// =================================================================================================
 constexpr int kTileWindows = 256;
 #ifndef TILE_MINB
 #define TILE_MINB 4
@@ -843,6 +834,231 @@ constexpr int kTileWindows = 256;
 #define WIN_UNROLL 2
 #endif
 
+// Phase 1 of the tile / lean kernels for ONE window (one thread): everything scalar -- index / goal streams (drawn here when DRAW),
+// episode extents, hindsight reward / task_done / episode_step, the relabelled return, every scalar key and the learner aux are
+// written to the time-major outputs; returns what the wide-key phase needs (start row, goal row, last in-episode window row or -1).
+template <bool HASH, bool DRAW>
+__device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t b, uint64_t draw_ctr, int& s_out, int& grow_out,
+                                                    int& tail_out) {
+  const ArenaDev& A = g.A;
+  const int T = g.T;
+  const int cap32 = (int)A.capacity, len32 = (int)g.len;
+  const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t s64;
+  bool relabel = false;
+  int tail_last = -1, ep_first = 0, grow = 0;
+  if (DRAW) {  // fused draw: same generator, same streams as sample_streams_kernel
+    int64_t g64;
+    bool f;
+    int es, ee;
+    draw_window(A, b, g.draw_range, g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64, es, ee);
+    if (g.starts_out) g.starts_out[b] = s64;
+    if (g.flags_out) g.flags_out[b] = f ? 1 : 0;
+    if (g.goal_out) g.goal_out[b] = g64;
+    if (HASH && f) {
+      relabel = true;
+      ep_first = es;
+      tail_last = ee - (int)s64 + (ee < (int)s64 ? cap32 : 0);
+      grow = (int)g64;
+    }
+  } else {
+    s64 = __ldg(g.starts + b);
+    if (s64 >= g.len) s64 %= g.len;
+    if (HASH && g.flags != nullptr && __ldg(g.flags + b) != 0) {
+      const float* rec = A.rec + s64 * A.rec_stride;
+      const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
+      if (es >= 0) {
+        relabel = true;
+        ep_first = es;
+        tail_last = ee - (int)s64 + (ee < (int)s64 ? cap32 : 0);
+        grow = (int)__ldg(g.goal_rows + b);
+      }
+    }
+  }
+  const int s = (int)s64;
+  s_out = s;
+  grow_out = grow;
+  tail_out = tail_last;
+  float* o_ret = A.col_mc_return >= 0 ? g.out.p[A.scal_key[A.col_mc_return]] : nullptr;
+
+  float4 gsc = zero4;
+  int gd = -1;
+  // the hindsight predicate of one tail row: R(ag_j, g*) == 0  <=>  achieved_goal[row] == achieved_goal[goal_row]
+  auto matches = [&](int j, const float4& r) {
+    bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+    if (m) {  // hash match: the goal row itself is equal unless it holds a NaN; any other row is verified
+      if (j == gd) m = (__float_as_uint(r.w) & 1u) == 0u;
+      else m = rows_equal(A, ring_row32(s, j, cap32), grow);
+    }
+    return m;
+  };
+  // ---- link path (common.cuh): the rows that hit g* are the chain of bit-identical achieved goals through the goal row, so
+  // the relabelled return of window row t is GA_t + sum_{hits m >= t} gamma^(m-t); nothing is read from the rest of the tail
+  bool linked = false;
+  uint32_t inwin = 0;  // bit t: window row t hits the goal
+  double W = 0.0;      // sum over the hits m >= 0 (relative to the window start) of gamma^m
+  int seg_first = -1;  // first row of the synthetic episode the window starts in, episode-relative (exact mode)
+  int j0 = 0;
+  if (HASH && relabel) j0 = s - ep_first + (s < ep_first ? cap32 : 0);
+  if (HASH && relabel && g.use_link) {
+    const int jg = grow - ep_first + (grow < ep_first ? cap32 : 0);
+    const float4 lg = __ldg(A.link + grow);
+    const int pk = __float_as_int(lg.z);
+    if (pk >= 0 && jg <= j0 + tail_last) {  // a chain exists and the goal row belongs to this episode
+      linked = true;
+      int near_before = -0x40000000;
+      if (((pk >> 30) & 1) == 0) {  // a goal holding a NaN is hit by nothing, not even by its own row
+        auto visit = [&](int m) {
+          if (m >= 0) {
+            W += exp2((double)m * g.log2_gamma);
+            if (m < T) inwin |= 1u << m;
+          } else {
+            near_before = max(near_before, m);
+          }
+        };
+        const int mg = jg - j0;
+        visit(mg);
+        if (mg >= 0) {  // towards the window start; the first hit before it ends the walk
+          int cur = mg, d = __float_as_int(lg.w);
+          while (d > 0) {
+            cur -= d;
+            visit(cur);
+            if (cur < 0) break;
+            d = __float_as_int(__ldg(A.link + ring_row32(ep_first, j0 + cur, cap32)).w);
+          }
+        }
+        int cur = mg, d = pk & 0x7fff;
+        while (d > 0) {  // towards the episode end
+          cur += d;
+          visit(cur);
+          d = __float_as_int(__ldg(A.link + ring_row32(ep_first, j0 + cur, cap32)).z) & 0x7fff;
+        }
+      }
+      if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) seg_first = near_before < 0 && near_before > -0x40000000 ? j0 + near_before + 1 : 0;
+    }
+  }
+  if (HASH && relabel && !linked) {
+    gsc = __ldg(A.scan + grow);
+    gd = grow - s + (grow < s ? cap32 : 0);
+    // return-to-go over the whole real episode with relabelled rewards (quirk Q5), newest row first, each step in fp64
+    // and rounded to fp32 on store exactly like nstep_return.py:69-72
+    float acc = 0.f;
+    bool first = true;
+    constexpr int UR = TAIL_UNROLL;  // scan records in flight per thread (per-thread L2 prefetches were measured slower)
+    for (int jt = tail_last; jt >= 0; jt -= UR) {
+      float4 r4[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) r4[u] = jt - u >= 0 ? __ldg(A.scan + ring_row32(s, jt - u, cap32)) : zero4;
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const int j = jt - u;
+        if (j < 0) break;
+        const bool m = matches(j, r4[u]);
+        const float rnew = (float)((double)r4[u].z + (m ? 0.0 : -1.0));
+        acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
+        first = false;
+        if (j < T && o_ret != nullptr) st_stream1(o_ret + (int64_t)j * g.n + b, acc);
+      }
+    }
+    // first row of the synthetic episode the window starts in (exact mode scans the episode prefix, her.py:72-83)
+    if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+      seg_first = 0;
+      for (int j = j0 - 1; j >= 0; --j) {
+        const int row = ring_row32(ep_first, j, cap32);
+        const float4 r = __ldg(A.scan + row);
+        bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+        if (m) {
+          if (row == grow) m = (__float_as_uint(r.w) & 1u) == 0u;
+          else m = rows_equal(A, row, grow);
+        }
+        if (m) {
+          seg_first = j + 1;
+          break;
+        }
+      }
+    }
+  }
+  double gp = 1.0, gi = 1.0, Wsub = 0.0;  // gamma^t, gamma^-t, hits before window row t
+  // forward over the window rows: scalar keys (with the hindsight overrides) and the learner aux
+  float prev_step = 0.f, prev_mask = 0.f, csum = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const int row = ring_row32(s, t, len32);
+    const float* rec = A.rec + (int64_t)row * A.rec_stride;
+    const bool in_ep = HASH && relabel && t <= tail_last;
+    float v_step = A.col_ep_step >= 0 ? __ldg(rec + A.col_ep_step) : 0.f;
+    float v_done = A.col_task_done >= 0 ? __ldg(rec + A.col_task_done) : 0.f;
+    float v_rew = 0.f;
+    if (in_ep) {
+      bool m;
+      if (linked) {
+        const float4 lt = __ldg(A.link + ring_row32(s, t, cap32));
+        m = ((inwin >> t) & 1u) != 0u;
+        v_rew = (float)((double)lt.y + (m ? 0.0 : -1.0));
+        if (o_ret != nullptr) st_stream1(o_ret + (int64_t)t * g.n + b, (float)((double)lt.x + gi * (W - Wsub)));
+        if (m) Wsub += gp;
+        gp *= g.gamma;
+        gi *= g.inv_gamma;
+      } else {
+        const float4 r = __ldg(A.scan + ring_row32(s, t, cap32));
+        m = matches(t, r);
+        v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
+      }
+      v_done = m ? 1.f : 0.f;
+      if (seg_first >= 0 && A.col_ep_step >= 0)
+        v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + A.col_ep_step);
+      if (m) seg_first = j0 + t + 1;
+    }
+    for (int c = 0; c < A.n_scal; ++c) {
+      float* o = g.out.p[A.scal_key[c]];
+      if (o == nullptr) continue;
+      float val;
+      if (c == A.col_ep_step) val = v_step;
+      else if (c == A.col_task_done) val = v_done;
+      else if (in_ep && c == A.col_reward) val = v_rew;
+      else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
+      else val = __ldg(rec + c);
+      st_stream1(o + (int64_t)t * g.n + b, val);
+    }
+    if (want_aux) {
+      // mask = !task_done (deepQlearning.py:201); is_contiguous[t-1] = (step[t]==step[t-1]+1) & mask[t-1] (:202-203)
+      const float v_mask = v_done != 0.f ? 0.f : 1.f;
+      if (g.aux_mask) st_stream1(g.aux_mask + (int64_t)t * g.n + b, v_mask);
+      if (t > 0) {
+        const float c = (v_step == prev_step + 1.f && prev_mask != 0.f) ? 1.f : 0.f;
+        csum += c;
+        if (g.aux_contig) st_stream1(g.aux_contig + (int64_t)(t - 1) * g.n + b, c);
+        if (g.aux_weight && T > 2) g.aux_weight[(int64_t)(t - 1) * g.n + b] = c;  // parked, rescaled below
+      }
+      prev_step = v_step;
+      prev_mask = v_mask;
+    }
+  }
+  if (want_aux && g.aux_weight && T >= 2) {
+    // upstream weight of q_loss[t,b]: contig / ((sum_t contig + 1e-4) * B * T)  (deepQlearning.py:222-225,249)
+    const float scale = g.inv_bt / (csum + 1e-4f);
+    if (T == 2) {
+      st_stream1(g.aux_weight + b, csum * scale);
+    } else {
+      for (int t = 0; t < T - 1; ++t) {
+        float* w = g.aux_weight + (int64_t)t * g.n + b;
+        *w = *w * scale;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// Tile kernel (plain gather and equality-reward hindsight): a block owns a tile of 256 sampled windows.
+//   phase 1, one THREAD per window -- everything scalar: index / goal streams, episode extents, the hindsight scan over
+//     the tail's 16-byte scan records (hash match -> verified), the return recurrence in the reference's own order
+//     (fp64 step, fp32 store: bit-exact mc_return), task_done / episode_step re-basing, every scalar key of the row and
+//     the learner aux.  All 32 lanes of a warp work on different windows, stores are coalesced over the batch index.
+//   phase 2, one WARP per window -- the wide keys: each lane owns <= S float4 of a row (row plan in registers), loads of four
+//     windows are in flight before their stores; the desired_goal lanes read the hindsight goal row instead.
+// The two phases meet in 12 bytes of shared memory per window (start row, goal row, last in-episode window row).
+// =================================================================================================
+
 template <int S, bool HASH, bool DRAW>
 __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_kernel(const __grid_constant__ GatherArgs g) {
   __shared__ int sm_s[kTileWindows], sm_grow[kTileWindows], sm_tail[kTileWindows];
@@ -850,8 +1066,7 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
   const int lane = lane_id();
   const int wib = threadIdx.x >> 5;
   const int T = g.T;
-  const int cap32 = (int)A.capacity, len32 = (int)g.len;
-  const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
+  const int len32 = (int)g.len;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // ---- the lane's plan for phase 2: wide keys only ---------------------------------------------------------------
@@ -892,208 +1107,11 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
 
     // ================= phase 1: thread <-> window =================
     if ((int)threadIdx.x < n_here) {
-      const int64_t b = b0 + threadIdx.x;
-      int64_t s64;
-      bool relabel = false;
-      int tail_last = -1, ep_first = 0, grow = 0;
-      if (DRAW) {  // fused draw: same generator, same streams as sample_streams_kernel
-        int64_t g64;
-        bool f;
-        int es, ee;
-        draw_window(A, b, g.draw_range, g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64, es, ee);
-        if (g.starts_out) g.starts_out[b] = s64;
-        if (g.flags_out) g.flags_out[b] = f ? 1 : 0;
-        if (g.goal_out) g.goal_out[b] = g64;
-        if (HASH && f) {
-          relabel = true;
-          ep_first = es;
-          tail_last = ee - (int)s64 + (ee < (int)s64 ? cap32 : 0);
-          grow = (int)g64;
-        }
-      } else {
-        s64 = __ldg(g.starts + b);
-        if (s64 >= g.len) s64 %= g.len;
-        if (HASH && g.flags != nullptr && __ldg(g.flags + b) != 0) {
-          const float* rec = A.rec + s64 * A.rec_stride;
-          const int es = __float_as_int(__ldg(rec + A.col_ep_start)), ee = __float_as_int(__ldg(rec + A.col_ep_end));
-          if (es >= 0) {
-            relabel = true;
-            ep_first = es;
-            tail_last = ee - (int)s64 + (ee < (int)s64 ? cap32 : 0);
-            grow = (int)__ldg(g.goal_rows + b);
-          }
-        }
-      }
-      const int s = (int)s64;
+      int s, grow, tail_last;
+      window_scalar_phase<HASH, DRAW>(g, b0 + threadIdx.x, draw_ctr, s, grow, tail_last);
       sm_s[threadIdx.x] = s;
       sm_grow[threadIdx.x] = grow;
       sm_tail[threadIdx.x] = tail_last;
-      float* o_ret = A.col_mc_return >= 0 ? g.out.p[A.scal_key[A.col_mc_return]] : nullptr;
-
-      float4 gsc = zero4;
-      int gd = -1;
-      // the hindsight predicate of one tail row: R(ag_j, g*) == 0  <=>  achieved_goal[row] == achieved_goal[goal_row]
-      auto matches = [&](int j, const float4& r) {
-        bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
-        if (m) {  // hash match: the goal row itself is equal unless it holds a NaN; any other row is verified
-          if (j == gd) m = (__float_as_uint(r.w) & 1u) == 0u;
-          else m = rows_equal(A, ring_row32(s, j, cap32), grow);
-        }
-        return m;
-      };
-      // ---- link path (common.cuh): the rows that hit g* are the chain of bit-identical achieved goals through the goal row, so
-      // the relabelled return of window row t is GA_t + sum_{hits m >= t} gamma^(m-t); nothing is read from the rest of the tail
-      bool linked = false;
-      uint32_t inwin = 0;  // bit t: window row t hits the goal
-      double W = 0.0;      // sum over the hits m >= 0 (relative to the window start) of gamma^m
-      int seg_first = -1;  // first row of the synthetic episode the window starts in, episode-relative (exact mode)
-      int j0 = 0;
-      if (HASH && relabel) j0 = s - ep_first + (s < ep_first ? cap32 : 0);
-      if (HASH && relabel && g.use_link) {
-        const int jg = grow - ep_first + (grow < ep_first ? cap32 : 0);
-        const float4 lg = __ldg(A.link + grow);
-        const int pk = __float_as_int(lg.z);
-        if (pk >= 0 && jg <= j0 + tail_last) {  // a chain exists and the goal row belongs to this episode
-          linked = true;
-          int near_before = -0x40000000;
-          if (((pk >> 30) & 1) == 0) {  // a goal holding a NaN is hit by nothing, not even by its own row
-            auto visit = [&](int m) {
-              if (m >= 0) {
-                W += exp2((double)m * g.log2_gamma);
-                if (m < T) inwin |= 1u << m;
-              } else {
-                near_before = max(near_before, m);
-              }
-            };
-            const int mg = jg - j0;
-            visit(mg);
-            if (mg >= 0) {  // towards the window start; the first hit before it ends the walk
-              int cur = mg, d = __float_as_int(lg.w);
-              while (d > 0) {
-                cur -= d;
-                visit(cur);
-                if (cur < 0) break;
-                d = __float_as_int(__ldg(A.link + ring_row32(ep_first, j0 + cur, cap32)).w);
-              }
-            }
-            int cur = mg, d = pk & 0x7fff;
-            while (d > 0) {  // towards the episode end
-              cur += d;
-              visit(cur);
-              d = __float_as_int(__ldg(A.link + ring_row32(ep_first, j0 + cur, cap32)).z) & 0x7fff;
-            }
-          }
-          if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) seg_first = near_before < 0 && near_before > -0x40000000 ? j0 + near_before + 1 : 0;
-        }
-      }
-      if (HASH && relabel && !linked) {
-        gsc = __ldg(A.scan + grow);
-        gd = grow - s + (grow < s ? cap32 : 0);
-        // return-to-go over the whole real episode with relabelled rewards (quirk Q5), newest row first, each step in fp64
-        // and rounded to fp32 on store exactly like nstep_return.py:69-72
-        float acc = 0.f;
-        bool first = true;
-        constexpr int UR = TAIL_UNROLL;  // scan records in flight per thread (per-thread L2 prefetches were measured slower)
-        for (int jt = tail_last; jt >= 0; jt -= UR) {
-          float4 r4[UR];
-#pragma unroll
-          for (int u = 0; u < UR; ++u) r4[u] = jt - u >= 0 ? __ldg(A.scan + ring_row32(s, jt - u, cap32)) : zero4;
-#pragma unroll
-          for (int u = 0; u < UR; ++u) {
-            const int j = jt - u;
-            if (j < 0) break;
-            const bool m = matches(j, r4[u]);
-            const float rnew = (float)((double)r4[u].z + (m ? 0.0 : -1.0));
-            acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
-            first = false;
-            if (j < T && o_ret != nullptr) st_stream1(o_ret + (int64_t)j * g.n + b, acc);
-          }
-        }
-        // first row of the synthetic episode the window starts in (exact mode scans the episode prefix, her.py:72-83)
-        if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
-          seg_first = 0;
-          for (int j = j0 - 1; j >= 0; --j) {
-            const int row = ring_row32(ep_first, j, cap32);
-            const float4 r = __ldg(A.scan + row);
-            bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
-            if (m) {
-              if (row == grow) m = (__float_as_uint(r.w) & 1u) == 0u;
-              else m = rows_equal(A, row, grow);
-            }
-            if (m) {
-              seg_first = j + 1;
-              break;
-            }
-          }
-        }
-      }
-      double gp = 1.0, gi = 1.0, Wsub = 0.0;  // gamma^t, gamma^-t, hits before window row t
-      // forward over the window rows: scalar keys (with the hindsight overrides) and the learner aux
-      float prev_step = 0.f, prev_mask = 0.f, csum = 0.f;
-      for (int t = 0; t < T; ++t) {
-        const int row = ring_row32(s, t, len32);
-        const float* rec = A.rec + (int64_t)row * A.rec_stride;
-        const bool in_ep = HASH && relabel && t <= tail_last;
-        float v_step = A.col_ep_step >= 0 ? __ldg(rec + A.col_ep_step) : 0.f;
-        float v_done = A.col_task_done >= 0 ? __ldg(rec + A.col_task_done) : 0.f;
-        float v_rew = 0.f;
-        if (in_ep) {
-          bool m;
-          if (linked) {
-            const float4 lt = __ldg(A.link + ring_row32(s, t, cap32));
-            m = ((inwin >> t) & 1u) != 0u;
-            v_rew = (float)((double)lt.y + (m ? 0.0 : -1.0));
-            if (o_ret != nullptr) st_stream1(o_ret + (int64_t)t * g.n + b, (float)((double)lt.x + gi * (W - Wsub)));
-            if (m) Wsub += gp;
-            gp *= g.gamma;
-            gi *= g.inv_gamma;
-          } else {
-            const float4 r = __ldg(A.scan + ring_row32(s, t, cap32));
-            m = matches(t, r);
-            v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
-          }
-          v_done = m ? 1.f : 0.f;
-          if (seg_first >= 0 && A.col_ep_step >= 0)
-            v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + A.col_ep_step);
-          if (m) seg_first = j0 + t + 1;
-        }
-        for (int c = 0; c < A.n_scal; ++c) {
-          float* o = g.out.p[A.scal_key[c]];
-          if (o == nullptr) continue;
-          float val;
-          if (c == A.col_ep_step) val = v_step;
-          else if (c == A.col_task_done) val = v_done;
-          else if (in_ep && c == A.col_reward) val = v_rew;
-          else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
-          else val = __ldg(rec + c);
-          st_stream1(o + (int64_t)t * g.n + b, val);
-        }
-        if (want_aux) {
-          // mask = !task_done (deepQlearning.py:201); is_contiguous[t-1] = (step[t]==step[t-1]+1) & mask[t-1] (:202-203)
-          const float v_mask = v_done != 0.f ? 0.f : 1.f;
-          if (g.aux_mask) st_stream1(g.aux_mask + (int64_t)t * g.n + b, v_mask);
-          if (t > 0) {
-            const float c = (v_step == prev_step + 1.f && prev_mask != 0.f) ? 1.f : 0.f;
-            csum += c;
-            if (g.aux_contig) st_stream1(g.aux_contig + (int64_t)(t - 1) * g.n + b, c);
-            if (g.aux_weight && T > 2) g.aux_weight[(int64_t)(t - 1) * g.n + b] = c;  // parked, rescaled below
-          }
-          prev_step = v_step;
-          prev_mask = v_mask;
-        }
-      }
-      if (want_aux && g.aux_weight && T >= 2) {
-        // upstream weight of q_loss[t,b]: contig / ((sum_t contig + 1e-4) * B * T)  (deepQlearning.py:222-225,249)
-        const float scale = g.inv_bt / (csum + 1e-4f);
-        if (T == 2) {
-          st_stream1(g.aux_weight + b, csum * scale);
-        } else {
-          for (int t = 0; t < T - 1; ++t) {
-            float* w = g.aux_weight + (int64_t)t * g.n + b;
-            *w = *w * scale;
-          }
-        }
-      }
     }
     __syncthreads();
 
@@ -1153,7 +1171,161 @@ __global__ void __launch_bounds__(kTileWindows, TILE_MINB) sample_gather_tile_ke
   }
 }
 
+
+// =================================================================================================
+// Lean kernel: the tile kernel's work with the wide keys moved by the copy engines instead of through registers.
+//   A warp owns a chunk of 32 consecutive windows.  Phase 1 is the same thread-per-window scalar phase (window_scalar_phase).
+//   Phase 2 stages the wide keys of 16 windows x one window row in shared memory with 16-byte asynchronous copies (cp.async:
+//   lane v of the warp owns float4 v of the row, the desired_goal lanes read the hindsight goal row instead) and writes every key
+//   of the stage back with ONE bulk copy (cp.async.bulk shared -> global): the outputs are time-major [T, n, w], so the 16 rows
+//   of a key are contiguous.  Two stages per warp are in flight while the warp runs phase 1 of its next chunk, so a block of a
+//   few warps keeps as many bytes in flight as the tile kernel does with 32 warps per SM, for ~6x fewer issued instructions.
+//   It can therefore run as ONE small block per SM next to the issue-bound loss kernel (FDQL_OPT_CORESIDENT), which is how the
+//   reference overlaps sampling with training (torch_dataloader.py:22-39, a prefetch thread one batch ahead).
+// Served: plain gathers and equality-reward hindsight, every wide key with an output a whole number of float4 and 16-byte aligned
+// outputs, at most 32 float4 per row; everything else takes the tile kernel.
+// =================================================================================================
+constexpr int kLeanWarps = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <bool HASH, bool DRAW, int kLeanStageWindows>
+__global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(const __grid_constant__ GatherArgs g) {
+  extern __shared__ __align__(128) unsigned char lean_smem[];
+  const ArenaDev& A = g.A;
+  const int lane = lane_id();
+  const int wib = threadIdx.x >> 5;
+  const int T = g.T;
+  const int len32 = (int)g.len;
+
+  // ---- row plan: lane v owns float4 v of the concatenated wide row (keys without an output take no lanes) -------------------
+  const char* src = nullptr;   // slab base + 16 * (float4 index inside the key)
+  uint32_t sstride = 0;        // bytes between slab rows
+  uint32_t dst_off = 0;        // byte offset of this lane's float4 inside a stage, window 0
+  uint32_t dst_pitch = 0;      // bytes between windows of the key inside a stage
+  const char* ag_src = nullptr;  // desired_goal lanes: the achieved_goal slab + 16 * (float4 index), read for relabelled rows
+  uint32_t ag_stride = 0;
+  int dg_bias = 0x40000000;    // t + dg_bias <= tail_last  <=>  this lane is a desired_goal lane and window row t is relabelled
+  uint32_t stage_bytes = 0;
+  {
+    int i = lane;
+    bool found = false;
+    uint32_t off = 0;
+    for (int w = 0; w < A.n_wide; ++w) {
+      const int vecs = g.out.p[A.wide[w].key] != nullptr ? A.wide[w].vecs : 0;
+      if (!found && i >= 0 && i < vecs) {
+        found = true;
+        src = reinterpret_cast<const char*>(A.wide[w].base) + 16 * i;
+        sstride = 4u * (uint32_t)A.wide[w].stride;
+        dst_off = off + 16u * i;
+        dst_pitch = 16u * vecs;
+        if (HASH && w == A.wide_dg) {
+          dg_bias = 0;
+          ag_src = reinterpret_cast<const char*>(A.wide[A.wide_ag].base) + 16 * i;
+          ag_stride = 4u * (uint32_t)A.wide[A.wide_ag].stride;
+        }
+      }
+      i -= vecs;
+      off += 16u * vecs * kLeanStageWindows;
+    }
+    stage_bytes = off;
+  }
+  const bool has_vec = src != nullptr;
+  const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * 2u * stage_bytes;  // two stages per warp
+
+  const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter) : 0;
+  const int64_t n_windows = g.b_end - g.b_begin;
+  const int64_t n_chunks = (n_windows + 31) / 32;
+  const int64_t warps_total = (int64_t)gridDim.x * kLeanWarps;
+  uint32_t it = 0;            // stages issued by this warp
+  // the stage whose copies are in flight and whose write-back is still to be issued
+  int p_t = 0, p_n = 0;
+  int64_t p_b0 = 0;
+  auto finish_stage = [&](uint32_t buf, int t, int64_t b0, int nw) {
+    // (the caller has waited for the stage's cp.async groups)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy engine
+    __syncwarp();
+    if (lane == 0) {  // one bulk copy per key: its 16 rows are contiguous in the stage and in the time-major output
+      uint32_t off = warp_smem + buf * stage_bytes;
+      const int64_t orow = (int64_t)t * g.n + b0;
+      for (int w = 0; w < A.n_wide; ++w) {
+        float* o = g.out.p[A.wide[w].key];
+        if (o == nullptr) continue;
+        const uint32_t row_bytes = 16u * (uint32_t)A.wide[w].vecs;
+        bulk_store_s2g(reinterpret_cast<char*>(o) + orow * (int64_t)row_bytes, off, (uint32_t)nw * row_bytes);
+        off += row_bytes * kLeanStageWindows;
+      }
+      bulk_commit_group();
+    }
+  };
+  for (int64_t chunk = (int64_t)blockIdx.x * kLeanWarps + wib; chunk < n_chunks; chunk += warps_total) {
+    const int64_t cb0 = g.b_begin + chunk * 32;
+    const int n_here = (int)min((int64_t)32, g.b_end - cb0);
+    int s = 0, grow = 0, tail_last = -1;
+    if (g.dbg & 4) {  // probe: the issue load of the scalar phase (~70 warp instructions per window) as a tiny loop of dependent FMAs
+      float x = (float)lane;
+      for (int i = 0; i < 2240; ++i) x = fmaf(x, 1.0001f, 0.5f);
+      if (x == 12345.f) g.aux_mask[0] = x;
+    }
+    if (g.dbg & 2) s = (int)(((cb0 + lane) * 7919) % (len32 - T));
+    else if (lane < n_here) window_scalar_phase<HASH, DRAW>(g, cb0 + lane, draw_ctr, s, grow, tail_last);
+    __syncwarp();
+    for (int t = 0; t < ((g.dbg & 1) ? 0 : T); ++t) {
+      const int t_dg = t + dg_bias;
+      for (int w0 = 0; w0 < n_here; w0 += kLeanStageWindows, ++it) {
+        const int nw = min(kLeanStageWindows, n_here - w0);
+        const uint32_t buf = it & 1u;
+        // the bulk write-back that read this buffer (issued one stage ago, for the stage before that) must be done reading it
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+        uint32_t sdst = warp_smem + buf * stage_bytes + dst_off;
+#pragma unroll 4
+        for (int w = 0; w < nw; ++w, sdst += dst_pitch) {
+          // (registers, not shared memory: next to the loss kernel the shared-memory pipe is the busiest unit of the SM)
+          const int sw = __shfl_sync(kFull, s, w0 + w);
+          const int tlw = __shfl_sync(kFull, tail_last, w0 + w);
+          const int gw = __shfl_sync(kFull, grow, w0 + w);
+          unsigned row = (unsigned)sw + (unsigned)t;
+          if (row >= (unsigned)len32) row -= (unsigned)len32;
+          const char* p = src + (uint64_t)row * sstride;
+          if (HASH && t_dg <= tlw) p = ag_src + (uint64_t)(unsigned)gw * ag_stride;
+          if (has_vec) cp_async16(sdst, p);
+        }
+        cp_async_commit_group();
+        if (it > 0) {  // the previous stage has had a whole stage of issue time to land
+          cp_async_wait_group<1>();
+          finish_stage(buf ^ 1u, p_t, p_b0, p_n);
+        }
+        p_t = t;
+        p_b0 = cb0 + w0;
+        p_n = nw;
+      }
+    }
+  }
+  if (it > 0) {
+    cp_async_wait_group<0>();
+    finish_stage((it - 1) & 1u, p_t, p_b0, p_n);
+  }
+  if (lane == 0) bulk_wait_group_read<0>();
+}
+
 int g_tile_override = 0;
+int g_tile_ctas_per_sm = 0;  // tuning hook: resident tile-kernel blocks per SM (0 = as many as fit)
 int g_force_generic_gather = 0;       // tests flip this to cover the descriptor-walking kernel
 int g_force_full_vector_relabel = 0;  // ... and this to cover MODE 1 with the bitflip functor
 
@@ -1224,6 +1396,53 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   const bool link_ok = hash_ok && a->link_state == 1 && a->link_gamma == gamma && gamma > 0.0 && T <= 32 && !(g_force_generic_gather & 16);
   // with link records the tile kernel has no tail loop and wins from ~1K windows on (measured 4096 windows: 14.7 us vs 19.5 us per call)
   const bool big = (b_end - b_begin) >= 49152 || (link_ok && (b_end - b_begin) >= 1024) || g_tile_override != 0;
+  // lean kernel (wide keys through cp.async staging + bulk write-back): asked for by FDQL_OPT_CORESIDENT (one block per SM, next to
+  // the loss kernel of another stream) or by the tuning hook; needs whole-float4 keys and 16-byte aligned outputs
+  bool lean_ok = wslots <= 1 && wide_vecs > 0 && (!relabel || hash_ok) && !(g_force_generic_gather & (1 | 8));
+  for (int w = 0; w < a->dev.n_wide && lean_ok; ++w) {
+    const float* o = out[a->dev.wide[w].key];
+    if (o != nullptr && ((a->dev.wide[w].width & 3) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0)) lean_ok = false;
+  }
+  const bool coresident = (opts & FDQL_OPT_CORESIDENT) != 0;
+  if (lean_ok && (coresident || (g_force_generic_gather & 32))) {
+    g.use_link = link_ok;
+    g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
+    g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
+    const int stage_w = coresident ? 8 : 16;  // co-resident: two blocks of half-size stages per SM (eight warps in 54 KB)
+    const size_t lean_smem = (size_t)kLeanWarps * 2 * stage_w * 16 * wide_vecs;
+    const int64_t chunks = (b_end - b_begin + 31) / 32;
+    g.dbg = (g_force_generic_gather >> 6) & 7;
+#define FDQL_LAUNCH_LEAN(HASHV, DRAWV)                                                                                     \
+  do {                                                                                                                     \
+    auto kern = coresident ? sample_gather_lean_kernel<HASHV, DRAWV, 8> : sample_gather_lean_kernel<HASHV, DRAWV, 16>;     \
+    static int per_sm_cached2[2] = {0, 0};                                                                                 \
+    static size_t smem_cached2[2] = {0, 0};                                                                                \
+    int& per_sm_cached = per_sm_cached2[coresident ? 1 : 0];                                                               \
+    size_t& smem_cached = smem_cached2[coresident ? 1 : 0];                                                                \
+    if (per_sm_cached == 0 || smem_cached != lean_smem) {                                                                  \
+      FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem));                  \
+      FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+      FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, kern, kLeanWarps * 32, lean_smem));          \
+      if (per_sm_cached < 1) per_sm_cached = 1;                                                                            \
+      smem_cached = lean_smem;                                                                                             \
+    }                                                                                                                      \
+    int per_sm = coresident ? (per_sm_cached < 2 ? per_sm_cached : 2) : per_sm_cached;                                     \
+    if (g_tile_ctas_per_sm > 0 && g_tile_ctas_per_sm < per_sm) per_sm = g_tile_ctas_per_sm;                                \
+    int64_t blocks = (chunks + kLeanWarps - 1) / kLeanWarps;                                                               \
+    if (blocks > (int64_t)a->num_sms * per_sm) blocks = (int64_t)a->num_sms * per_sm;                                      \
+    kern<<<(unsigned)blocks, kLeanWarps * 32, lean_smem, st>>>(g);                                                         \
+  } while (0)
+    if (hash_ok) {
+      if (draw != nullptr) FDQL_LAUNCH_LEAN(true, true);
+      else FDQL_LAUNCH_LEAN(true, false);
+    } else {
+      if (draw != nullptr) FDQL_LAUNCH_LEAN(false, true);
+      else FDQL_LAUNCH_LEAN(false, false);
+    }
+#undef FDQL_LAUNCH_LEAN
+    FDQL_CUDA(cudaGetLastError());
+    return FDQL_OK;
+  }
   if (wslots <= 4 && (!relabel || hash_ok) && big && !(g_force_generic_gather & (1 | 8))) {
     // tile size: 256 windows when there is enough work to fill the machine, down to 32 for small batches
     int tile_w = kTileWindows;
@@ -1243,7 +1462,8 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
       FDQL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWindows, 0));                  \
       if (per_sm < 1) per_sm = 1;                                                                                \
     }                                                                                                            \
-    if (tiles > (int64_t)a->num_sms * per_sm) tiles = (int64_t)a->num_sms * per_sm;                              \
+    const int use_per_sm = g_tile_ctas_per_sm > 0 && g_tile_ctas_per_sm < per_sm ? g_tile_ctas_per_sm : per_sm; \
+    if (tiles > (int64_t)a->num_sms * use_per_sm) tiles = (int64_t)a->num_sms * use_per_sm;                      \
     kern<<<(unsigned)tiles, kTileWindows, 0, st>>>(g);                                                           \
   } while (0)
 #define FDQL_TILE_S(HASHV)                                   \
@@ -1338,9 +1558,11 @@ extern "C" {
 
 int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
-  g_tile_override = (on >> 8) & 0x1ff;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
-  g_force_generic_gather = on & 29;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
-                                     // bit 3: warp-per-window kernels instead of the tile kernel, bit 4: tile kernel without link records
+  g_tile_override = (on >> 8) & 0x1e0;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
+  g_tile_ctas_per_sm = (on >> 20) & 0xf;  // bits 20..23: resident tile-kernel blocks per SM (0 = as many as fit)
+  g_force_generic_gather = on & 509;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
+                                     // bit 3: warp-per-window kernels instead of the tile kernel, bit 4: tile kernel without link records,
+                                     // bit 5: lean kernel (cp.async staging + bulk write-back) wherever it can serve
   g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }

@@ -545,8 +545,11 @@ __device__ __forceinline__ bool grp_stage_rows(float* dst, const float* __restri
 constexpr int kGrpLb = 1, kGrpStats = 2, kGrpFull = 4;  // kernel flavours: lower bound (mc_return given), summaries (stats given),
                                                           // every atom slot but the last one holds 32 real atoms (n_atoms > 32 * (R - 1))
 
+#ifndef FDQL_TQC_BOUND_THREADS
+#define FDQL_TQC_BOUND_THREADS 768  // register budget of the group kernel: 65536 / 768 -> 80 per thread (it needs 72)
+#endif
 template <int NT, int FLAGS>
-__global__ void __launch_bounds__(GrpCfg<NT>::kMaxWarps * 32, 1) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
+__global__ void __launch_bounds__(FDQL_TQC_BOUND_THREADS, 1) tqc_loss_group_kernel(const __grid_constant__ TqcArgs a) {
   using C = GrpCfg<NT>;
   constexpr int E = C::E, LPT = C::LPT, G = C::G, R = C::R, TP = C::TP;
   constexpr bool LB = (FLAGS & kGrpLb) != 0, STATS = (FLAGS & kGrpStats) != 0, FULL = (FLAGS & kGrpFull) != 0;
@@ -1003,6 +1006,7 @@ static int num_sms() {
 int g_tqc_warp_kernel = 0;  // test hook: 1 = always the warp-per-transition kernel
 
 int g_tqc_grp_warps = 0;  // test / tuning hook: warps per block of the group kernel (0 = automatic)
+int g_tqc_coresident = 0; // fdql_set_coresident: leave room on every SM for one lean gather block of another stream
 
 template <int NT, int FLAGS>
 static int launch_tqc_group_f(const TqcArgs& a0, cudaStream_t st) {
@@ -1011,7 +1015,7 @@ static int launch_tqc_group_f(const TqcArgs& a0, cudaStream_t st) {
   const int64_t n_groups = (a.M + C::G - 1) / C::G;
   // the per-lane sums of transition t (three rows) fit into the dead q_pred rows 0..t when a row is at least as long as they are
   a.grp_red_alias = a.n_atoms >= 3 * C::kRedPitch ? 1 : 0;
-  const int auto_warps = a.grp_red_alias ? C::kWarpsAlias : C::kWarps;
+  const int auto_warps = (a.grp_red_alias && !g_tqc_coresident) ? C::kWarpsAlias : C::kWarps;
   const int full_warps = g_tqc_grp_warps > 0 && g_tqc_grp_warps < auto_warps ? g_tqc_grp_warps : auto_warps;
   const int warp_floats = a.grp_red_alias ? C::kWarpFloatsAlias : C::kWarpFloats;
   // large batches: one block per SM (its warps share a work counter, see the kernel); batches of at most two rounds per warp: the
@@ -1028,6 +1032,10 @@ static int launch_tqc_group_f(const TqcArgs& a0, cudaStream_t st) {
                                                   ? C::kWarps * C::kWarpFloats
                                                   : C::kWarpsAlias * C::kWarpFloatsAlias);
     FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeed));
+    // the whole unified L1 / shared memory as shared memory: the SM's split is fixed while a block is resident, and a block of a
+    // co-resident gather (FDQL_OPT_CORESIDENT) only fits next to this one under the largest carve-out
+    FDQL_CUDA(cudaFuncSetAttribute(tqc_loss_group_kernel<NT, FLAGS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
   }
   int& per_sm = per_sm_cached[small ? 1 : 0][a.grp_red_alias];
   if (per_sm == 0) {
@@ -1082,6 +1090,12 @@ static int launch_tqc(const TqcArgs& a, cudaStream_t st) {
 using namespace fdql;
 
 extern "C" {
+
+int fdql_set_coresident(int on) {
+  const int old = g_tqc_coresident;
+  g_tqc_coresident = on != 0;
+  return old;
+}
 
 int fdql_debug_tqc_warp_kernel(int on) {
   const int old = g_tqc_warp_kernel | (g_tqc_grp_warps << 8);

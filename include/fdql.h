@@ -65,6 +65,10 @@ enum {
 /* fdql_sample_gather option bits */
 #define FDQL_OPT_EXACT_EPISODE_STEP 1u /* scan the episode prefix so relabelled episode_step equals her.py:72-83 bit for bit */
 #define FDQL_OPT_EMIT_LEARNER_AUX 2u   /* also write mask / is_contiguous / upstream weight (deepQlearning.py:201-203,222-225) */
+#define FDQL_OPT_CORESIDENT 4u         /* this gather runs on one stream while a loss kernel runs on another (the reference's prefetch
+                                          thread, torch_dataloader.py:22-39): take ONE small block per SM whose wide keys move through
+                                          cp.async staging + bulk write-back, leaving the issue slots to the loss kernel.  See
+                                          fdql_set_coresident.  Shapes the lean kernel does not serve ignore the bit. */
 
 typedef struct fdql_arena fdql_arena;
 
@@ -191,6 +195,11 @@ int fdql_debug_force_generic_gather(int on);
 /* test hook (returns the previous setting): 1 routes the TQC / quantile-Huber losses through the warp-per-transition kernel
  * that serves more than 128 atoms instead of the quad kernel (4 lanes per transition) */
 int fdql_debug_tqc_warp_kernel(int on);
+
+/* Co-residency of the two hot kernels (returns the previous setting).  on != 0: the loss kernels (fdql_tqc_loss*, fdql_quantile_huber)
+ * size their blocks so that every SM keeps room for one block of a gather launched with FDQL_OPT_CORESIDENT on another stream
+ * (16 instead of 20 warps of the group kernel: 56 KB of shared memory and a quarter of the register file stay free). */
+int fdql_set_coresident(int on);
 
 /* DistributionalSoftActorCritic.q_loss from the MLP outputs onward + quantile_huber_loss_f, forward and backward
  * (franQ/Agent/components/distributional_soft_actor_critic.py:50-58,70,76-82,90-103): pool+sort the n_atoms target

@@ -14,7 +14,8 @@ units = int(sys.argv[3]) if len(sys.argv) > 3 else 262144
 HERE = os.path.dirname(os.path.abspath(__file__))
 out = [f"# per-line instruction / shared-memory view ({tag}); report {os.path.basename(rep)}; all figures per unit "
        f"(= per transition / window, {units} per launch)\n"]
-for kern, label in (("tqc_loss_group", "tqc_loss_group_kernel"), ("sample_gather_tile", "sample_gather_tile_kernel")):
+for kern, label in (("tqc_loss_group", "tqc_loss_group_kernel"), ("sample_gather_tile", "sample_gather_tile_kernel"),
+                    ("sample_gather_lean", "sample_gather_lean_kernel")):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))

@@ -443,3 +443,86 @@ def test_partly_overwritten_episode_is_not_relabelled(fdql):
         s, f, gr = ring.draw_streams(256, 2, goal_mode=L.GOAL_RANDOM, relabel_prob=1.0)
         s, f = npy(s), npy(f)
         assert not f[(s >= 7) & (s < 20)].any() and f[(s >= 20) & (s < 98)].all()
+
+
+# ------------------------------------------------------------------------------------------------ lean (cp.async + bulk write-back) kernel
+@pytest.mark.parametrize("links", [True, False])
+@pytest.mark.parametrize("T,G,obs,act,B", [(2, 16, 64, 8, 700), (1, 4, 8, 4, 33), (5, 8, 12, 4, 1000), (50, 16, 64, 8, 90), (2, 16, 64, 8, 4096 + 17)])
+def test_lean_kernel_vs_oracle_and_tile_kernel(fdql, T, G, obs, act, B, links):
+    """fdql_sample_gather through the lean kernel (cp.async staging of 16-window stages, one bulk shared->global copy per key and
+    stage; what FDQL_OPT_CORESIDENT selects): partial chunks, partial stages, windows straddling episode ends and the ring length,
+    relabelled and plain windows mixed -- equal to oracle.sample_time_relabel and, bit for bit, to the tile kernel."""
+    from fastdeepqlearning_b200 import Replay, _lib as L
+    from test_gpu_replay import _synthetic
+    rng = np.random.default_rng(T * 1000 + G + B)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 60, 130, G, obs=obs, act=act)
+    N = int(lengths.sum())
+    ring = Replay.ReplayMemory(N + 3, 16, T)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.98)
+    ring.add_rows(cols, episode_lengths=lengths)
+    starts = rng.integers(0, N - T, B)
+    starts[:3] = [0, N - T - 1, N - T - 1]
+    flags = rng.random(B) < 0.8
+    goal_rows = np.array([rng.integers(s, ends[ep_of[s]] + 1) for s in starts])
+    want = O.sample_time_relabel(cols, starts, T, flags, goal_rows, starts_ep[ep_of], ends[ep_of], O.reward_bitflip, 0.98)
+    lib = fdql.lib()
+    kw = dict(starts=starts, flags=flags.astype(np.uint8), goal_rows=goal_rows, exact_episode_step=True, aux=T > 1, length=N)
+    old = lib.fdql_debug_force_generic_gather(32 | (0 if links else 16))
+    try:
+        got = {k: v.clone() for k, v in ring.temporal_sample(**kw).items()}
+        plain = {k: v.clone() for k, v in ring.temporal_sample(starts=starts, length=N).items()}
+        lib.fdql_debug_force_generic_gather((64 << 8) | (0 if links else 16))
+        tile = ring.temporal_sample(**kw)
+    finally:
+        lib.fdql_debug_force_generic_gather(old)
+    for k in cols:
+        if k in ("reward", "mc_return"):
+            np.testing.assert_allclose(npy(got[k]), want[k], rtol=1e-5, atol=1e-6, err_msg=k)
+        else:
+            np.testing.assert_array_equal(npy(got[k]), want[k], err_msg=k)
+    for k in tile:
+        assert torch_equal(tile[k], got[k]), k
+    idx = np.arange(T)[:, None] + starts[None]
+    for k in cols:
+        np.testing.assert_array_equal(npy(plain[k]), cols[k][idx], err_msg=k)
+
+
+def torch_equal(a, b):
+    import torch
+    return torch.equal(a, b)
+
+
+def test_coresident_option_selects_the_lean_kernel_and_matches(fdql):
+    """FDQL_OPT_CORESIDENT through the fused-draw entry point: identical streams and identical batch to the default kernels."""
+    import ctypes as C
+    import torch
+    from fastdeepqlearning_b200 import Replay, _lib as L
+    from test_gpu_replay import _synthetic
+    rng = np.random.default_rng(77)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 400, 0, 16, obs=64, act=8, fixed_len=64)
+    N = int(lengths.sum())
+    ring = Replay.ReplayMemory(N + 1, 4096, 2)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.99)
+    ring.add_rows(cols, episode_lengths=lengths, with_returns=True)
+    n, T = 8192, 2
+    lib = fdql.lib()
+    res = []
+    for opt in (0, L.OPT_CORESIDENT):
+        out = {k: torch.full((T, n, w), -7.0, device="cuda") for k, w in zip(ring._keys, ring._widths)}
+        aux = [torch.empty(T, n, device="cuda"), torch.empty(T - 1, n, device="cuda"), torch.empty(T - 1, n, device="cuda")]
+        st, fl, go = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda"),
+                      torch.empty(n, dtype=torch.int64, device="cuda"))
+        params, n_params = ring.reward_op.c_params()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        L.check(lib.fdql_sample_gather_draw(ring._h, n, T, L.GOAL_FUTURE, 0.8, 5, 3, None, p(st), p(fl), p(go), ring.reward_op.op, params,
+                                            n_params, 0.99, L.OPT_EMIT_LEARNER_AUX | L.OPT_EXACT_EPISODE_STEP | opt, 4096,
+                                            L.ptr_array([out[k].data_ptr() for k in ring._keys]), *[p(t) for t in aux],
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        res.append((out, aux, st, fl, go))
+    (o0, a0, s0, f0, g0), (o1, a1, s1, f1, g1) = res
+    assert torch.equal(s0, s1) and torch.equal(f0, f1) and torch.equal(g0, g1) and float(f0.float().mean()) > 0.7
+    for k in o0:
+        assert torch.equal(o0[k], o1[k]), k
+    for x, y in zip(a0, a1):
+        assert torch.equal(x, y)
