@@ -391,7 +391,7 @@ def run_ours(args):
             so = {k: torch.empty((T, B, w), device=device) for k, w in zip(keys, ring._widths)}
             slots.append({"out": so, "outp": L.ptr_array([so[k].data_ptr() for k in keys]), "mask": torch.empty(T, B, device=device),
                           "contig": torch.empty(T - 1, B, device=device), "weight": torch.empty(T - 1, B, device=device),
-                          "ctr": torch.zeros(2, dtype=torch.int64, device=device)})
+                          "ctr": torch.zeros(4, dtype=torch.int64, device=device)})
 
         def graph_batch(i, st):
             sl, o, spx = slots[i], i * B, C.c_void_p(st.cuda_stream)

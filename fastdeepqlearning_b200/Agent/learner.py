@@ -56,6 +56,8 @@ class Learner:
         self.replays = list(replays or [])
         self.train_steps = 0
         self._flat = None
+        self._side = None
+        self._prefetched = {}  # replay -> batch sampled during the previous step's gradient all-reduce
         self.last_summaries = {}
 
     def close(self):
@@ -124,15 +126,37 @@ class Learner:
         torch._foreach_copy_([g.reshape(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
 
     def _one_update(self, replay, **sample_kw):
-        xp = replay.temporal_sample(**sample_kw)
+        """sample -> loss -> backward -> gradient all-reduce -> Adam -> targets.  Under torch.distributed the all-reduce runs on a
+        side stream while the main stream already samples and relabels the NEXT step's batch (the only
+        collective of the path hides behind work that does not depend on it); the prefetched batch is consumed by the next call."""
+        key = id(replay)
+        xp = self._prefetched.pop(key, None)
+        if xp is None:
+            xp = replay.temporal_sample(**sample_kw)
         loss = self.get_losses(xp)
         loss.backward()
-        self._allreduce_grads()
+        if self._world_size() > 1 and getattr(self.conf, "overlap_allreduce", True):
+            cur = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._allreduce_grads()
+            # backward has consumed the current batch (stream order), so the same output buffers can take the next one
+            self._prefetched[key] = replay.temporal_sample(**sample_kw)
+            cur.wait_stream(self._side)
+        else:
+            self._allreduce_grads()
         if self.conf.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.params, self.conf.clip_grad_norm)
         self.optimizer.step()
         self.actor_critic.update_target()
         return loss.detach()
+
+    @staticmethod
+    def _world_size():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
     def train_step(self):
         """deepQlearning.py:105-127: for each local shard: sample -> loss -> backward -> (all-reduce) -> Adam -> targets."""
@@ -156,15 +180,14 @@ class Learner:
         ring.flush()
         n_now = len(ring)
         entry = self._graphs.get(i)
-        if entry is not None and abs(n_now - entry[2]) > 0.05 * entry[2]:
-            entry = None  # the sampling range is baked into the captured launch: refresh it when the ring has grown
         if entry is None:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not getattr(self.conf, "graph_allreduce", False):
                 raise RuntimeError("use_cuda_graph with world_size > 1 needs conf.graph_allreduce=True (NCCL capture)")
             if self.conf.clip_grad_norm:
                 raise RuntimeError("clip_grad_norm is not capturable")
-            ring.device_counter = True
+            ring.device_counter = True  # draw counter AND ring length are read from device memory: one capture serves a filling ring
+            ring.publish_len()
             cur = torch.cuda.current_stream(self.device)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(cur)
@@ -180,5 +203,6 @@ class Learner:
                 static_loss = self._one_update(replay, reuse_outputs=True)
             entry = (graph, static_loss, n_now)
             self._graphs[i] = entry
+        ring.publish_len()  # (a no-op unless rows were added since the last step)
         entry[0].replay()
         return entry[1]

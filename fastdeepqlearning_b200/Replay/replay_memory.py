@@ -60,6 +60,7 @@ class ReplayMemory:
         self._rng_counter = 0
         self._rng_counter_dev = None
         self.device_counter = False  # True: the draw counter lives in device memory (CUDA-graph capture of the learner step)
+        self._published_len = -1     # ring length last stored next to the device-side draw counter (see publish_len)
         self._out_cache: T.Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ allocation (replay_memory.py:23-35)
@@ -401,7 +402,7 @@ class ReplayMemory:
             goals = torch.empty(n, dtype=torch.int64, device=self.device)
         self._sync_cursor()
         if self._rng_counter_dev is None:  # {draw counter, block ticket}: lets a captured graph draw fresh streams per replay
-            self._rng_counter_dev = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self._rng_counter_dev = torch.zeros(4, dtype=torch.int64, device=self.device)
         check(self._lib.fdql_sample_streams(self._h, n, Tn, L.GOAL_FUTURE if goal_mode is None else int(goal_mode),
                                             float(relabel_prob), self._rng_seed, self._rng_counter,
                                             C.c_void_p(self._rng_counter_dev.data_ptr()) if self.device_counter else None,
@@ -412,6 +413,15 @@ class ReplayMemory:
         if not self.device_counter:
             self._rng_counter += 1
         return starts, flags, goals
+
+    def publish_len(self):
+        """Store the ring's length next to the device-side draw counter ({counter, ticket, length, 0}): a captured sample / gather
+        launch reads its start range from there, so one captured learner step keeps sampling the whole ring while it fills."""
+        if self._rng_counter_dev is None:
+            self._rng_counter_dev = torch.zeros(4, dtype=torch.int64, device=self.device)
+        if self._published_len != self._curr_len:
+            self._rng_counter_dev[2:3].fill_(self._curr_len)
+            self._published_len = self._curr_len
 
     def _sync_cursor(self):
         top, ln = C.c_int64(), C.c_int64()
@@ -444,7 +454,7 @@ class ReplayMemory:
                 flags = torch.empty(n, dtype=torch.uint8, device=self.device)
                 goal_rows = torch.empty(n, dtype=torch.int64, device=self.device)
             if self._rng_counter_dev is None:
-                self._rng_counter_dev = torch.zeros(2, dtype=torch.int64, device=self.device)
+                self._rng_counter_dev = torch.zeros(4, dtype=torch.int64, device=self.device)
         elif starts is None:
             starts, flags, goal_rows = self.draw_streams(n, Tn, goal_mode, relabel_prob)
         starts = self._to_dev_i64(starts)

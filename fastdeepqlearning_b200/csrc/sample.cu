@@ -61,6 +61,13 @@ __device__ __forceinline__ void draw_window(const ArenaDev& A, int64_t b, int64_
     }
   }
 }
+// counter_dev[2] (optional, non-zero): the ring's current length, so that a captured launch keeps sampling the whole ring while it
+// fills (the range len - T is otherwise baked into the launch)
+__device__ __forceinline__ int64_t device_draw_range(const unsigned long long* counter_dev, int64_t range, int T) {
+  if (counter_dev == nullptr) return range;
+  const unsigned long long len = *reinterpret_cast<const volatile unsigned long long*>(counter_dev + 2);
+  return len != 0ull ? (int64_t)len - T : range;
+}
 // counter_dev (optional): {draw counter, block ticket} in device memory, so that a captured CUDA graph draws fresh streams at
 // every replay.  Every block reads the counter before it takes its ticket; the block with the last ticket advances it.
 __device__ __forceinline__ uint64_t device_draw_counter(unsigned long long* counter_dev, uint64_t counter) {
@@ -85,10 +92,11 @@ __device__ __forceinline__ uint64_t device_draw_counter(unsigned long long* coun
 // starts ~ U[0, len-T) like np.random.randint(0, len-T, B) (replay_memory.py:59); flag ~ Bernoulli(p); goal row by mode
 // over the committed extents of the start row's episode (her.py:48-53).  Uncommitted rows are never relabelled.
 __global__ void __launch_bounds__(256)
-sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int goal_mode, float relabel_prob, uint64_t seed, uint64_t counter,
+sample_streams_kernel(ArenaDev A, int64_t n, int64_t range, int T, int goal_mode, float relabel_prob, uint64_t seed, uint64_t counter,
                       unsigned long long* counter_dev, int64_t* __restrict__ starts, uint8_t* __restrict__ flags,
                       int64_t* __restrict__ goal_rows) {
   counter = device_draw_counter(counter_dev, counter);
+  range = device_draw_range(counter_dev, range, T);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   int64_t s, g;
@@ -852,7 +860,8 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
     int64_t g64;
     bool f;
     int es, ee;
-    draw_window(A, b, g.draw_range, g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64, es, ee);
+    draw_window(A, b, device_draw_range(g.counter_dev, g.draw_range, T), g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64,
+                es, ee);
     if (g.starts_out) g.starts_out[b] = s64;
     if (g.flags_out) g.flags_out[b] = f ? 1 : 0;
     if (g.goal_out) g.goal_out[b] = g64;
@@ -1586,7 +1595,7 @@ int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_
     const int rc = flush_pending_invalidation(a, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  sample_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->dev, n, range, goal_mode, relabel_prob,
+  sample_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->dev, n, range, T, goal_mode, relabel_prob,
                                                                                        seed, counter,
                                                                                        reinterpret_cast<unsigned long long*>(counter_dev),
                                                                                        starts, flags, goal_rows);

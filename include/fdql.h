@@ -155,8 +155,10 @@ int fdql_vmap_select_column(const fdql_arena* a, int64_t n_windows, int32_t T, i
 
 /* np.random.randint(0, len-T, B) (replay_memory.py:59) + HER goal choice (her.py:48-53), drawn on the device with a
  * counter-based generator.  Parity runs inject the streams instead.  flags[b]=1 with probability relabel_prob.
- * counter_dev (may be NULL): two uint64 in device memory {draw counter, 0}; when given, the draw uses counter + *counter_dev and
- * the kernel advances it, so a captured CUDA graph draws fresh streams at every replay. */
+ * counter_dev (may be NULL): four uint64 in device memory {draw counter, 0, ring length or 0, 0}; when given, the draw uses
+ * counter + counter_dev[0] and the kernel advances it, so a captured CUDA graph draws fresh streams at every replay; a non-zero
+ * counter_dev[2] replaces the ring length the launch was given (starts ~ U[0, counter_dev[2] - T)), so the same captured launch keeps
+ * sampling the whole ring while it fills -- the caller stores the length there after every append. */
 int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
                         uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows,
                         void* stream);

@@ -157,6 +157,86 @@ def test_cuda_graph_step_matches_eager_and_draws_fresh_streams(fdql):
     le, _ = build(False)
     le_losses = [float(le.train_step()) for _ in range(3)]
     assert all(np.isfinite(le_losses))
+    # the captured step IS the eager step: the first train_step() of a graphed learner runs three eager warm-up updates and one replay,
+    # with draw counters 0..3 (device side) and the generator's next four noise draws -- four eager steps from the same state must
+    # leave the same weights, targets and temperature
+    lg2, _ = build(True)
+    lg2.train_step()
+    le2, _ = build(False)
+    for _ in range(4):
+        le2.train_step()
+    for (n1, p1), (n2, p2) in zip(lg2.actor_critic.state_dict().items(), le2.actor_critic.state_dict().items()):
+        assert n1 == n2
+        torch.testing.assert_close(p1, p2, rtol=1e-5, atol=1e-6, msg=lambda m, n1=n1: f"{n1}: {m}")
+
+
+def test_graphed_learner_is_captured_once_while_the_ring_fills(fdql):
+    """The sampling range of the captured launch comes from device memory (counter_dev[2]): one capture serves a ring that grows
+    by far more than 5 %, and the new rows are sampled."""
+    import torch
+    from fastdeepqlearning_b200 import Agent, Replay
+    rng = np.random.default_rng(1)
+    Lep = 32
+
+    def episodes(n_eps):
+        N = Lep * n_eps
+        ag = rng.integers(0, 2, (N, 16)).astype(np.float32)
+        dg = np.repeat(rng.integers(0, 2, (n_eps, 16)).astype(np.float32), Lep, 0)
+        hit = (ag == dg).all(-1, keepdims=True).astype(np.float32)
+        step = (np.arange(N) % Lep).astype(np.float32).reshape(-1, 1)
+        return {"obs_1d": rng.standard_normal((N, 64)).astype(np.float32), "action": rng.uniform(-1, 1, (N, 8)).astype(np.float32),
+                "achieved_goal": ag, "desired_goal": dg, "reward": hit - 1, "task_done": hit,
+                "episode_done": (step == Lep - 1).astype(np.float32), "episode_step": step}
+    torch.manual_seed(0)
+    conf = make_conf(Agent, replay_size=40000, use_HER=True, her_mode="future", num_instances=1, temporal_len=2, batch_size=512,
+                     use_cuda_graph=True)
+    read, write = Replay.make(conf, compute_reward=fdql.RewardOp.bitflip())
+    write[0].add_rows(episodes(40), episode_lengths=[Lep] * 40)          # 1280 rows
+    learner = Agent.Learner(conf, read)
+    learner.train_step()
+    graph0 = learner._graphs[0][0]
+    ring = read[0].replay_buffer.replay
+    assert int(ring.last_streams[0].max()) < 1280
+    write[0].add_rows(episodes(900), episode_lengths=[Lep] * 900)        # 30080 rows: 23x the ring the graph was captured on
+    seen = 0
+    for _ in range(4):
+        assert np.isfinite(float(learner.train_step()))
+        seen = max(seen, int(ring.last_streams[0].max()))
+    assert learner._graphs[0][0] is graph0, "the step must not be re-captured when the ring grows"
+    assert seen > 20000, "the captured launch must sample the rows added after the capture"
+
+
+def test_data_parallel_gradients_equal_the_concatenated_batch(fdql, monkeypatch):
+    """DP over N shards steps on the AVERAGE of the ranks' gradients; that equals one learner on the
+    concatenation of the ranks' injected batches (the loss is a mean over the batch), <= 1e-5 of each gradient's scale.  Two
+    'ranks' are emulated on one GPU: same weights, disjoint batches, the rank-mean formed as NCCL's all-reduce(sum) / world does."""
+    import torch
+    from fastdeepqlearning_b200 import Agent
+    torch.manual_seed(3)
+    conf = make_conf(Agent, batch_size=48, temporal_len=3)
+    learner = Agent.Learner(conf)
+    T, Bh = 3, 48
+    xps = [random_xp(torch, T, Bh) for _ in range(2)]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for xp in xps:  # random_xp is seeded: make the two shards differ
+        for k in ("obs_1d", "achieved_goal", "desired_goal", "reward", "mc_return"):
+            xp[k] = xp[k] + torch.randn(xp[k].shape, device="cuda", generator=g)
+    noise = [[torch.randn(T - 1, Bh, 8, device="cuda", generator=g) for _ in range(2)] for _ in range(2)]  # (actor_target, actor) per shard
+
+    def grads_of(xp, eps):
+        tape = iter(eps)
+        monkeypatch.setattr(torch, "randn_like", lambda t, **kw: next(tape))
+        learner.optimizer.zero_grad(set_to_none=True)
+        learner.get_losses(dict(xp)).backward()
+        monkeypatch.undo()
+        return [p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p) for p in learner.params]
+    per_rank = [grads_of(xps[r], noise[r]) for r in range(2)]
+    mean = [(a + b) / 2 for a, b in zip(*per_rank)]
+    cat = {k: torch.cat([xps[0][k], xps[1][k]], dim=1) for k in xps[0]}
+    whole = grads_of(cat, [torch.cat([noise[0][i], noise[1][i]], dim=1) for i in range(2)])
+    for m, w in zip(mean, whole):
+        scale = float(w.abs().max()) + 1e-12
+        assert float((m - w).abs().max()) <= 1e-5 * scale + 1e-9
 
 
 def test_action_onehot_kernel_golden_and_random(fdql):
