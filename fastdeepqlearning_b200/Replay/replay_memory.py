@@ -12,6 +12,8 @@ arithmetic (quirk Q1: the length saturates at maxlen-1) and the same `Oversample
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 import typing as T
 
 import numpy as np
@@ -20,6 +22,18 @@ import torch
 from .. import _lib as L
 from .._lib import OversampleError, check
 from ..reward_ops import RewardOp
+
+
+def _locked(fn):
+    """One writer thread (Runner._replay_handler) and the learner's reader thread share a ring in the reference without a lock
+    (async_replay_memory.py:55-70: the two sides live in different threads of the child process).  Here both sides touch the host
+    staging block and the arena cursor, so the public entry points serialise on a re-entrant lock; the device work they enqueue is
+    ordered by the stream."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with self._lock:
+            return fn(self, *a, **k)
+    return wrapper
 
 
 def _stream_ptr(device):
@@ -39,6 +53,7 @@ class ReplayMemory:
         self._batch_size, self._temporal_len, self._maxlen = batch_size, temporal_len, int(maxlen)
         self.batch_size = batch_size
         self._top, self._curr_len = 0, 0
+        self._lock = threading.RLock()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.FdqlError("ReplayMemory lives in HBM: device must be a CUDA device (no CPU path)")
@@ -102,6 +117,7 @@ class ReplayMemory:
             self._top = (top + n) % cap
             self._curr_len = max(self._curr_len, mx)
 
+    @_locked
     def add(self, experience_dict: dict):
         if self._h is None:
             widths, shapes = {}, {}
@@ -133,6 +149,7 @@ class ReplayMemory:
                 self._pending_eps.append((self._open_ep_first, self._open_ep_len))
             self._open_ep_len = 0
 
+    @_locked
     def flush(self):
         """Move staged rows to the arena and commit the extents of the episodes that finished."""
         if self._h is None:
@@ -151,6 +168,7 @@ class ReplayMemory:
         lens = torch.tensor([e[1] for e in eps], dtype=torch.int32, device=self.device)
         self.commit_episodes(begins, lens, with_returns=with_returns, gamma=gamma)
 
+    @_locked
     def commit_episodes(self, begins: torch.Tensor, lens: torch.Tensor, with_returns=False, gamma=None):
         """Record episode extents (and optionally return-to-go, nstep_return.py:60-72) for episodes already in the ring."""
         op = self.reward_op or RewardOp(L.REWARD_NONE)
@@ -159,6 +177,7 @@ class ReplayMemory:
                                              C.c_void_p(lens.data_ptr()), float(self.gamma if gamma is None else gamma),
                                              int(bool(with_returns)), op.op, params, n_params, _stream_ptr(self.device)))
 
+    @_locked
     def add_rows(self, cols: T.Dict[str, T.Any], episode_lengths=None, with_returns=False, gamma=None):
         """Batched `add`: cols[k] is [n, w] (numpy or torch, host or device).  When `episode_lengths` is given the rows
         are whole episodes laid end to end and are committed (extents, optional returns) in the same call."""
@@ -181,6 +200,7 @@ class ReplayMemory:
                                  with_returns=with_returns, gamma=gamma)
         return begin
 
+    @_locked
     def add_vmap_rows(self, cols, L, picks):
         """HindsightVmapWrite without an NStepReturnVmap underneath (use_nStep_lowerbounds=False): no virtual_mc_return key."""
         begin = self.add_rows(cols, episode_lengths=[L])
@@ -188,6 +208,7 @@ class ReplayMemory:
         self.vmap_flush([begin], [L], pick_rows=rows, fill=True, returns=False)
         return begin
 
+    @_locked
     def add_hindsight_rows(self, src_begins, lens, goal_rows, with_returns=True, gamma=None):
         """Write-time hindsight copy of whole episodes (her.py:55-95): reserves sum(lens) rows at the cursor and fills
         them on the device.  Returns the first destination row of each copy."""
@@ -221,6 +242,7 @@ class ReplayMemory:
             raise KeyError("the ring has no virtual_goals / virtual_rewards / virtual_dones keys (write with HindsightVmapWrite)")
         return ids
 
+    @_locked
     def vmap_flush(self, begins, lens, pick_rows=None, fill=True, returns=False, gamma=None, done_quirk=False):
         """Fill the virtual columns of whole episodes already in the ring: goals / rewards / dones from `pick_rows`
         ([n_eps, V] ring rows whose achieved_goal become the virtual goals; her_vmap.py:66-88) and / or the per-column
@@ -245,6 +267,7 @@ class ReplayMemory:
                                                  float(self.gamma if gamma is None else gamma), (1 if fill else 0) | (2 if returns else 0),
                                                  int(bool(done_quirk)), _stream_ptr(self.device)))
 
+    @_locked
     def vmap_temporal_sample(self, column, starts=None, aux=False, n=None, length=None):
         """HindsightVmapRead.temporal_sample (her_vmap.py:104-123): the window batch with desired_goal / reward / task_done /
         mc_return taken from virtual column `column` and the virtual keys removed.  Only that column is read from HBM."""
@@ -278,6 +301,7 @@ class ReplayMemory:
             self._jit_initialize({k: int(np.prod(v.shape[1:])) if len(v.shape) > 1 else 1 for k, v in cols.items()},
                                  {k: tuple(v.shape[1:]) or (1,) for k, v in cols.items()})
 
+    @_locked
     def reserve_rows(self, n):
         """Advance the cursor by n rows whose content a device kernel will produce; returns the first reserved row."""
         self.flush()
@@ -286,6 +310,7 @@ class ReplayMemory:
         self._advance(int(n))
         return first.value
 
+    @_locked
     def q3_duplicate(self, src_row, n_step, dst_row, gamma):
         """quirk Q3: the oldest row of an episode longer than n_step, stored once more with the n-step-truncated return."""
         check(self._lib.fdql_q3_duplicate(self._h, int(src_row), int(n_step), int(dst_row), float(gamma), _stream_ptr(self.device)))
@@ -298,6 +323,7 @@ class ReplayMemory:
         check(self._lib.fdql_arena_meta_view(self._h, which, C.byref(base), C.byref(stride), C.byref(col)))
         return torch.as_tensor(_DevView(base.value, (self._maxlen, 4), (4 * stride.value, 4)), device=self.device)
 
+    @_locked
     def state_dict(self):
         self.flush()
         es, ee = self.episode_extents()
@@ -309,6 +335,7 @@ class ReplayMemory:
                 "memory": {k: v.cpu().clone() for k, v in self.memory.items()}, "ep_start": es.cpu().clone(), "ep_end": ee.cpu().clone(),
                 "scan": self._meta_rows(2).view(torch.int32).cpu().clone(), "links": self._meta_rows(3).view(torch.int32).cpu().clone()}
 
+    @_locked
     def load_state_dict(self, sd):
         if self._h is not None:
             raise RuntimeError("load_state_dict needs a fresh ReplayMemory")
@@ -378,6 +405,7 @@ class ReplayMemory:
         return torch.as_tensor(np.asarray(x, dtype=np.int64) if not isinstance(x, torch.Tensor) else x,
                                dtype=torch.int64).to(self.device).contiguous()
 
+    @_locked
     def __getitem__(self, idxes) -> T.Dict[str, torch.Tensor]:
         self.flush()
         idx = self._to_dev_i64(idxes)
@@ -390,6 +418,7 @@ class ReplayMemory:
                                          L.ptr_array([out[k].data_ptr() for k in self._keys]), _stream_ptr(self.device)))
         return {k: v.reshape(shape + (v.shape[-1],)) for k, v in out.items()}
 
+    @_locked
     def draw_streams(self, n=None, temporal_len=None, goal_mode=None, relabel_prob=0.0):
         """Device-side np.random.randint(0, len-T, B) (+ hindsight flag / goal row per window when relabel_prob > 0)."""
         self.flush()
@@ -414,6 +443,7 @@ class ReplayMemory:
             self._rng_counter += 1
         return starts, flags, goals
 
+    @_locked
     def publish_len(self):
         """Store the ring's length next to the device-side draw counter ({counter, ticket, length, 0}): a captured sample / gather
         launch reads its start range from there, so one captured learner step keeps sampling the whole ring while it fills."""
@@ -428,6 +458,7 @@ class ReplayMemory:
         check(self._lib.fdql_arena_info(self._h, None, C.byref(top), C.byref(ln), None))
         assert (top.value, ln.value) == (self._top, self._curr_len), "host and arena cursors diverged"
 
+    @_locked
     def sample(self, idx=None) -> T.Dict[str, torch.Tensor]:
         if len(self) < self._batch_size:
             raise OversampleError("Trying to sample more memories than available!")
@@ -435,6 +466,7 @@ class ReplayMemory:
             idx, _, _ = self.draw_streams(self._batch_size, 0)
         return self[idx]
 
+    @_locked
     def temporal_sample(self, starts=None, flags=None, goal_rows=None, exact_episode_step=False, aux=False,
                         reuse_outputs=False, n=None, relabel_prob=0.0, goal_mode=None, length=None, exclude_keys=()):
         """[T, B, w] window gather (replay_memory.py:54-66).  `starts` (and for hindsight relabelling `flags`,

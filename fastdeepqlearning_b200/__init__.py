@@ -6,11 +6,11 @@ operation needs the built library and a CUDA device and fails loudly otherwise."
 from ._lib import lib, FdqlError, OversampleError, LIB_PATH, EXPORTS  # noqa: F401
 from .reward_ops import RewardOp  # noqa: F401
 
-__all__ = ["lib", "FdqlError", "OversampleError", "RewardOp", "Replay", "Agent"]
+__all__ = ["lib", "FdqlError", "OversampleError", "RewardOp", "Replay", "Agent", "Runner"]
 
 
 def __getattr__(name):  # lazy: the sub-packages import torch
-    if name in ("Replay", "Agent"):
+    if name in ("Replay", "Agent", "Runner"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)
