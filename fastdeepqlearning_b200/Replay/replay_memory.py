@@ -64,9 +64,12 @@ class ReplayMemory:
         self._shapes: T.Dict[str, tuple] = {}
         self._role_override = dict(roles or {})
         self._stage_rows = max(1, min(int(stage_rows), self._maxlen))  # a flush never carries more rows than the ring holds
-        self._stage = None
-        self._stage_np = None
+        self._stage = None       # two pinned host blocks [stage_rows, row_floats]: add() packs rows into one while the other drains
+        self._stage_np = None    # per block: key -> numpy view [stage_rows, width] into the block
+        self._stage_ev = [None, None]
+        self._stage_cur = 0
         self._n_staged = 0
+        self.squash_rewards = False  # Pohlen transform of the reward column inside the append kernel (wrappers.SquashRewards)
         self._pending_eps: T.List[T.Tuple[int, int]] = []  # (first row, length) of finished, uncommitted episodes
         self._open_ep_first, self._open_ep_len = 0, 0
         self.reward_op: T.Optional[RewardOp] = None
@@ -92,9 +95,21 @@ class ReplayMemory:
         check(self._lib.fdql_arena_create(self._maxlen, n, (C.c_int32 * n)(*self._widths), (C.c_int32 * n)(*roles),
                                           self.device.index or 0, C.byref(h)))
         self._h = h
-        self._stage = {k: torch.zeros((self._stage_rows, w), dtype=torch.float32).pin_memory()
-                       for k, w in zip(self._keys, self._widths)}
-        self._stage_np = {k: v.numpy() for k, v in self._stage.items()}
+        # packed staging: every key of a row side by side, offsets and row size multiples of 4 floats (128-bit path of the append kernel)
+        self._key_off, off = [], 0
+        for w in self._widths:
+            self._key_off.append(off)
+            off += (w + 3) // 4 * 4
+        self._row_floats = off
+        self._key_off_c = (C.c_int32 * n)(*self._key_off)
+        self._stage = [torch.zeros((self._stage_rows, self._row_floats), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._stage_np = [{k: blk.numpy()[:, o:o + w] for k, o, w in zip(self._keys, self._key_off, self._widths)} for blk in self._stage]
+        self._scalar_key = {k: (w == 1) for k, w in zip(self._keys, self._widths)}
+
+    def enable_squash_rewards(self, on=True):
+        """wrappers.SquashRewards: Pohlen transform (squash_rewards.py:5-7) of the reward column of every row appended from now on."""
+        self.flush()
+        self.squash_rewards = bool(on)
 
     def set_reward_op(self, op, gamma=None):
         self.reward_op = RewardOp.coerce(op)
@@ -130,8 +145,11 @@ class ReplayMemory:
                     widths[k], shapes[k] = 1, (1,)
             self._jit_initialize(widths, shapes)
         i = self._n_staged
+        views = self._stage_np[self._stage_cur]
         for k, v in experience_dict.items():
-            self._stage_np[k][i] = np.asarray(v, dtype=np.float32).reshape(-1)
+            if getattr(v, "ndim", 0) > 1:
+                v = v.reshape(-1)
+            views[k][i] = v  # numpy casts to fp32 on assignment
         self._track_episode(bool(experience_dict.get("episode_done", False)) if "episode_done" in experience_dict else None)
         self._n_staged += 1
         self._advance(1)
@@ -155,9 +173,18 @@ class ReplayMemory:
         if self._h is None:
             return
         if self._n_staged:
-            ptrs = L.ptr_array([self._stage[k].data_ptr() for k in self._keys])
-            check(self._lib.fdql_arena_append_host(self._h, self._n_staged, ptrs, _stream_ptr(self.device)))
-            torch.cuda.current_stream(self.device).synchronize()  # staging is reused by the next add
+            cur = self._stage_cur
+            stream = torch.cuda.current_stream(self.device)
+            check(self._lib.fdql_arena_append_packed_host(self._h, self._n_staged, C.c_void_p(self._stage[cur].data_ptr()), self._row_floats,
+                                                          self._key_off_c, L.APPEND_SQUASH_REWARDS if self.squash_rewards else 0,
+                                                          C.c_void_p(stream.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._stage_ev[cur] = ev
+            # the other block takes the next rows; its own copy was enqueued a whole flush ago (no stream sync in steady state)
+            self._stage_cur = cur ^ 1
+            if self._stage_ev[cur ^ 1] is not None:
+                self._stage_ev[cur ^ 1].synchronize()
             self._n_staged = 0
         if self._pending_eps:
             eps, self._pending_eps = self._pending_eps, []
@@ -189,6 +216,9 @@ class ReplayMemory:
         for k, w in zip(self._keys, self._widths):
             t = torch.as_tensor(cols[k])
             t = t.to(device=self.device, dtype=torch.float32, non_blocking=True).reshape(n, w).contiguous()
+            if self.squash_rewards and k == "reward":  # squash_rewards.py:5-7 in fp64 like numpy on the Python float, fp32 store
+                x = t.double()
+                t = (torch.sign(x) * (torch.sqrt(x.abs() + 1) - 1) + 1e-2 * x).float()
             dev.append(t)
         begin = self._top
         check(self._lib.fdql_arena_append(self._h, n, L.ptr_array([t.data_ptr() for t in dev]), _stream_ptr(self.device)))

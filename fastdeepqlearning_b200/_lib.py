@@ -22,6 +22,7 @@ ROLE_BY_NAME = {"reward": ROLE_REWARD, "task_done": ROLE_TASK_DONE, "episode_don
 REWARD_NONE, REWARD_BITFLIP, REWARD_ALL_GEQ, REWARD_FIRST_GEQ, REWARD_WEIGHTED_PNORM = range(5)
 GOAL_FINAL, GOAL_RANDOM, GOAL_FUTURE = range(3)
 OPT_EXACT_EPISODE_STEP, OPT_EMIT_LEARNER_AUX, OPT_CORESIDENT = 1, 2, 4
+APPEND_SQUASH_REWARDS = 1
 
 
 class FdqlError(RuntimeError):
@@ -51,6 +52,7 @@ _SIGNATURES = {
     "fdql_arena_link_state": (C.c_int, [_p, _i32, C.POINTER(_f64), C.POINTER(_i32)]),
     "fdql_arena_append": (C.c_int, [_p, _i64, _pp, _p]),
     "fdql_arena_append_host": (C.c_int, [_p, _i64, _pp, _p]),
+    "fdql_arena_append_packed_host": (C.c_int, [_p, _i64, _p, _i32, C.POINTER(_i32), _u32, _p]),
     "fdql_commit_episodes": (C.c_int, [_p, _i32, _p, _p, _f64, _i32, _i32, C.POINTER(_f32), _i32, _p]),
     "fdql_her_flush_episodes": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _i32, _p]),
     "fdql_action_onehot": (C.c_int, [_i64, _i32, _p, _p, _p, _p]),

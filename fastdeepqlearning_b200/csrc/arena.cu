@@ -41,19 +41,24 @@ int upload_reward_spec(const Arena* a, int32_t op, const float* params_host, int
 // -------------------------------------------------------------------------------------------------
 // append: dense [n, width] sources -> ring rows top.. (mod capacity)
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) append_kernel(ArenaDev A, SrcPtrs src, int64_t n_rows, int64_t top) {
+// src_stride: floats between consecutive source rows of every key (0: each key is a dense [n_rows, width] array).  A packed host
+// block [n_rows, src_stride] holds all keys of a row side by side, src.p[k] pointing at key k's offset inside row 0.
+// squash: the Pohlen transform of franQ/Replay/wrappers/squash_rewards.py:5-7, sign(r) (sqrt(|r| + 1) - 1) + 0.01 r, applied to the
+// reward column on its way into the ring (evaluated in fp64 like numpy does on the Python float, stored as fp32).
+__global__ void __launch_bounds__(256) append_kernel(ArenaDev A, SrcPtrs src, int64_t n_rows, int64_t top, int32_t src_stride, int32_t squash) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int s = 0; s < A.n_wide; ++s) {
     const WideSlab W = A.wide[s];
     const float* __restrict__ sp = src.p[W.key];
     const int64_t items = n_rows * W.vecs;
-    const bool vec_ok = (W.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0);
+    const int64_t rstride = src_stride > 0 ? src_stride : W.width;
+    const bool vec_ok = (W.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0) && (rstride % 4 == 0);
     for (int64_t i = tid; i < items; i += nthreads) {
       const int64_t r = i / W.vecs;
       const int v = (int)(i - r * W.vecs);
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* q = sp + r * W.width + 4 * v;
+      const float* q = sp + r * rstride + 4 * v;
       if (vec_ok) {
         x = ld_stream4(q);
       } else {
@@ -74,7 +79,13 @@ __global__ void __launch_bounds__(256) append_kernel(ArenaDev A, SrcPtrs src, in
       for (int c = 0; c < 4; ++c) {
         const int col = c0 + c;
         float val = 0.f;
-        if (col < A.n_scal) val = src.p[A.scal_key[col]][r];
+        if (col < A.n_scal) {
+          val = src.p[A.scal_key[col]][src_stride > 0 ? r * (int64_t)src_stride : r];
+          if (squash && col == A.col_reward) {
+            const double x = (double)val;
+            val = (float)(copysign(sqrt(fabs(x) + 1.0) - 1.0, x) * (x != 0.0 ? 1.0 : 0.0) + 1e-2 * x);
+          }
+        }
         else if (col == A.col_ep_start || col == A.col_ep_end) val = __int_as_float(-1);
         t[c] = val;
       }
@@ -562,10 +573,40 @@ int fdql_arena_append(fdql_arena* a, int64_t n_rows, const float* const* src, vo
   if (blocks > cap_blocks) blocks = cap_blocks;
   note_overwrite(a, n_rows);
   { int rc = flush_pending_invalidation(a, (cudaStream_t)stream); if (rc) return rc; }
-  append_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a->dev, sp, n_rows, a->top);
+  append_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a->dev, sp, n_rows, a->top, a->append_src_stride, a->append_squash);
   FDQL_CUDA(cudaGetLastError());
   advance_cursor(a, n_rows);
   return FDQL_OK;
+}
+
+int fdql_arena_append_packed_host(fdql_arena* a, int64_t n_rows, const float* packed_host, int32_t row_floats,
+                                  const int32_t* key_offsets_host, uint32_t flags, void* stream) {
+  FDQL_REQUIRE(a != nullptr && packed_host != nullptr && key_offsets_host != nullptr, "null argument");
+  FDQL_REQUIRE(n_rows >= 0 && n_rows <= a->dev.capacity, "n_rows must be in [0, capacity]");
+  FDQL_REQUIRE(row_floats >= 1, "bad row size");
+  if (n_rows == 0) return FDQL_OK;
+  for (int k = 0; k < a->n_keys; ++k)
+    FDQL_REQUIRE(key_offsets_host[k] >= 0 && key_offsets_host[k] + a->widths[k] <= row_floats, "key %d does not fit the packed row", k);
+  if (flags & FDQL_APPEND_SQUASH_REWARDS) FDQL_REQUIRE(a->dev.col_reward >= 0, "squashed rewards need a reward key");
+  const size_t need = (size_t)n_rows * row_floats * sizeof(float);
+  if (need > a->stage_bytes) {
+    FDQL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (a->stage_dev) cudaFree(a->stage_dev);
+    a->stage_dev = nullptr;
+    a->stage_bytes = 0;
+    FDQL_CUDA(cudaMalloc(&a->stage_dev, need));
+    a->stage_bytes = need;
+  }
+  // ONE host-to-device copy for the whole block; the append kernel then reads the keys with the packed row stride
+  FDQL_CUDA(cudaMemcpyAsync(a->stage_dev, packed_host, need, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  const float* dev_ptrs[FDQL_MAX_KEYS];
+  for (int k = 0; k < a->n_keys; ++k) dev_ptrs[k] = static_cast<const float*>(a->stage_dev) + key_offsets_host[k];
+  a->append_src_stride = row_floats;
+  a->append_squash = (flags & FDQL_APPEND_SQUASH_REWARDS) ? 1 : 0;
+  const int rc = fdql_arena_append(a, n_rows, dev_ptrs, stream);
+  a->append_src_stride = 0;
+  a->append_squash = 0;
+  return rc;
 }
 
 int fdql_arena_append_host(fdql_arena* a, int64_t n_rows, const float* const* src_host, void* stream) {

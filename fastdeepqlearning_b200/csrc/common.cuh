@@ -169,6 +169,7 @@ struct Arena {
   double link_gamma;    // discount the link records were built with
   int link_state;       // 0: none yet, 1: link_gamma valid, 2: episodes were committed with different discounts (links unusable)
   int num_sms;
+  int32_t append_src_stride, append_squash;  // set around fdql_arena_append by the packed host form (see arena.cu)
   int64_t rows_written;        // rows [0, rows_written) of the ring have held data (capacity once it has wrapped)
   int64_t pending_inval_row;   // first row behind the write head whose episode may have lost its beginning (-1: none); see arena.cu
 };

@@ -98,6 +98,16 @@ int fdql_arena_link_state(fdql_arena* a, int32_t set, double* gamma, int32_t* st
 int fdql_arena_append(fdql_arena* a, int64_t n_rows, const float* const* src, void* stream);
 int fdql_arena_append_host(fdql_arena* a, int64_t n_rows, const float* const* src_host, void* stream);
 
+/* The same from ONE packed host block [n_rows, row_floats] (pinned for the copy to be asynchronous): key k of row r lives at
+ * packed_host[r * row_floats + key_offsets_host[k] ..].  One host-to-device copy per call instead of one per key; this is what the
+ * Python mirror's add() stages rows into (Runner._replay_handler -> replay.add, franQ/Runner/runner.py:177-191).  Offsets and
+ * row_floats that are multiples of 4 keep the 128-bit path.  flags: FDQL_APPEND_SQUASH_REWARDS applies the Pohlen transform of
+ * franQ/Replay/wrappers/squash_rewards.py:5-7 to the reward column inside the append kernel (SquashRewards.add, :15-18).
+ * The block may be reused by the host once the work enqueued on `stream` so far has completed (record an event after the call). */
+#define FDQL_APPEND_SQUASH_REWARDS 1u
+int fdql_arena_append_packed_host(fdql_arena* a, int64_t n_rows, const float* packed_host, int32_t row_floats,
+                                  const int32_t* key_offsets_host, uint32_t flags, void* stream);
+
 /* NStepReturn._flush + calculate_montecarlo_return (franQ/Replay/wrappers/nstep_return.py:36-48,60-72) for n_eps
  * complete episodes already in the ring: episode e occupies rows ep_begin[e] .. ep_begin[e]+ep_len[e]-1 (mod capacity).
  * Writes mc_return (if with_returns), the episode extents, and (if reward_op != NONE and the goal roles are bound)

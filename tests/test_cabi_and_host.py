@@ -100,6 +100,10 @@ def test_pohlen_transform_matches_golden():
     g = load_golden("get_losses")
     got = np.array([_pohlen_transform(x) for x in g["pohlen_in"]])
     np.testing.assert_allclose(got, g["pohlen_out"], rtol=1e-12, atol=1e-15)
+    # arrays like the reference's numpy form (squash_rewards.py:5-7), Python ints and zeros
+    np.testing.assert_allclose(_pohlen_transform(g["pohlen_in"]), g["pohlen_out"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(_pohlen_transform(g["pohlen_in"].reshape(8, 8)), g["pohlen_out"].reshape(8, 8), rtol=1e-12, atol=1e-15)
+    assert _pohlen_transform(0) == 0 and _pohlen_transform(0.0) == 0.0 and _pohlen_transform(3) == 1.0 + 0.03
 
 
 def test_hindsight_goal_pick_indexing():

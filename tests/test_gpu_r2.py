@@ -526,3 +526,35 @@ def test_coresident_option_selects_the_lean_kernel_and_matches(fdql):
         assert torch.equal(o0[k], o1[k]), k
     for x, y in zip(a0, a1):
         assert torch.equal(x, y)
+
+
+# ------------------------------------------------------------------------------------------------ SquashRewards on the device
+@pytest.mark.parametrize("with_nstep", [True, False])
+def test_squash_rewards_in_the_append_kernel(fdql, with_nstep):
+    """Replay.make with use_squashed_rewards (Replay/__init__.py:28-29: SquashRewards over NStepReturn, no HER): the stored reward is
+    the Pohlen transform of the env reward (golden pohlen_in/out from the reference function) and mc_return is the reference
+    recurrence over the SQUASHED rewards."""
+    from fastdeepqlearning_b200 import Replay
+    g = load_golden("get_losses")
+    x, want = g["pohlen_in"], g["pohlen_out"]
+    x32 = x.astype(np.float32).astype(np.float64)  # rewards must be fp32-representable (replay_memory.py:31-32)
+    want32 = O.pohlen_transform(x32)
+    np.testing.assert_allclose(O.pohlen_transform(x), want, rtol=1e-12)
+    conf = types.SimpleNamespace(replay_size=512, batch_size=8, temporal_len=2, num_instances=1, use_nStep_lowerbounds=with_nstep,
+                                 nStep_return_steps=1000, gamma=0.9, use_squashed_rewards=True, use_HER=False, training_device="cuda:0")
+    read, write = Replay.make(conf)
+    assert type(write[0]).__name__ == "SquashRewards"
+    lengths = [7, 1, 20, 36]
+    i = 0
+    for L in lengths:
+        for t in range(L):
+            write[0].add({"obs_1d": np.full(3, i, np.float32), "reward": float(x32[i]), "episode_done": t == L - 1, "episode_step": t})
+            i += 1
+    n = sum(lengths)
+    mem = {k: npy(v)[:n] for k, v in read[0].memory.items()}
+    np.testing.assert_array_equal(mem["reward"].reshape(-1), want32[:n].astype(np.float32))
+    np.testing.assert_array_equal(mem["obs_1d"][:, 0], np.arange(n, dtype=np.float32))
+    if with_nstep:
+        done = np.zeros(n, bool)
+        done[np.cumsum(lengths) - 1] = True
+        np.testing.assert_array_equal(mem["mc_return"].reshape(-1), O.segmented_returns(want32[:n].astype(np.float32), done, 0.9))
