@@ -78,6 +78,7 @@ def parse():
     ap.add_argument("--serial", action="store_true", help="gather and loss back to back on one stream instead of pipelined on two")
     ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE.json configs[0..2] sections (Pendulum / CartPole / 64-bit HER shapes)")
     ap.add_argument("--no-graph", action="store_true", help="learner step launched eagerly instead of as one CUDA graph")
     ap.add_argument("--separate-streams", action="store_true", help="draw the index / goal streams in their own launch (fdql_sample_streams)")
     ap.add_argument("--tail-scan", action="store_true", help="relabelled returns by scanning the episode tail instead of the link records")
@@ -470,7 +471,17 @@ def run_ours(args):
             tm = torch.tensor([ms2], device=device)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             ms2 = float(tm.item())
-        secondary = {"temporal_len": T2, "windows_per_step": n2, "transitions_per_step_per_gpu": M2, "ms_per_step": ms2,
+        peak2, _ = peaks()
+        # bytes per TD pair at T = 50: every window row is read and written once (436 B each way) per 49/50 pairs, relabelled windows
+        # scan their episode tail's 16-byte records once per WINDOW; the loss moves 1520 B per pair
+        gb2 = (2 * ROW_BYTES * T2 + 8 + P_RELABEL * (4 * GOAL + 25 + 16 * (LEP + 1) / 2)) / (T2 - 1)
+        roof2 = {"bound": "hbm", "peak": peak2, "unit": "GB/s",
+                 "gather": {"bytes_per_transition": gb2, "achieved": gb2 * M2 / (acc2[0] / reps2 * 1e-3) / 1e9,
+                            "frac": gb2 * M2 / (acc2[0] / reps2 * 1e-3) / 1e9 / peak2},
+                 "tqc": {"bytes_per_transition": BYTES_TQC, "achieved": BYTES_TQC * M2 / (acc2[1] / reps2 * 1e-3) / 1e9,
+                         "frac": BYTES_TQC * M2 / (acc2[1] / reps2 * 1e-3) / 1e9 / peak2},
+                 "whole_step": {"bytes_per_transition": gb2 + BYTES_TQC, "frac": (gb2 + BYTES_TQC) * M2 / (ms2 * 1e-3) / 1e9 / peak2}}
+        secondary = {"temporal_len": T2, "windows_per_step": n2, "transitions_per_step_per_gpu": M2, "ms_per_step": ms2, "roofline": roof2,
                      "transitions_per_s": world * M2 / (ms2 * 1e-3), "rows_gathered_per_s": world * T2 * n2 / (acc2[0] / reps2 * 1e-3),
                      "gather_ms": float(acc2[0] / reps2), "tqc_ms": float(acc2[1] / reps2), "loss_mean": float(loss2.mean()),
                      "note": "reference default temporal_len (conf.py:38): one window gives 49 TD pairs, so the gather is amortised and "
@@ -641,6 +652,8 @@ def run_ours(args):
                        "violations": float(stats[2] / max(float(stats[3]), 1) / CQ), "parity_vs_oracle": parity}}
     if secondary:
         line["secondary_T50"] = secondary
+    if not args.no_extra and rank == 0:
+        line["extra"] = extra_configs(torch, pkg, Replay, L, lib, device)
     if e2e:
         line["e2e"] = e2e
     if updates:
@@ -663,6 +676,93 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
         os._exit(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+EXTRA_SPECS = {
+    # BASELINE.json configs[0]: SAC on Pendulum with uniform replay + n-step lower bound (obs 3, act 1, no goals; the non-distributional
+    # head: 5 critics x 1 value, min over the ensemble, smooth-L1, lower bound replaces the TD term -- soft_actor_critic.py:63-99)
+    "config0_pendulum_sac": dict(obs=3, act=1, goal=0, discrete_n=0, critics=5, atoms=1, n_drop=0, her=False, loss="sac"),
+    # configs[1]: discrete Gumbel-softmax SAC on CartPole with n-step replay, batch 4096 (obs 4, 2 actions stored as an index and
+    # one-hot encoded by get_losses, deepQlearning.py:206-210; reference default head 5 x 10 atoms, drop int(0.2 * 50) = 10)
+    "config1_cartpole_discrete": dict(obs=4, act=1, goal=0, discrete_n=2, critics=5, atoms=10, n_drop=10, her=False, loss="tqc"),
+    # configs[2]: HER on the 64-bit bit-flipping env (bitflip.py: obs 64, achieved / desired goal 64, 64 discrete actions), future k=4
+    "config2_her_bitflip64": dict(obs=64, act=1, goal=64, discrete_n=64, critics=5, atoms=25, n_drop=10, her=True, loss="tqc"),
+}
+
+
+def extra_configs(torch, pkg, Replay, L, lib, device, rows=2_000_000, D=16, reps=10):
+    """One serial pass (gather [+ relabel] [+ one-hot] + loss) at the other BASELINE.json shapes: D batches of 4096 windows, T = 2, on a
+    ring of `rows` rows; per-kernel CUDA-event times, algorithmic bytes (SURVEY.md section 8d applied to the shape) and roofline
+    fractions.  Parity on the same shapes: tests/test_gpu_r2.py::test_baseline_config_shapes_vs_oracle."""
+    from fastdeepqlearning_b200 import ops
+    peak, _ = peaks()
+    out = {}
+    n = D * B
+    for name, sp in EXTRA_SPECS.items():
+        gen = torch.Generator(device=device).manual_seed(5)
+        n_eps = rows // LEP
+        N = n_eps * LEP
+        ring = Replay.ReplayMemory(N + 1, B, T, device=device, seed=11)
+        step = torch.arange(N, device=device).remainder(LEP).float().unsqueeze(-1)
+        cols = {"obs_1d": torch.randn(N, sp["obs"], device=device, generator=gen)}
+        if sp["discrete_n"]:
+            cols["action"] = torch.randint(0, sp["discrete_n"], (N, 1), device=device, generator=gen).float()
+        else:
+            cols["action"] = torch.rand(N, sp["act"], device=device, generator=gen) * 2 - 1
+        if sp["goal"]:
+            ag = (torch.rand(N, sp["goal"], device=device, generator=gen) < 0.5).float()
+            dg = (torch.rand(n_eps, sp["goal"], device=device, generator=gen) < 0.5).float().repeat_interleave(LEP, 0)
+            hit = (ag == dg).all(-1, keepdim=True).float()
+            cols.update(achieved_goal=ag, desired_goal=dg, reward=hit - 1, task_done=hit)
+            ring.set_reward_op(pkg.RewardOp.bitflip(), GAMMA)
+        else:
+            cols.update(reward=-torch.rand(N, 1, device=device, generator=gen), task_done=(step == LEP - 1).float())
+        cols.update(episode_done=(step == LEP - 1).float(), episode_step=step, mc_return=torch.zeros(N, 1, device=device))
+        ring.add_rows(cols, episode_lengths=torch.full((n_eps,), LEP), with_returns=True)
+        del cols
+        CQx = sp["critics"] * sp["atoms"]
+        z = torch.randn(T - 1, n, CQx, device=device, generator=gen) * 3
+        q = torch.randn(T - 1, n, CQx, device=device, generator=gen) * 3
+        lp = torch.randn(T - 1, n, 1, device=device, generator=gen)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = np.zeros(3)
+        for i in range(3 + reps):
+            ev[0].record()
+            xp = ring.temporal_sample(n=n, relabel_prob=P_RELABEL if sp["her"] else 0.0, aux=True, exact_episode_step=True, reuse_outputs=True)
+            ev[1].record()
+            if sp["discrete_n"]:
+                onehot = ops.action_onehot(xp["action"], sp["discrete_n"])
+            ev[2].record()
+            if sp["loss"] == "sac":
+                r = ops.sac_min_target_loss(q, z, lp, xp["reward"][1:], xp["mask"][1:], xp["mc_return"][1:], ALPHA, GAMMA,
+                                            grad_scale=xp["loss_weight"], want_stats=True)
+            else:
+                r = ops.tqc_loss(q, z, lp, xp["reward"][1:], xp["mask"][1:], xp["mc_return"][1:], ALPHA, GAMMA, sp["n_drop"],
+                                 grad_scale=xp["loss_weight"], want_stats=True)
+            ev[3].record()
+            torch.cuda.synchronize(device)
+            if i >= 3:
+                acc += [ev[j].elapsed_time(ev[j + 1]) for j in range(3)]
+        ms = acc / reps
+        row_b = 4 * (sp["obs"] + sp["act"] + 2 * sp["goal"]) + 4 * 5
+        b_gather = 4 * row_b + 8 + (P_RELABEL * (4 * sp["goal"] + 25 + 16 * T) + 17 if sp["her"] else 8)
+        b_onehot = (4 + 4 * sp["discrete_n"]) * T if sp["discrete_n"] else 0
+        b_loss = 3 * 4 * CQx + 20
+        tot = float(ms.sum())
+        gf = lambda b_, m_: b_ * n / (m_ * 1e-3) / 1e9 if m_ > 0 else 0.0
+        out[name] = {"shape": sp, "ring_rows": N, "windows_per_pass": n, "ms": {"gather": float(ms[0]), "onehot": float(ms[1]), "loss": float(ms[2])},
+                     "transitions_per_s": n / (tot * 1e-3), "loss_mean": float(r["loss"].mean()),
+                     "bytes_per_transition": {"gather": b_gather, "onehot": b_onehot, "loss": b_loss},
+                     "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s",
+                                  "gather": {"achieved": gf(b_gather, ms[0]), "frac": gf(b_gather, ms[0]) / peak},
+                                  "loss": {"achieved": gf(b_loss, ms[2]), "frac": gf(b_loss, ms[2]) / peak},
+                                  "whole_pass": {"achieved": gf(b_gather + b_onehot + b_loss, tot), "frac": gf(b_gather + b_onehot + b_loss, tot) / peak}},
+                     "kernels": ("sample_gather_tile_kernel (fused draw)" + (" + onehot_kernel" if sp["discrete_n"] else "") +
+                                 (" + sac_min_target_kernel" if sp["loss"] == "sac" else " + tqc_loss_group_kernel"))}
+        del ring, z, q, lp, xp, r
+        torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -992,6 +992,79 @@ __global__ void __launch_bounds__(256) sac_min_target_kernel(const __grid_consta
   }
 }
 
+// the same for narrow heads (n_atoms <= 16, e.g. 5 critics x 1 value): one THREAD per transition -- a warp per transition would
+// leave most lanes idle and the launch latency-bound; neighbouring threads read neighbouring rows, so the loads still coalesce
+__global__ void __launch_bounds__(256) sac_min_target_thread_kernel(const __grid_constant__ SacArgs a) {
+  __shared__ double sm_stats[3];
+  const int n = a.n_atoms;
+  const float inv_n = 1.f / (float)n;
+  if (a.stats && threadIdx.x < 3) sm_stats[threadIdx.x] = 0.0;
+  if (a.stats) __syncthreads();
+  const float alpha = a.alpha_dev ? __ldg(a.alpha_dev) : a.alpha;
+  double st_sum = 0.0, st_var = 0.0, st_viol = 0.0;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += (int64_t)gridDim.x * blockDim.x) {
+    const float* __restrict__ zrow = a.target_z + m * n;
+    const float* __restrict__ qrow = a.q_pred + m * n;
+    const float ent = a.next_log_pi ? __fmul_rn(alpha, -__ldg(a.next_log_pi + m)) : 0.f;
+    float zmin = CUDART_INF_F;
+    for (int j = 0; j < n; ++j) {
+      float z = ld_stream1(zrow + j);
+      if (a.next_log_pi) z = __fadd_rn(z, ent);
+      zmin = fminf(zmin, z);
+    }
+    const float td = __fadd_rn(__ldg(a.reward + m), __fmul_rn(__fmul_rn(__ldg(a.mask + m), a.gamma), zmin));
+    const float G = a.mc_return ? __ldg(a.mc_return + m) : 0.f;
+    const float gs = a.grad_scale ? __ldg(a.grad_scale + m) : 1.f;
+    float acc = 0.f, qsum = 0.f;
+    int viol = 0;
+    for (int j = 0; j < n; ++j) {
+      const float q = ld_stream1(qrow + j);
+      const float d = q - td, ad = fabsf(d);
+      float l = ad < 1.f ? 0.5f * d * d : ad - 0.5f;  // F.smooth_l1_loss, beta = 1
+      float gq = fminf(fmaxf(d, -1.f), 1.f);
+      if (a.mc_return) {  // soft_actor_critic.py:93-97: q_loss = q_loss * (lb == 0) + lb
+        const float lb = fmaxf(G - q, 0.f);
+        if (lb != 0.f) {
+          l = lb;
+          gq = -1.f;
+          ++viol;
+        }
+      }
+      acc += l;
+      qsum += q;
+      if (a.grad_q) st_stream1(a.grad_q + m * n + j, gq * inv_n * gs);
+    }
+    if (a.loss) a.loss[m] = acc * inv_n;
+    if (a.stats) {
+      const float mean = qsum * inv_n;
+      float dv = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float d = __ldg(qrow + j) - mean;
+        dv = fmaf(d, d, dv);
+      }
+      st_sum += (double)mean * n;
+      st_var += n > 1 ? (double)dv / (double)(n - 1) : 0.0;
+      st_viol += (double)viol;
+    }
+  }
+  if (a.stats) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      st_sum += shfl_xor_f64(st_sum, d);
+      st_var += shfl_xor_f64(st_var, d);
+      st_viol += shfl_xor_f64(st_viol, d);
+    }
+    if (lane_id() == 0) {
+      atomicAdd(&sm_stats[0], st_sum);
+      atomicAdd(&sm_stats[1], st_var);
+      atomicAdd(&sm_stats[2], st_viol);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(a.stats + threadIdx.x, sm_stats[threadIdx.x]);
+    if (threadIdx.x == 3 && blockIdx.x == 0) atomicAdd(a.stats + 3, (double)a.M);
+  }
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -1148,6 +1221,14 @@ int fdql_quantile_huber(int64_t M, int32_t n_quantiles, int32_t n_samples, const
 }
 
 static int launch_sac(const SacArgs& a, cudaStream_t st) {
+  if (a.n_atoms <= 16 && !g_tqc_warp_kernel) {
+    int64_t tb = (a.M + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (tb > cap) tb = cap;
+    sac_min_target_thread_kernel<<<(unsigned)tb, 256, 0, st>>>(a);
+    FDQL_CUDA(cudaGetLastError());
+    return FDQL_OK;
+  }
   int64_t blocks = (a.M + 7) / 8;
   const int64_t max_blocks = (int64_t)num_sms() * 8;
   if (blocks > max_blocks) blocks = max_blocks;

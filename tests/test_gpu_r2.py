@@ -558,3 +558,100 @@ def test_squash_rewards_in_the_append_kernel(fdql, with_nstep):
         done = np.zeros(n, bool)
         done[np.cumsum(lengths) - 1] = True
         np.testing.assert_array_equal(mem["mc_return"].reshape(-1), O.segmented_returns(want32[:n].astype(np.float32), done, 0.9))
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs[0..2] shapes
+@pytest.mark.parametrize("name", ["config0_pendulum_sac", "config1_cartpole_discrete", "config2_her_bitflip64"])
+def test_baseline_config_shapes_vs_oracle(fdql, name):
+    """The shapes bench.py times in its `extra` sections (Pendulum: obs 3 / act 1 / SAC min-target head; CartPole: obs 4, discrete
+    n = 2, 5 x 10 atoms; 64-bit HER: obs 64, goals 64 + 64, discrete n = 64, 5 x 25 atoms), at test size, against the oracle:
+    gathered and relabelled batch, one-hot, loss and gradient."""
+    import torch
+    import bench
+    from fastdeepqlearning_b200 import Replay, ops
+    sp = bench.EXTRA_SPECS[name]
+    rng = np.random.default_rng(len(name))
+    T, B, Lep, n_eps, gamma = 2, 600, 40, 30, 0.99
+    N = Lep * n_eps
+    step = (np.arange(N) % Lep).astype(np.float32).reshape(-1, 1)
+    ends = np.arange(n_eps) * Lep + Lep - 1
+    ep_of = np.arange(N) // Lep
+    cols = {"obs_1d": rng.standard_normal((N, sp["obs"])).astype(np.float32)}
+    cols["action"] = (rng.integers(0, sp["discrete_n"], (N, 1)).astype(np.float32) if sp["discrete_n"]
+                      else rng.uniform(-1, 1, (N, sp["act"])).astype(np.float32))
+    if sp["goal"]:
+        ag = rng.integers(0, 2, (N, sp["goal"])).astype(np.float32)
+        dg = rng.integers(0, 2, (n_eps, sp["goal"])).astype(np.float32)[ep_of]
+        ag[rng.random(N) < 0.2] = dg[0]  # revisited goals
+        hit = (ag == dg).all(-1, keepdims=True).astype(np.float32)
+        cols.update(achieved_goal=ag, desired_goal=dg, reward=hit - 1, task_done=hit)
+    else:
+        cols.update(reward=-rng.random((N, 1)).astype(np.float32), task_done=(step == Lep - 1).astype(np.float32))
+    cols.update(episode_done=(step == Lep - 1).astype(np.float32), episode_step=step)
+    cols["mc_return"] = O.segmented_returns(cols["reward"], cols["episode_done"], gamma).reshape(-1, 1)
+    ring = Replay.ReplayMemory(N + 1, B, T)
+    if sp["goal"]:
+        ring.set_reward_op(fdql.RewardOp.bitflip(), gamma)
+    ring.add_rows(cols, episode_lengths=[Lep] * n_eps, with_returns=True)
+    np.testing.assert_array_equal(npy(ring.memory["mc_return"])[:N], cols["mc_return"])
+    starts = rng.integers(0, N - T, B)
+    if sp["her"]:
+        flags = rng.random(B) < 0.8
+        goal_rows = np.array([rng.integers(s, ends[ep_of[s]] + 1) for s in starts])
+        want = O.sample_time_relabel(cols, starts, T, flags, goal_rows, ep_of * Lep, ends[ep_of], O.reward_bitflip, gamma)
+        xp = ring.temporal_sample(starts=starts, flags=flags.astype(np.uint8), goal_rows=goal_rows, exact_episode_step=True, aux=True, length=N)
+    else:
+        idx = np.arange(T)[:, None] + starts[None]
+        want = {k: v[idx] for k, v in cols.items()}
+        xp = ring.temporal_sample(starts=starts, aux=True, length=N)
+    for k in cols:
+        if k in ("reward", "mc_return"):
+            np.testing.assert_allclose(npy(xp[k]), want[k], rtol=1e-5, atol=1e-6, err_msg=k)
+        else:
+            np.testing.assert_array_equal(npy(xp[k]), want[k], err_msg=k)
+    mask, contig = O.learner_preprocess(want["task_done"], want["episode_step"])
+    np.testing.assert_array_equal(npy(xp["mask"]), mask.astype(np.float32))
+    np.testing.assert_array_equal(npy(xp["is_contiguous"]), contig.astype(np.float32))
+    if sp["discrete_n"]:
+        np.testing.assert_array_equal(npy(ops.action_onehot(xp["action"], sp["discrete_n"])), O.action_onehot(want["action"], sp["discrete_n"]))
+    CQ = sp["critics"] * sp["atoms"]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    z, q = torch.randn(T - 1, B, CQ, device="cuda", generator=g) * 3, torch.randn(T - 1, B, CQ, device="cuda", generator=g) * 3
+    lp = torch.randn(T - 1, B, 1, device="cuda", generator=g)
+    f64 = lambda t: npy(t).astype(np.float64)
+    if sp["loss"] == "sac":
+        got = ops.sac_min_target_loss(q, z, lp, xp["reward"][1:], xp["mask"][1:], xp["mc_return"][1:], 0.7, gamma)
+        wl, wg, _ = O.sac_min_target_loss(f64(q), f64(z), f64(lp), want["reward"][1:], mask[1:], want["mc_return"][1:], 0.7, gamma)
+    else:
+        got = ops.tqc_loss(q, z, lp, xp["reward"][1:], xp["mask"][1:], xp["mc_return"][1:], 0.7, gamma, sp["n_drop"])
+        wl, wg, _ = O.tqc_q_loss(f64(q), f64(z), f64(lp), want["reward"][1:].astype(np.float64), mask[1:].astype(np.float64),
+                                 want["mc_return"][1:].astype(np.float64), 0.7, gamma, sp["n_drop"])
+    np.testing.assert_allclose(npy(got["loss"]), wl, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(got["grad"]), wg, rtol=1e-4, atol=1e-5 * np.abs(wg).max())
+
+
+@pytest.mark.parametrize("n_atoms", [1, 5, 12, 16])
+def test_sac_thread_kernel_equals_warp_kernel(fdql, n_atoms):
+    """Narrow heads (<= 16 atoms) take one thread per transition; same results as the warp-per-transition kernel and the oracle."""
+    import torch
+    from fastdeepqlearning_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n_atoms)
+    M = 3001
+    z, q = torch.randn(M, n_atoms, device="cuda", generator=g) * 2, torch.randn(M, n_atoms, device="cuda", generator=g) * 2
+    lp, rew, mc = (torch.randn(M, 1, device="cuda", generator=g) for _ in range(3))
+    mask = (torch.rand(M, 1, device="cuda", generator=g) > 0.2).float()
+    w = torch.rand(M, 1, device="cuda", generator=g)
+    a = ops.sac_min_target_loss(q, z, lp, rew, mask, mc, 0.6, 0.97, grad_scale=w, want_stats=True)
+    lib = fdql.lib()
+    old = lib.fdql_debug_tqc_warp_kernel(1)
+    try:
+        b = ops.sac_min_target_loss(q, z, lp, rew, mask, mc, 0.6, 0.97, grad_scale=w, want_stats=True)
+    finally:
+        lib.fdql_debug_tqc_warp_kernel(old)
+    torch.testing.assert_close(a["loss"], b["loss"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(a["grad"], b["grad"])
+    torch.testing.assert_close(a["stats"], b["stats"], rtol=1e-6, atol=1e-6)  # per-row sums in fp32, different orders
+    f64 = lambda t: npy(t).astype(np.float64)
+    wl, wg, _ = O.sac_min_target_loss(f64(q), f64(z), f64(lp), f64(rew), f64(mask), f64(mc), 0.6, 0.97)
+    np.testing.assert_allclose(npy(a["loss"]), wl, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(a["grad"]), wg * f64(w), rtol=1e-4, atol=1e-6)
