@@ -358,6 +358,15 @@ def run_ours(args):
     value = world * M * P / (ms_step * 1e-3)
     chk = bufs[last_buf[0]] if pipelined else bufs[0]  # the batch of the last timed pass: spot-checked against the oracle below
 
+    # ---- spot check of the last timed pass against the oracle (outside the timed region; oracle/ is the checker only).  It runs here,
+    #      before the sections below reuse the batch buffers and loss / grad for their own launches ------------------------------------
+    parity = None
+    if not args.no_parity_check and rank == 0:
+        parity = oracle_spot_check(torch, ring, chk, z, q, lp, loss, grad, n, exact)
+    loss_mean_timed, relabel_frac_timed = float(loss.mean()), float(chk["flags"].float().mean())
+    if dist:
+        dist.barrier()
+
     # ---- single-batch launches (B=4096 windows per launch): latency-bound figure, reported beside the headline ----
     def small_step(i):
         o = (i % D) * B
@@ -566,11 +575,6 @@ def run_ours(args):
                    "note": "policy/critic MLPs are ordinary PyTorch fp32 modules; sample/relabel/target/loss are this repo's CUDA kernels; "
                            "the whole step (kernels + MLP fwd/bwd + gradient all-reduce + Adam + target update) is one captured CUDA graph"}
 
-    # ---- spot check of the last timed pass against the oracle (outside the timed region; oracle/ is the checker only) ----------------
-    parity = None
-    if not args.no_parity_check and rank == 0:
-        parity = oracle_spot_check(torch, ring, chk, z, q, lp, loss, grad, n, exact)
-
     # ---- roofline of the dominant kernel (by measured time) ------------------------------------------------------------
     peak, peak_src = peaks()
     gname = "sample_gather_lean_kernel" if pipelined else "sample_gather_tile_kernel"
@@ -648,7 +652,7 @@ def run_ours(args):
                                       "note": "2 launches per 4096-window batch from Python (gather with fused draw, loss), launch-latency bound",
                                       "cuda_graph_4_streams": {"ms_per_batch": graph_ms, "transitions_per_s": world * B / (graph_ms * 1e-3),
                                                                "note": "16 batches x 2 launches captured once, round-robin over four streams"}},
-            "checks": {"loss_mean": float(loss.mean()), "relabel_frac": float(flags.float().mean()),
+            "checks": {"loss_mean": loss_mean_timed, "relabel_frac": relabel_frac_timed,
                        "violations": float(stats[2] / max(float(stats[3]), 1) / CQ), "parity_vs_oracle": parity}}
     if secondary:
         line["secondary_T50"] = secondary

@@ -531,6 +531,14 @@ __device__ __forceinline__ bool grp_stage_rows(float* dst, const float* __restri
                                                bool aligned, int lane, uint32_t bar) {
   const float* g1 = src + m0 * width;
   const int nfl = rows * width;
+#ifdef FDQL_TQC_STAGE_LDGSTS
+  if (aligned && rows == full_rows && (nfl & 3) == 0) {  // 16-byte asynchronous copies by every lane; the reader waits on the group
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    for (int i = lane; i < (nfl >> 2); i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * (uint32_t)i), "l"(g1 + 4 * i) : "memory");
+    return true;
+  }
+#endif
   if (aligned && rows == full_rows) {
     if (lane == 0) {
       mbar_expect_tx(bar, 4u * (uint32_t)nfl);
@@ -640,8 +648,13 @@ __global__ void __launch_bounds__(FDQL_TQC_BOUND_THREADS, 1) tqc_loss_group_kern
     float* Zb = W + buf * C::kZY;
     const uint32_t aZb = aW + 4 * buf * C::kZY;
     const bool q_bulk = grp_stage_rows(qs, a.q_pred, m0, n, rows, G, qal, lane, aBar + 16);
+#ifdef FDQL_TQC_STAGE_LDGSTS
+    cp_async_commit();   // (group of this round's q_pred rows)
+    cp_async_wait<1>();  // everything older has landed: this round's per-transition inputs and next_z rows
+#else
     cp_async_wait<0>();  // this round's per-transition inputs have landed
     if (z_bulk) mbar_wait(aBar + 8 * buf, (it >> 1) & 1);  // ... and its next_z rows
+#endif
     __syncwarp();
 
     // ================= phase A: LPT lanes per transition =================
@@ -769,7 +782,11 @@ __global__ void __launch_bounds__(FDQL_TQC_BOUND_THREADS, 1) tqc_loss_group_kern
       }
       cp_async_commit();
     }
+#ifdef FDQL_TQC_STAGE_LDGSTS
+    cp_async_wait<1>();  // all but the group committed just above: this round's q_pred rows have landed
+#else
     if (q_bulk) mbar_wait(aBar + 16, it & 1);  // this round's q_pred rows have landed
+#endif
     __syncwarp();
 
     // ================= phase B: the warp per transition =================
