@@ -76,6 +76,8 @@ def parse():
                     help="episode_step of relabelled rows re-based inside the window only (mask / is_contiguous stay exact); default: "
                          "the reference's value (her.py:72-83), bit for bit")
     ap.add_argument("--serial", action="store_true", help="gather and loss back to back on one stream instead of pipelined on two")
+    ap.add_argument("--no-step-graph", action="store_true",
+                    help="pipelined schedule launched from Python every step instead of one captured CUDA graph per step")
     ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE.json configs[0..2] sections (Pendulum / CartPole / 64-bit HER shapes)")
@@ -216,7 +218,10 @@ def run_ours(args):
     p = lambda t: C.c_void_p(t.data_ptr())
     rlen = len(ring)
     counter = [0]
+    ctr_dev = torch.zeros(4, dtype=torch.int64, device=device)  # device-side draw counter of the captured step
+    use_ctr_dev = [False]
     pipelined = not args.serial and not args.separate_streams
+    step_graph = pipelined and not args.no_step_graph
     P = args.passes_per_step or 64
 
     # argument tuples are built once per (buffer, stream): the pipelined schedule needs ~6000 launches per second from this loop
@@ -237,6 +242,8 @@ def run_ours(args):
         if args.separate_streams:
             L.check(lib.fdql_sample_streams(*a["draw_head"], counter[0], *a["streams_tail"]))
             L.check(lib.fdql_sample_gather(*a["gather"]))
+        elif use_ctr_dev[0]:  # captured launches: the draw counter lives in device memory and every launch advances it
+            L.check(lib.fdql_sample_gather_draw(*a["draw_head"], 1 << 40, p(ctr_dev), *a["draw_tail"][1:]))
         else:  # streams drawn inside the gather kernel: one launch
             L.check(lib.fdql_sample_gather_draw(*a["draw_head"], counter[0], *a["draw_tail"]))
         counter[0] += 1
@@ -269,9 +276,11 @@ def run_ours(args):
     def run_pipelined(n_pass, evs=None, every=16):
         """loss stream: loss(k); side stream: gather(k+1).  loss(k) waits for gather(k); gather(k+2) waits for loss(k), whose
         inputs it overwrites.  Starts and ends with nothing in flight: n_pass gathers and n_pass losses, all inside the call
-        (both streams fork from and join back into the caller's stream)."""
+        (both streams fork from and join back into the caller's stream, so the call can be captured into a CUDA graph).  Timing
+        events (evs) only take timestamps; the dependencies ride on their own events."""
+        cur_stream = torch.cuda.current_stream(device)
         t0 = torch.cuda.Event()
-        t0.record(stream)
+        t0.record(cur_stream)
         side.wait_event(t0)
         loss_stream.wait_event(t0)
         done_g, done_t = [None, None], [None, None]
@@ -287,16 +296,20 @@ def run_ours(args):
                 if e:
                     e[0].record(side)
                 gather(bufs[nxt], side, L.OPT_CORESIDENT)
-                done_g[nxt] = e[1] if e else torch.cuda.Event()
+                if e:
+                    e[1].record(side)
+                done_g[nxt] = torch.cuda.Event()
                 done_g[nxt].record(side)
             loss_stream.wait_event(done_g[cur])
             if e:
                 e[2].record(loss_stream)
             tqc(bufs[cur], loss_stream)
-            done_t[cur] = e[3] if e else torch.cuda.Event()
+            if e:
+                e[3].record(loss_stream)
+            done_t[cur] = torch.cuda.Event()
             done_t[cur].record(loss_stream)
-        stream.wait_event(done_t[(n_pass - 1) & 1])
-        stream.wait_event(done_g[(n_pass - 1) & 1])
+        cur_stream.wait_event(done_t[(n_pass - 1) & 1])
+        cur_stream.wait_event(done_g[(n_pass - 1) & 1])
         last_buf[0] = (n_pass - 1) & 1
 
     # ---- the two kernels alone, back to back on one stream (kernel-level figures; also the --serial headline) ----
@@ -316,6 +329,21 @@ def run_ours(args):
     torch.cuda.synchronize(device)
     K = args.steps
     n_ev = 8
+    cg_step = None
+    if step_graph:
+        # one step = P passes of the pipelined schedule captured ONCE (both streams, every cross-stream dependency, device-side draw
+        # counter); the timed region replays it K times.  Eight passes of the step carry external timing events around their two
+        # kernels (event-record nodes: they take real timestamps at every replay).
+        use_ctr_dev[0] = True
+        run_pipelined(2)  # the counter-from-device variant of the launch, once outside the capture
+        torch.cuda.synchronize(device)
+        gev = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(4)] for _ in range(n_ev)]
+        cg_step = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg_step):
+            run_pipelined(P, gev, every=max(P // n_ev, 1))
+        for _ in range(2):
+            cg_step.replay()
+        torch.cuda.synchronize(device)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K * n_ev)]
     clocks = ClockSampler(local)
     clocks.start()
@@ -326,8 +354,14 @@ def run_ours(args):
     t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    g_acc = np.zeros((0, 3))
     for i in range(K):
-        if pipelined:
+        if cg_step is not None:
+            cg_step.replay()
+            if i % 25 == 24 or i == K - 1:  # read the in-graph timestamps of this replay (a sync every 25 steps; the GPU queue is 25 deep)
+                torch.cuda.current_stream(device).synchronize()
+                g_acc = np.concatenate([g_acc, [[float("nan"), e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])] for e in gev]])
+        elif pipelined:
             run_pipelined(P, evs[i * n_ev:(i + 1) * n_ev], every=max(P // n_ev, 1))
         else:
             run_serial(P, [[a, b_, c] for a, b_, c, _ in evs[i * n_ev:(i + 1) * n_ev]])
@@ -344,7 +378,9 @@ def run_ours(args):
             return a.elapsed_time(b_)
         except Exception:  # an event that was never recorded (P < 8 passes per step)
             return float("nan")
-    if pipelined:
+    if cg_step is not None:
+        k_ms = np.nanmean(g_acc, 0)
+    elif pipelined:
         k_ms = np.nanmean(np.array([[float("nan"), _el(e[0], e[1]), _el(e[2], e[3])] for e in evs]), 0)  # -, gather, tqc (overlapped)
     else:
         k_ms = np.nanmean(np.array([[float("nan"), _el(e[0], e[1]), _el(e[1], e[2])] for e in evs]), 0)
@@ -640,7 +676,9 @@ def run_ours(args):
                        "transitions_per_pass_per_gpu": M,
                        "schedule": ("pipelined on two streams: gather of pass k+1 (FDQL_OPT_CORESIDENT, two 4-warp blocks per SM) under the "
                                     "loss of pass k, as the reference's prefetch thread does (torch_dataloader.py:22-39); every pass complete "
-                                    "inside the timed region") if pipelined else "gather and loss back to back on one stream",
+                                    "inside the timed region" + ("; one step = one captured CUDA graph, replayed" if step_graph else
+                                                                  "; launched from Python")) if pipelined
+                       else "gather and loss back to back on one stream",
                        "ring_rows_per_gpu": len(ring) + 1,
                        "l2": "inputs larger than L2 (random rows of a %.1f GB arena; %d MB of critic outputs per step)"
                              % ((len(ring) + 1) * (ROW_BYTES + 16) / 1e9, M * CQ * 8 // 2 ** 20),

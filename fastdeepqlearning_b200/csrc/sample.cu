@@ -1222,40 +1222,19 @@ __global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(con
   const int T = g.T;
   const int len32 = (int)g.len;
 
-  // ---- row plan: lane v owns float4 v of the concatenated wide row (keys without an output take no lanes) -------------------
-  const char* src = nullptr;   // slab base + 16 * (float4 index inside the key)
-  uint32_t sstride = 0;        // bytes between slab rows
-  uint32_t dst_off = 0;        // byte offset of this lane's float4 inside a stage, window 0
-  uint32_t dst_pitch = 0;      // bytes between windows of the key inside a stage
-  const char* ag_src = nullptr;  // desired_goal lanes: the achieved_goal slab + 16 * (float4 index), read for relabelled rows
-  uint32_t ag_stride = 0;
-  int dg_bias = 0x40000000;    // t + dg_bias <= tail_last  <=>  this lane is a desired_goal lane and window row t is relabelled
-  uint32_t stage_bytes = 0;
-  {
-    int i = lane;
-    bool found = false;
-    uint32_t off = 0;
-    for (int w = 0; w < A.n_wide; ++w) {
-      const int vecs = g.out.p[A.wide[w].key] != nullptr ? A.wide[w].vecs : 0;
-      if (!found && i >= 0 && i < vecs) {
-        found = true;
-        src = reinterpret_cast<const char*>(A.wide[w].base) + 16 * i;
-        sstride = 4u * (uint32_t)A.wide[w].stride;
-        dst_off = off + 16u * i;
-        dst_pitch = 16u * vecs;
-        if (HASH && w == A.wide_dg) {
-          dg_bias = 0;
-          ag_src = reinterpret_cast<const char*>(A.wide[A.wide_ag].base) + 16 * i;
-          ag_stride = 4u * (uint32_t)A.wide[A.wide_ag].stride;
-        }
-      }
-      i -= vecs;
-      off += 16u * vecs * kLeanStageWindows;
+  // ---- lane plan: lane = window-in-stage * kParts + part; a lane moves float4 part, part + kParts, ... of every wide key of its
+  //      window, so ONE cp.async instruction serves all the windows of a stage (keys without an output are skipped)
+  constexpr int kParts = 32 / kLeanStageWindows;
+  const int wl = lane / kParts, part = lane % kParts;
+  uint32_t stage_bytes = 0, key_mask = 0;  // bit w: wide key w has an output
+  for (int w = 0; w < A.n_wide; ++w)
+    if (g.out.p[A.wide[w].key] != nullptr) {
+      key_mask |= 1u << w;
+      stage_bytes += 16u * (uint32_t)A.wide[w].vecs * kLeanStageWindows;
     }
-    stage_bytes = off;
-  }
-  const bool has_vec = src != nullptr;
   const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * 2u * stage_bytes;  // two stages per warp
+  const char* ag_base = HASH ? reinterpret_cast<const char*>(A.wide[A.wide_ag].base) : nullptr;
+  const uint32_t ag_stride = HASH ? 4u * (uint32_t)A.wide[A.wide_ag].stride : 0u;
 
   const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter) : 0;
   const int64_t n_windows = g.b_end - g.b_begin;
@@ -1295,25 +1274,37 @@ __global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(con
     else if (lane < n_here) window_scalar_phase<HASH, DRAW>(g, cb0 + lane, draw_ctr, s, grow, tail_last);
     __syncwarp();
     for (int t = 0; t < ((g.dbg & 1) ? 0 : T); ++t) {
-      const int t_dg = t + dg_bias;
       for (int w0 = 0; w0 < n_here; w0 += kLeanStageWindows, ++it) {
         const int nw = min(kLeanStageWindows, n_here - w0);
         const uint32_t buf = it & 1u;
         // the bulk write-back that read this buffer (issued one stage ago, for the stage before that) must be done reading it
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
-        uint32_t sdst = warp_smem + buf * stage_bytes + dst_off;
-#pragma unroll 4
-        for (int w = 0; w < nw; ++w, sdst += dst_pitch) {
-          // (registers, not shared memory: next to the loss kernel the shared-memory pipe is the busiest unit of the SM)
-          const int sw = __shfl_sync(kFull, s, w0 + w);
-          const int tlw = __shfl_sync(kFull, tail_last, w0 + w);
-          const int gw = __shfl_sync(kFull, grow, w0 + w);
-          unsigned row = (unsigned)sw + (unsigned)t;
-          if (row >= (unsigned)len32) row -= (unsigned)len32;
-          const char* p = src + (uint64_t)row * sstride;
-          if (HASH && t_dg <= tlw) p = ag_src + (uint64_t)(unsigned)gw * ag_stride;
-          if (has_vec) cp_async16(sdst, p);
+        // (registers, not shared memory: next to the loss kernel the shared-memory pipe is the busiest unit of the SM)
+        const int sw = __shfl_sync(kFull, s, w0 + wl);
+        const int tlw = __shfl_sync(kFull, tail_last, w0 + wl);
+        const int gw = __shfl_sync(kFull, grow, w0 + wl);
+        unsigned row = (unsigned)sw + (unsigned)t;
+        if (row >= (unsigned)len32) row -= (unsigned)len32;
+        const bool relab = HASH && t <= tlw;
+        uint32_t koff = warp_smem + buf * stage_bytes + 16u * (uint32_t)part;
+        for (int w = 0; w < A.n_wide; ++w) {
+          if (((key_mask >> w) & 1u) == 0u) continue;
+          const int vecs = A.wide[w].vecs;
+          const char* kb = reinterpret_cast<const char*>(A.wide[w].base);
+          uint32_t kst = 4u * (uint32_t)A.wide[w].stride, kr = row;
+          if (HASH && w == A.wide_dg && relab) {  // desired_goal of a relabelled row: the hindsight goal row's achieved_goal
+            kb = ag_base;
+            kst = ag_stride;
+            kr = (unsigned)gw;
+          }
+          const char* p = kb + (uint64_t)kr * kst + 16 * part;
+          uint32_t d = koff + (uint32_t)wl * (16u * (uint32_t)vecs);
+          if (wl < nw) {
+            for (int j = 0; j < vecs; j += kParts, p += 16 * kParts, d += 16u * kParts)
+              if (j + part < vecs) cp_async16(d, p);
+          }
+          koff += 16u * (uint32_t)vecs * kLeanStageWindows;
         }
         cp_async_commit_group();
         if (it > 0) {  // the previous stage has had a whole stage of issue time to land

@@ -121,13 +121,14 @@ def free_running():
 lib.fdql_debug_force_generic_gather(0)
 lib.fdql_set_coresident(0)
 print(f"tile gather alone {timed(only_gather):.4f}  tqc alone (20 warps) {timed(only_tqc):.4f}", flush=True)
-for w in (16, 14, 12):
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
+for w in ((16,) if quick else (16, 14, 12)):
     lib.fdql_debug_tqc_warp_kernel(w << 8)
     lib.fdql_set_coresident(1)
     gopt[0] = L.OPT_CORESIDENT
     tt = timed(only_tqc)
-    for ctas in (1, 2):
-        for dbg in (0, 1, 2, 4):
+    for ctas in ((2,) if quick else (1, 2)):
+        for dbg in ((0, 1, 2) if quick else (0, 1, 2, 4)):
             lib.fdql_debug_force_generic_gather((ctas << 20) | (dbg << 6))
             ga = timed(only_gather)
             o2 = timed(lambda: overlapped(2))
