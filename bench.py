@@ -76,6 +76,7 @@ def parse():
                     help="episode_step of relabelled rows re-based inside the window only (mask / is_contiguous stay exact); default: "
                          "the reference's value (her.py:72-83), bit for bit")
     ap.add_argument("--serial", action="store_true", help="gather and loss back to back on one stream instead of pipelined on two")
+    ap.add_argument("--buffers", type=int, default=3, help="batch buffers of the pipelined schedule (gathers run up to buffers-1 passes ahead)")
     ap.add_argument("--no-step-graph", action="store_true",
                     help="pipelined schedule launched from Python every step instead of one captured CUDA graph per step")
     ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
@@ -200,7 +201,8 @@ def run_ours(args):
                 "contig": torch.empty(T - 1, n, device=device), "weight": torch.empty(T - 1, n, device=device),
                 "starts": torch.empty(n, dtype=torch.int64, device=device), "flags": torch.empty(n, dtype=torch.uint8, device=device),
                 "goals": torch.empty(n, dtype=torch.int64, device=device)}
-    bufs = [make_buf(), make_buf()]  # the pipelined schedule samples pass k+1 into one while pass k's loss reads the other
+    NB = max(2, args.buffers)
+    bufs = [make_buf() for _ in range(NB)]  # the pipelined schedule samples passes k+1 .. k+NB-1 into the others while pass k's loss reads one
     out, outp, aux_mask, aux_contig, aux_weight = (bufs[0][k] for k in ("out", "outp", "mask", "contig", "weight"))
     starts, flags, goals = bufs[0]["starts"], bufs[0]["flags"], bufs[0]["goals"]
     loss = torch.empty(M, device=device)
@@ -274,32 +276,38 @@ def run_ours(args):
     loss_stream = torch.cuda.Stream(device)
 
     def run_pipelined(n_pass, evs=None, every=16):
-        """loss stream: loss(k); side stream: gather(k+1).  loss(k) waits for gather(k); gather(k+2) waits for loss(k), whose
-        inputs it overwrites.  Starts and ends with nothing in flight: n_pass gathers and n_pass losses, all inside the call
-        (both streams fork from and join back into the caller's stream, so the call can be captured into a CUDA graph).  Timing
-        events (evs) only take timestamps; the dependencies ride on their own events."""
+        """loss stream: loss(k); side stream: gathers up to NB - 1 passes ahead.  loss(k) waits for gather(k); gather(k + NB) waits
+        for loss(k), whose inputs it overwrites (NB batch buffers: with three, the gather of pass k+2 fills the SMs while loss(k)
+        drains and loss(k+1) ramps up).  Starts and ends with nothing in flight: n_pass gathers and n_pass losses, all inside the
+        call (both streams fork from and join back into the caller's stream, so the call can be captured into a CUDA graph).
+        Timing events (evs) only take timestamps; the dependencies ride on their own events."""
         cur_stream = torch.cuda.current_stream(device)
         t0 = torch.cuda.Event()
         t0.record(cur_stream)
         side.wait_event(t0)
         loss_stream.wait_event(t0)
-        done_g, done_t = [None, None], [None, None]
-        gather(bufs[0], side, L.OPT_CORESIDENT)
-        done_g[0] = torch.cuda.Event()
-        done_g[0].record(side)
-        for k in range(n_pass):
-            cur, nxt = k & 1, (k + 1) & 1
+        done_g, done_t = [None] * NB, [None] * NB
+
+        def issue_gather(k):
             e = evs[k // every] if evs is not None and k % every == every // 2 and k // every < len(evs) else None
-            if k + 1 < n_pass:
-                if done_t[nxt] is not None:
-                    side.wait_event(done_t[nxt])
-                if e:
-                    e[0].record(side)
-                gather(bufs[nxt], side, L.OPT_CORESIDENT)
-                if e:
-                    e[1].record(side)
-                done_g[nxt] = torch.cuda.Event()
-                done_g[nxt].record(side)
+            slot = k % NB
+            if done_t[slot] is not None:
+                side.wait_event(done_t[slot])
+            if e:
+                e[0].record(side)
+            gather(bufs[slot], side, L.OPT_CORESIDENT)
+            if e:
+                e[1].record(side)
+            done_g[slot] = torch.cuda.Event()
+            done_g[slot].record(side)
+
+        for k in range(min(NB - 1, n_pass)):
+            issue_gather(k)
+        for k in range(n_pass):
+            cur = k % NB
+            e = evs[k // every] if evs is not None and k % every == every // 2 and k // every < len(evs) else None
+            if k + NB - 1 < n_pass:
+                issue_gather(k + NB - 1)
             loss_stream.wait_event(done_g[cur])
             if e:
                 e[2].record(loss_stream)
@@ -308,9 +316,14 @@ def run_ours(args):
                 e[3].record(loss_stream)
             done_t[cur] = torch.cuda.Event()
             done_t[cur].record(loss_stream)
-        cur_stream.wait_event(done_t[(n_pass - 1) & 1])
-        cur_stream.wait_event(done_g[(n_pass - 1) & 1])
-        last_buf[0] = (n_pass - 1) & 1
+        cur_stream.wait_event(done_t[(n_pass - 1) % NB])
+        cur_stream.wait_event(side_join(side))
+        last_buf[0] = (n_pass - 1) % NB
+
+    def side_join(st):
+        e = torch.cuda.Event()
+        e.record(st)
+        return e
 
     # ---- the two kernels alone, back to back on one stream (kernel-level figures; also the --serial headline) ----
     lib.fdql_set_coresident(0)
@@ -674,10 +687,10 @@ def run_ours(args):
                                    % (len(ring) + 1),
                        "batch": B, "temporal_len": T, "batches_per_step": D, "passes_per_step": P, "transitions_per_step_per_gpu": M * P,
                        "transitions_per_pass_per_gpu": M,
-                       "schedule": ("pipelined on two streams: gather of pass k+1 (FDQL_OPT_CORESIDENT, two 4-warp blocks per SM) under the "
-                                    "loss of pass k, as the reference's prefetch thread does (torch_dataloader.py:22-39); every pass complete "
+                       "schedule": ("pipelined on two streams over %d batch buffers: gather of pass k+1 (FDQL_OPT_CORESIDENT, two 4-warp blocks per SM) "
+                                    "under the loss of pass k, as the reference's prefetch thread does (torch_dataloader.py:22-39); every pass complete "
                                     "inside the timed region" + ("; one step = one captured CUDA graph, replayed" if step_graph else
-                                                                  "; launched from Python")) if pipelined
+                                                                  "; launched from Python")) % NB if pipelined
                        else "gather and loss back to back on one stream",
                        "ring_rows_per_gpu": len(ring) + 1,
                        "l2": "inputs larger than L2 (random rows of a %.1f GB arena; %d MB of critic outputs per step)"

@@ -64,11 +64,11 @@ def test_q_loss_matches_reference_operator_sequence(fdql, distributional):
                                           c(nxt["mask"]).numpy(), c(nxt["mc_return"]).numpy(), float(ac.curr_alpha), conf.gamma)
         np.testing.assert_allclose(c(q_loss).numpy(), lo, rtol=1e-5, atol=1e-6)
         want = gr * c(w).numpy()
-        np.testing.assert_allclose(c(gq).numpy(), want, rtol=1e-4, atol=1e-5 * np.abs(want).max())
+        np.testing.assert_allclose(c(gq).numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
         return
     np.testing.assert_allclose(c(q_loss).numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
     (gref,) = torch.autograd.grad((ref * c(w)).sum(), qp)
-    np.testing.assert_allclose(c(gq).numpy(), gref.numpy(), rtol=1e-4, atol=1e-5 * float(gref.abs().max()))
+    np.testing.assert_allclose(c(gq).numpy(), gref.numpy(), rtol=1e-5, atol=1e-5 * float(gref.abs().max()))
     np.testing.assert_allclose(float(summ["q_pred_mu"]), float(q_pred.mean()), rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(float(summ["q_pred_var"]), float(q_pred.var(-1).mean()), rtol=1e-4)
     lb = (nxt["mc_return"] - q_pred).relu()

@@ -342,7 +342,7 @@ def test_sac_bootstrap_bound_matches_reference(fdql):
         np.testing.assert_allclose(npy(bound), g[p + "bound"], rtol=1e-5, atol=1e-6)
         ((loss * t("up_q")).sum() + (bound * t("up_b")).sum()).backward()
         want = g[p + "grad"]
-        np.testing.assert_allclose(npy(q_pred.grad), want, rtol=1e-4, atol=1e-5 * np.abs(want).max())
+        np.testing.assert_allclose(npy(q_pred.grad), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
         np.testing.assert_allclose(float(summ["bootstrap_minibatch_nstep_violations"]), float(g[p + "viol"]), rtol=1e-6)
 
 
@@ -627,7 +627,7 @@ def test_baseline_config_shapes_vs_oracle(fdql, name):
         wl, wg, _ = O.tqc_q_loss(f64(q), f64(z), f64(lp), want["reward"][1:].astype(np.float64), mask[1:].astype(np.float64),
                                  want["mc_return"][1:].astype(np.float64), 0.7, gamma, sp["n_drop"])
     np.testing.assert_allclose(npy(got["loss"]), wl, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(npy(got["grad"]), wg, rtol=1e-4, atol=1e-5 * np.abs(wg).max())
+    np.testing.assert_allclose(npy(got["grad"]), wg, rtol=1e-5, atol=1e-5 * np.abs(wg).max())
 
 
 @pytest.mark.parametrize("n_atoms", [1, 5, 12, 16])
@@ -654,4 +654,4 @@ def test_sac_thread_kernel_equals_warp_kernel(fdql, n_atoms):
     f64 = lambda t: npy(t).astype(np.float64)
     wl, wg, _ = O.sac_min_target_loss(f64(q), f64(z), f64(lp), f64(rew), f64(mask), f64(mc), 0.6, 0.97)
     np.testing.assert_allclose(npy(a["loss"]), wl, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(npy(a["grad"]), wg * f64(w), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(npy(a["grad"]), wg * f64(w), rtol=1e-5, atol=1e-6)

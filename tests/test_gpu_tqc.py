@@ -24,7 +24,7 @@ def dev(x):
 def grad_close(got, want, scale_ref):
     # elementwise 1e-5 of the gradient's own scale (entries can cancel to ~0, so pure relative is meaningless there)
     tol = 1e-5 * max(float(np.abs(scale_ref).max()), 1e-30)
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=tol)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=tol)
 
 
 def test_quantile_huber_goldens(ops):
