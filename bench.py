@@ -746,7 +746,7 @@ EXTRA_SPECS = {
 }
 
 
-def extra_configs(torch, pkg, Replay, L, lib, device, rows=2_000_000, D=16, reps=10):
+def extra_configs(torch, pkg, Replay, L, lib, device, rows=2_000_000, D=64, reps=10):
     """One serial pass (gather [+ relabel] [+ one-hot] + loss) at the other BASELINE.json shapes: D batches of 4096 windows, T = 2, on a
     ring of `rows` rows; per-kernel CUDA-event times, algorithmic bytes (SURVEY.md section 8d applied to the shape) and roofline
     fractions.  Parity on the same shapes: tests/test_gpu_r2.py::test_baseline_config_shapes_vs_oracle."""

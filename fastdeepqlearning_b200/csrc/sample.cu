@@ -33,9 +33,25 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr_lo, uint64_t ctr_hi, ui
   return make_uint4(c0, c1, c2, c3);
 }
 
+// a whole 8-float scalar record (one 32-byte sector) in ONE load instruction: a thread-per-window phase reads records of 32
+// unrelated rows per warp instruction, so every separate column load costs the L1 another 32 sector look-ups
+__device__ __forceinline__ void ld_rec8(const float* rec, float (&r)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(rec));
+}
+__device__ __forceinline__ float pick8(const float (&r)[8], int c) {  // r[c] for a run-time column without local memory
+  float v = r[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) v = c == k ? r[k] : v;
+  return v;
+}
+
 // one window's streams: start ~ U[0, range), flag ~ Bernoulli(p) (never for rows of uncommitted episodes), goal row by mode
+// (rec8: when given, the start row's scalar record is 8 floats wide and is returned whole for the caller's own use)
 __device__ __forceinline__ void draw_window(const ArenaDev& A, int64_t b, int64_t range, int goal_mode, float relabel_prob, uint64_t seed,
-                                            uint64_t counter, bool want_flags, int64_t& s, bool& f, int64_t& g, int& es, int& ee) {
+                                            uint64_t counter, bool want_flags, int64_t& s, bool& f, int64_t& g, int& es, int& ee,
+                                            float (*rec8)[8] = nullptr) {
   const uint4 x = philox4x32((uint64_t)b, counter, seed);
   const uint64_t r64 = ((uint64_t)x.x << 32) | x.y;
   s = (int64_t)__umul64hi(r64, (uint64_t)range);
@@ -45,8 +61,14 @@ __device__ __forceinline__ void draw_window(const ArenaDev& A, int64_t b, int64_
   ee = -1;
   if (!want_flags) return;
   const float* rec = A.rec + s * (int64_t)A.rec_stride;
-  es = __float_as_int(__ldg(rec + A.col_ep_start));
-  ee = __float_as_int(__ldg(rec + A.col_ep_end));
+  if (rec8 != nullptr) {
+    ld_rec8(rec, *rec8);
+    es = __float_as_int(pick8(*rec8, A.col_ep_start));
+    ee = __float_as_int(pick8(*rec8, A.col_ep_end));
+  } else {
+    es = __float_as_int(__ldg(rec + A.col_ep_start));
+    ee = __float_as_int(__ldg(rec + A.col_ep_end));
+  }
   f = (es >= 0) && ((float)x.z * 2.3283064365386963e-10f < relabel_prob);
   if (f) {
     const int64_t cap = A.capacity;
@@ -137,10 +159,25 @@ struct GatherArgs {
   int64_t* starts_out;
   uint8_t* flags_out;
   int64_t* goal_out;
-  int32_t dbg;       // probe switches of the lean kernel (1: no wide-key phase, 2: no scalar phase)
+  int32_t dbg;       // probe switches of the lean kernel (1: no wide-key phase, 2: no scalar phase, 4: FMA loop for the scalar phase,
+                     // 8: no cp.async fills, 16: no bulk write-back)
   int32_t use_link;  // tile kernel, equality rewards: link records are valid for this gamma -> O(hits) relabelled returns
   double log2_gamma, inv_gamma;
+  // lean kernel: the wide keys that have an output, resolved on the host (at most kLeanMaxKeys; more take the tile kernel)
+  struct LeanKey {
+    const char* base;    // slab
+    char* out;           // time-major output [T, n, 16 * vecs bytes]
+    uint32_t stride;     // bytes between slab rows
+    uint32_t vecs;       // float4 per row
+    uint32_t stage_off;  // byte offset of the key inside a stage, in units of one stage window (x kLeanStageWindows in the kernel)
+    int32_t is_dg;       // desired_goal: relabelled rows read the hindsight goal row's achieved_goal instead
+  } lean_key[4];
+  int32_t lean_nk;
+  uint32_t lean_row_bytes;  // sum of 16 * vecs over the keys = bytes of one window row in a stage
+  const char* lean_ag_base;
+  uint32_t lean_ag_stride;
 };
+constexpr int kLeanMaxKeys = 4;
 
 __device__ __forceinline__ double warp_suffix_scan(double v, double g, int lane) {
   // inclusive suffix scan of v with ratio g: out_l = sum_{m>=l} g^(m-l) v_m  (pairs (v, c) with c = g^(span))
@@ -856,12 +893,17 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
   int64_t s64;
   bool relabel = false;
   int tail_last = -1, ep_first = 0, grow = 0;
+  // 8-float scalar records (<= 6 scalar keys + the two extents) travel whole, one 256-bit load per row
+  const bool vec8 = A.rec_stride == 8;
+  float rv0[8];
+  bool have0 = false;
   if (DRAW) {  // fused draw: same generator, same streams as sample_streams_kernel
     int64_t g64;
     bool f;
     int es, ee;
+    have0 = HASH && vec8;
     draw_window(A, b, device_draw_range(g.counter_dev, g.draw_range, T), g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64,
-                es, ee);
+                es, ee, have0 ? &rv0 : nullptr);
     if (g.starts_out) g.starts_out[b] = s64;
     if (g.flags_out) g.flags_out[b] = f ? 1 : 0;
     if (g.goal_out) g.goal_out[b] = g64;
@@ -995,8 +1037,17 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
     const int row = ring_row32(s, t, len32);
     const float* rec = A.rec + (int64_t)row * A.rec_stride;
     const bool in_ep = HASH && relabel && t <= tail_last;
-    float v_step = A.col_ep_step >= 0 ? __ldg(rec + A.col_ep_step) : 0.f;
-    float v_done = A.col_task_done >= 0 ? __ldg(rec + A.col_task_done) : 0.f;
+    float rv[8];
+    if (vec8) {
+      if (t == 0 && have0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rv[k] = rv0[k];
+      } else {
+        ld_rec8(rec, rv);
+      }
+    }
+    float v_step = A.col_ep_step >= 0 ? (vec8 ? pick8(rv, A.col_ep_step) : __ldg(rec + A.col_ep_step)) : 0.f;
+    float v_done = A.col_task_done >= 0 ? (vec8 ? pick8(rv, A.col_task_done) : __ldg(rec + A.col_task_done)) : 0.f;
     float v_rew = 0.f;
     if (in_ep) {
       bool m;
@@ -1018,16 +1069,32 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
         v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + A.col_ep_step);
       if (m) seg_first = j0 + t + 1;
     }
-    for (int c = 0; c < A.n_scal; ++c) {
-      float* o = g.out.p[A.scal_key[c]];
-      if (o == nullptr) continue;
-      float val;
-      if (c == A.col_ep_step) val = v_step;
-      else if (c == A.col_task_done) val = v_done;
-      else if (in_ep && c == A.col_reward) val = v_rew;
-      else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
-      else val = __ldg(rec + c);
-      st_stream1(o + (int64_t)t * g.n + b, val);
+    if (vec8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c >= A.n_scal) break;
+        float* o = g.out.p[A.scal_key[c]];
+        if (o == nullptr) continue;
+        float val;
+        if (c == A.col_ep_step) val = v_step;
+        else if (c == A.col_task_done) val = v_done;
+        else if (in_ep && c == A.col_reward) val = v_rew;
+        else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
+        else val = rv[c];
+        st_stream1(o + (int64_t)t * g.n + b, val);
+      }
+    } else {
+      for (int c = 0; c < A.n_scal; ++c) {
+        float* o = g.out.p[A.scal_key[c]];
+        if (o == nullptr) continue;
+        float val;
+        if (c == A.col_ep_step) val = v_step;
+        else if (c == A.col_task_done) val = v_done;
+        else if (in_ep && c == A.col_reward) val = v_rew;
+        else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
+        else val = __ldg(rec + c);
+        st_stream1(o + (int64_t)t * g.n + b, val);
+      }
     }
     if (want_aux) {
       // mask = !task_done (deepQlearning.py:201); is_contiguous[t-1] = (step[t]==step[t-1]+1) & mask[t-1] (:202-203)
@@ -1213,28 +1280,29 @@ __device__ __forceinline__ void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {  // one lane of the converged warp, known to the compiler as a single-thread region
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 template <bool HASH, bool DRAW, int kLeanStageWindows>
-__global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(const __grid_constant__ GatherArgs g) {
+__global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(const __grid_constant__ GatherArgs g) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
-  const ArenaDev& A = g.A;
   const int lane = lane_id();
-  const int wib = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows that it (and the stage bookkeeping derived from it) is warp-uniform, and
+  // the bulk copies below take their operands from uniform registers without a per-lane uniformisation loop
+  const int wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const int T = g.T;
   const int len32 = (int)g.len;
 
   // ---- lane plan: lane = window-in-stage * kParts + part; a lane moves float4 part, part + kParts, ... of every wide key of its
-  //      window, so ONE cp.async instruction serves all the windows of a stage (keys without an output are skipped)
+  //      window, so ONE cp.async instruction serves all the windows of a stage
   constexpr int kParts = 32 / kLeanStageWindows;
+  constexpr int kMaxJ = 32 / kParts;  // a key has at most 32 float4 per row
   const int wl = lane / kParts, part = lane % kParts;
-  uint32_t stage_bytes = 0, key_mask = 0;  // bit w: wide key w has an output
-  for (int w = 0; w < A.n_wide; ++w)
-    if (g.out.p[A.wide[w].key] != nullptr) {
-      key_mask |= 1u << w;
-      stage_bytes += 16u * (uint32_t)A.wide[w].vecs * kLeanStageWindows;
-    }
+  const uint32_t stage_bytes = g.lean_row_bytes * kLeanStageWindows;
   const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * 2u * stage_bytes;  // two stages per warp
-  const char* ag_base = HASH ? reinterpret_cast<const char*>(A.wide[A.wide_ag].base) : nullptr;
-  const uint32_t ag_stride = HASH ? 4u * (uint32_t)A.wide[A.wide_ag].stride : 0u;
 
   const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter) : 0;
   const int64_t n_windows = g.b_end - g.b_begin;
@@ -1248,15 +1316,15 @@ __global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(con
     // (the caller has waited for the stage's cp.async groups)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy engine
     __syncwarp();
-    if (lane == 0) {  // one bulk copy per key: its 16 rows are contiguous in the stage and in the time-major output
-      uint32_t off = warp_smem + buf * stage_bytes;
+    if (elect_one()) {  // one bulk copy per key: its rows are contiguous in the stage and in the time-major output
+      const uint32_t sb = warp_smem + buf * stage_bytes;
       const int64_t orow = (int64_t)t * g.n + b0;
-      for (int w = 0; w < A.n_wide; ++w) {
-        float* o = g.out.p[A.wide[w].key];
-        if (o == nullptr) continue;
-        const uint32_t row_bytes = 16u * (uint32_t)A.wide[w].vecs;
-        bulk_store_s2g(reinterpret_cast<char*>(o) + orow * (int64_t)row_bytes, off, (uint32_t)nw * row_bytes);
-        off += row_bytes * kLeanStageWindows;
+#pragma unroll
+      for (int k = 0; k < kLeanMaxKeys; ++k) {
+        if (k < g.lean_nk && !(g.dbg & 16)) {
+          const uint32_t row_bytes = 16u * g.lean_key[k].vecs;
+          bulk_store_s2g(g.lean_key[k].out + orow * (int64_t)row_bytes, sb + g.lean_key[k].stage_off * kLeanStageWindows, (uint32_t)nw * row_bytes);
+        }
       }
       bulk_commit_group();
     }
@@ -1278,33 +1346,32 @@ __global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(con
         const int nw = min(kLeanStageWindows, n_here - w0);
         const uint32_t buf = it & 1u;
         // the bulk write-back that read this buffer (issued one stage ago, for the stage before that) must be done reading it
-        if (lane == 0) bulk_wait_group_read<0>();
+        if (elect_one()) bulk_wait_group_read<0>();
         __syncwarp();
         // (registers, not shared memory: next to the loss kernel the shared-memory pipe is the busiest unit of the SM)
-        const int sw = __shfl_sync(kFull, s, w0 + wl);
-        const int tlw = __shfl_sync(kFull, tail_last, w0 + wl);
-        const int gw = __shfl_sync(kFull, grow, w0 + wl);
+        // lanes past the last window of a short stage repeat that window: their slots are filled but never written back
+        const int src_lane = min(w0 + wl, n_here - 1);
+        const int sw = __shfl_sync(kFull, s, src_lane);
+        const int tlw = __shfl_sync(kFull, tail_last, src_lane);
+        const int gw = __shfl_sync(kFull, grow, src_lane);
         unsigned row = (unsigned)sw + (unsigned)t;
         if (row >= (unsigned)len32) row -= (unsigned)len32;
         const bool relab = HASH && t <= tlw;
-        uint32_t koff = warp_smem + buf * stage_bytes + 16u * (uint32_t)part;
-        for (int w = 0; w < A.n_wide; ++w) {
-          if (((key_mask >> w) & 1u) == 0u) continue;
-          const int vecs = A.wide[w].vecs;
-          const char* kb = reinterpret_cast<const char*>(A.wide[w].base);
-          uint32_t kst = 4u * (uint32_t)A.wide[w].stride, kr = row;
-          if (HASH && w == A.wide_dg && relab) {  // desired_goal of a relabelled row: the hindsight goal row's achieved_goal
-            kb = ag_base;
-            kst = ag_stride;
-            kr = (unsigned)gw;
+        const uint32_t dl = warp_smem + buf * stage_bytes + 16u * (uint32_t)part;
+#pragma unroll
+        for (int k = 0; k < kLeanMaxKeys; ++k) {
+          if (k < g.lean_nk) {
+            const uint32_t vecs = g.lean_key[k].vecs;
+            const char* p = g.lean_key[k].base + (uint64_t)row * g.lean_key[k].stride;
+            if (HASH && g.lean_key[k].is_dg && relab) p = g.lean_ag_base + (uint64_t)(unsigned)gw * g.lean_ag_stride;
+            p += 16 * part;
+            const uint32_t d = dl + g.lean_key[k].stage_off * kLeanStageWindows + (uint32_t)wl * (16u * vecs);
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j)
+              if ((uint32_t)(j * kParts) < vecs) {  // (uniform)
+                if ((uint32_t)(j * kParts + part) < vecs && !(g.dbg & 8)) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
+              }
           }
-          const char* p = kb + (uint64_t)kr * kst + 16 * part;
-          uint32_t d = koff + (uint32_t)wl * (16u * (uint32_t)vecs);
-          if (wl < nw) {
-            for (int j = 0; j < vecs; j += kParts, p += 16 * kParts, d += 16u * kParts)
-              if (j + part < vecs) cp_async16(d, p);
-          }
-          koff += 16u * (uint32_t)vecs * kLeanStageWindows;
         }
         cp_async_commit_group();
         if (it > 0) {  // the previous stage has had a whole stage of issue time to land
@@ -1321,7 +1388,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32) sample_gather_lean_kernel(con
     cp_async_wait_group<0>();
     finish_stage((it - 1) & 1u, p_t, p_b0, p_n);
   }
-  if (lane == 0) bulk_wait_group_read<0>();
+  if (elect_one()) bulk_wait_group_read<0>();
 }
 
 int g_tile_override = 0;
@@ -1399,9 +1466,27 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   // lean kernel (wide keys through cp.async staging + bulk write-back): asked for by FDQL_OPT_CORESIDENT (one block per SM, next to
   // the loss kernel of another stream) or by the tuning hook; needs whole-float4 keys and 16-byte aligned outputs
   bool lean_ok = wslots <= 1 && wide_vecs > 0 && (!relabel || hash_ok) && !(g_force_generic_gather & (1 | 8));
+  g.lean_nk = 0;
+  g.lean_row_bytes = 0;
   for (int w = 0; w < a->dev.n_wide && lean_ok; ++w) {
-    const float* o = out[a->dev.wide[w].key];
-    if (o != nullptr && ((a->dev.wide[w].width & 3) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0)) lean_ok = false;
+    float* o = out[a->dev.wide[w].key];
+    if (o == nullptr) continue;
+    if ((a->dev.wide[w].width & 3) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0 || g.lean_nk == kLeanMaxKeys) {
+      lean_ok = false;
+      break;
+    }
+    GatherArgs::LeanKey& K = g.lean_key[g.lean_nk++];
+    K.base = reinterpret_cast<const char*>(a->dev.wide[w].base);
+    K.out = reinterpret_cast<char*>(o);
+    K.stride = 4u * (uint32_t)a->dev.wide[w].stride;
+    K.vecs = (uint32_t)a->dev.wide[w].vecs;
+    K.stage_off = g.lean_row_bytes;
+    K.is_dg = (relabel && w == a->dev.wide_dg) ? 1 : 0;
+    g.lean_row_bytes += 16u * K.vecs;
+  }
+  if (relabel && a->dev.wide_ag >= 0) {
+    g.lean_ag_base = reinterpret_cast<const char*>(a->dev.wide[a->dev.wide_ag].base);
+    g.lean_ag_stride = 4u * (uint32_t)a->dev.wide[a->dev.wide_ag].stride;
   }
   const bool coresident = (opts & FDQL_OPT_CORESIDENT) != 0;
   if (lean_ok && (coresident || (g_force_generic_gather & 32))) {
@@ -1411,7 +1496,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     const int stage_w = coresident ? 8 : 16;  // co-resident: two blocks of half-size stages per SM (eight warps in 54 KB)
     const size_t lean_smem = (size_t)kLeanWarps * 2 * stage_w * 16 * wide_vecs;
     const int64_t chunks = (b_end - b_begin + 31) / 32;
-    g.dbg = (g_force_generic_gather >> 6) & 7;
+    g.dbg = (g_force_generic_gather >> 6) & 31;  // probe switches, see GatherArgs.dbg
 #define FDQL_LAUNCH_LEAN(HASHV, DRAWV)                                                                                     \
   do {                                                                                                                     \
     auto kern = coresident ? sample_gather_lean_kernel<HASHV, DRAWV, 8> : sample_gather_lean_kernel<HASHV, DRAWV, 16>;     \
@@ -1560,7 +1645,7 @@ int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
   g_tile_override = (on >> 8) & 0x1e0;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
   g_tile_ctas_per_sm = (on >> 20) & 0xf;  // bits 20..23: resident tile-kernel blocks per SM (0 = as many as fit)
-  g_force_generic_gather = on & 509;  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
+  g_force_generic_gather = on & (509 | (3 << 9));  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
                                      // bit 3: warp-per-window kernels instead of the tile kernel, bit 4: tile kernel without link records,
                                      // bit 5: lean kernel (cp.async staging + bulk write-back) wherever it can serve
   g_force_full_vector_relabel = (on >> 1) & 1;

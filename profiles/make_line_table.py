@@ -11,6 +11,7 @@ import sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 units = int(sys.argv[3]) if len(sys.argv) > 3 else 262144
+min_inst = float(sys.argv[4]) if len(sys.argv) > 4 else 2.0  # lines below this many warp instructions per unit are left out
 HERE = os.path.dirname(os.path.abspath(__file__))
 out = [f"# per-line instruction / shared-memory view ({tag}); report {os.path.basename(rep)}; all figures per unit "
        f"(= per transition / window, {units} per launch)\n"]
@@ -52,7 +53,7 @@ for kern, label in (("tqc_loss_group", "tqc_loss_group_kernel"), ("sample_gather
     out.append("opcodes: " + ", ".join(f"{k} {v / units:.1f}" for k, v in ops.most_common(16)) + "\n")
     out.append("| file:line | warp inst | smem wavefronts (ideal) | stall samples | source |\n|---|---|---|---|---|")
     for k in sorted(inst, key=lambda k: -inst[k]):
-        if inst[k] / units < 2.0 and wf[k] / units < 1.0 and smp[k] / ts < 0.01:
+        if inst[k] / units < min_inst and wf[k] / units < 1.0 and smp[k] / ts < 0.01:
             continue
         out.append(f"| {k[0]}:{k[1]} | {inst[k] / units:.1f} | {wf[k] / units:.1f} ({wfi[k] / units:.1f}) | {100 * smp[k] / ts:.1f} % | "
                    f"`{src[k][:90].replace('|', '/')}` |")

@@ -128,7 +128,7 @@ for w in ((16,) if quick else (16, 14, 12)):
     gopt[0] = L.OPT_CORESIDENT
     tt = timed(only_tqc)
     for ctas in ((2,) if quick else (1, 2)):
-        for dbg in ((0, 1, 2) if quick else (0, 1, 2, 4)):
+        for dbg in ((0, 1, 2, 2 | 8, 2 | 16, 2 | 8 | 16) if quick else (0, 1, 2, 4)):
             lib.fdql_debug_force_generic_gather((ctas << 20) | (dbg << 6))
             ga = timed(only_gather)
             o2 = timed(lambda: overlapped(2))

@@ -1,5 +1,5 @@
 """Launch the gather kernels alone at the bench's shape (262144 windows, T = 2, 1e7-row ring by default) for ncu captures.
-usage: python profiles/prof_gather.py [lean|tile] [ring_rows]"""
+usage: python profiles/prof_gather.py [lean|lean2|tile] [ring_rows]   (lean2 = the co-resident form bench.py runs: FDQL_OPT_CORESIDENT)"""
 import ctypes as C
 import os
 import sys
@@ -25,7 +25,7 @@ st, fl, go = (torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, dtyp
               torch.empty(n, dtype=torch.int64, device=dev))
 p = lambda t: C.c_void_p(t.data_ptr())
 params, n_params = ring.reward_op.c_params()
-opts = L.OPT_EMIT_LEARNER_AUX | L.OPT_EXACT_EPISODE_STEP
+opts = L.OPT_EMIT_LEARNER_AUX | L.OPT_EXACT_EPISODE_STEP | (L.OPT_CORESIDENT if which == "lean2" else 0)
 lib.fdql_debug_force_generic_gather(32 if which == "lean" else 0)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
