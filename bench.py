@@ -173,6 +173,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    if os.environ.get("FDQL_LIB"):  # A/B runs of kernel variants (profiles/variants/): another build of the same C ABI
+        L.LIB_PATH = os.environ["FDQL_LIB"]
     pkg.lib()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)

@@ -1286,6 +1286,9 @@ __device__ __forceinline__ bool elect_one() {  // one lane of the converged warp
   return pred != 0;
 }
 
+#ifndef FDQL_LEAN_MAXVECS
+#define FDQL_LEAN_MAXVECS 32
+#endif
 template <bool HASH, bool DRAW, int kLeanStageWindows>
 __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(const __grid_constant__ GatherArgs g) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
@@ -1299,8 +1302,10 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
   // ---- lane plan: lane = window-in-stage * kParts + part; a lane moves float4 part, part + kParts, ... of every wide key of its
   //      window, so ONE cp.async instruction serves all the windows of a stage
   constexpr int kParts = 32 / kLeanStageWindows;
-  constexpr int kMaxJ = 32 / kParts;  // a key has at most 32 float4 per row
-  const int wl = lane / kParts, part = lane % kParts;
+  constexpr int kMaxJ = FDQL_LEAN_MAXVECS / kParts;  // a key has at most FDQL_LEAN_MAXVECS float4 per row (wider keys: tile kernel)
+  const int wl = lane / kParts;
+  uint32_t wl_u = (uint32_t)wl, part_u = (uint32_t)(lane % kParts), part16 = 16u * part_u;
+  asm volatile("" : "+r"(wl_u), "+r"(part_u), "+r"(part16));  // held in registers (the compiler otherwise re-derives them per stage)
   const uint32_t stage_bytes = g.lean_row_bytes * kLeanStageWindows;
   const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * 2u * stage_bytes;  // two stages per warp
 
@@ -1350,27 +1355,33 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
         __syncwarp();
         // (registers, not shared memory: next to the loss kernel the shared-memory pipe is the busiest unit of the SM)
         // lanes past the last window of a short stage repeat that window: their slots are filled but never written back
-        const int src_lane = min(w0 + wl, n_here - 1);
+        const int src_lane = min(w0 + (int)wl_u, n_here - 1);
         const int sw = __shfl_sync(kFull, s, src_lane);
         const int tlw = __shfl_sync(kFull, tail_last, src_lane);
         const int gw = __shfl_sync(kFull, grow, src_lane);
         unsigned row = (unsigned)sw + (unsigned)t;
         if (row >= (unsigned)len32) row -= (unsigned)len32;
         const bool relab = HASH && t <= tlw;
-        const uint32_t dl = warp_smem + buf * stage_bytes + 16u * (uint32_t)part;
+        const uint32_t dl = warp_smem + buf * stage_bytes + part16;
 #pragma unroll
         for (int k = 0; k < kLeanMaxKeys; ++k) {
           if (k < g.lean_nk) {
-            const uint32_t vecs = g.lean_key[k].vecs;
             const char* p = g.lean_key[k].base + (uint64_t)row * g.lean_key[k].stride;
             if (HASH && g.lean_key[k].is_dg && relab) p = g.lean_ag_base + (uint64_t)(unsigned)gw * g.lean_ag_stride;
-            p += 16 * part;
-            const uint32_t d = dl + g.lean_key[k].stage_off * kLeanStageWindows + (uint32_t)wl * (16u * vecs);
+            p += part16;
+            const uint32_t d = dl + g.lean_key[k].stage_off * kLeanStageWindows + wl_u * (16u * g.lean_key[k].vecs);
+            if (!(g.dbg & 8)) {
+              // every round is one instruction predicated on "this lane has a float4 in it": no branches inside a stage, except that
+              // keys of a single round skip the other slots (measured: a jump table over the round count, and rotating the rounds per
+              // window so that the shared-memory writes are conflict free, both made the co-run slower)
+              const uint32_t vecs = g.lean_key[k].vecs;
+              if (part_u < vecs) cp_async16(d, p);
+              if (vecs > (uint32_t)kParts) {  // (uniform)
 #pragma unroll
-            for (int j = 0; j < kMaxJ; ++j)
-              if ((uint32_t)(j * kParts) < vecs) {  // (uniform)
-                if ((uint32_t)(j * kParts + part) < vecs && !(g.dbg & 8)) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
+                for (int j = 1; j < kMaxJ; ++j)
+                  if ((uint32_t)(j * kParts) + part_u < vecs) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
               }
+            }
           }
         }
         cp_async_commit_group();
@@ -1471,7 +1482,8 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   for (int w = 0; w < a->dev.n_wide && lean_ok; ++w) {
     float* o = out[a->dev.wide[w].key];
     if (o == nullptr) continue;
-    if ((a->dev.wide[w].width & 3) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0 || g.lean_nk == kLeanMaxKeys) {
+    if ((a->dev.wide[w].width & 3) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0 || g.lean_nk == kLeanMaxKeys ||
+        a->dev.wide[w].vecs > FDQL_LEAN_MAXVECS) {
       lean_ok = false;
       break;
     }

@@ -525,6 +525,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ bool grp_elect_one() {  // one lane of the converged warp
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 // rows [m0, m0 + rows) of a [M, width] matrix -> shared memory: one bulk copy issued by lane 0 and signalled on `bar` when the
 // run is 16-byte aligned and whole (returns true: the reader waits on the barrier), plain loads otherwise (returns false)
 __device__ __forceinline__ bool grp_stage_rows(float* dst, const float* __restrict__ src, int64_t m0, int width, int rows, int full_rows,
@@ -540,7 +545,7 @@ __device__ __forceinline__ bool grp_stage_rows(float* dst, const float* __restri
   }
 #endif
   if (aligned && rows == full_rows) {
-    if (lane == 0) {
+    if (grp_elect_one()) {
       mbar_expect_tx(bar, 4u * (uint32_t)nfl);
       bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), g1, 4u * (uint32_t)nfl, bar);
     }
@@ -564,7 +569,9 @@ __global__ void __launch_bounds__(FDQL_TQC_BOUND_THREADS, 1) tqc_loss_group_kern
   constexpr int NQ = STATS ? 3 : 1;  // per-transition sums reduced over the warp: loss, sum q, sum q^2
   extern __shared__ __align__(16) float grp_smem[];
   __shared__ double sm_stats[3];
-  const int lane = lane_id(), wib = threadIdx.x >> 5;
+  // (warp index through a shuffle: the compiler then knows that it, the group index and the staging addresses derived from it are
+  // warp-uniform, and the bulk copies take their operands from uniform registers without a per-lane uniformisation loop)
+  const int lane = lane_id(), wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const bool red_alias = a.grp_red_alias != 0;
   float* W = grp_smem + wib * (red_alias ? C::kWarpFloatsAlias : C::kWarpFloats);
   float2* QT = reinterpret_cast<float2*>(W + 2 * C::kZY);
