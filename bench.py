@@ -634,15 +634,16 @@ def run_ours(args):
                                  "bytes_per_transition": BYTES_GATHER + bytes_relabel + (0 if args.separate_streams else 17),
                                  "symbol": f"fdql::{gname}" + ("" if args.separate_streams else " (draws its own index / goal streams)"),
                                  "limiter": ("co-resident: two 4-warp blocks per SM under the loss kernel, wide keys through cp.async staging + "
-                                             "bulk shared->global write-back (LDGSTS / UBLKCP); its duration is set by the issue slots the loss "
-                                             "kernel leaves" if pipelined else
+                                             "bulk shared->global write-back (LDGSTS / UBLKCP), lane = (window, part) so one copy instruction "
+                                             "serves eight windows; alone it is HBM-latency bound (long-scoreboard stalls), next to the loss kernel "
+                                             "its duration is set by the issue slots that kernel leaves" if pipelined else
                                              "HBM latency on random 32-256 B segments (ncu: long-scoreboard stalls dominate)"),
                                  "relabelled_returns": "tail scan (16 B per tail row)" if args.tail_scan else
                                  "link records: chain of equal achieved goals + goal-agnostic return, O(hits) per window"},
         "tqc_loss_kernel": {"ms": float(k_ms[2]), "ms_alone": float(alone_ms[1]), "bytes_per_transition": BYTES_TQC,
                             "symbol": "fdql::tqc_loss_group_kernel<128, 7>",
-                            "limiter": "instruction issue (81% active alone, ALU pipe 60%) and shared-memory wavefronts (79% of peak): 128-value "
-                                       "sort network + 375 seven-level searches per transition; not HBM (ncu, profiles/)"},
+                            "limiter": "instruction issue (82% active alone, ALU pipe 63%) and the LSU data pipe (shared-memory wavefronts 81% of "
+                                       "peak): 128-value sort network + 375 seven-level searches per transition; not HBM (ncu, profiles/r2_*)"},
     }
     for kd in kernels.values():
         kd["note"] = ("ms = average launch duration inside the timed region, where the two kernels share every SM; ms_alone = the same "
