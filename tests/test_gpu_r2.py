@@ -492,30 +492,33 @@ def torch_equal(a, b):
     return torch.equal(a, b)
 
 
-def test_coresident_option_selects_the_lean_kernel_and_matches(fdql):
-    """FDQL_OPT_CORESIDENT through the fused-draw entry point: identical streams and identical batch to the default kernels."""
+@pytest.mark.parametrize("obs,act,G,T,n", [(64, 8, 16, 2, 8192), (12, 4, 8, 5, 1000), (8, 4, 4, 1, 33), (200, 8, 16, 2, 600), (20, 12, 24, 3, 4099)])
+def test_coresident_option_selects_the_lean_kernel_and_matches(fdql, obs, act, G, T, n):
+    """FDQL_OPT_CORESIDENT through the fused-draw entry point: identical streams and identical batch to the default kernels.  The shapes
+    cover keys narrower than one copy round (3, 1 and 2 float4 per row against 4 parts per window), several rounds with a partial last
+    one (5 and 6 float4), partial chunks and stages, and a key wider than the lean plan serves (50 float4: the request falls back to the
+    tile kernel and must still match)."""
     import ctypes as C
     import torch
     from fastdeepqlearning_b200 import Replay, _lib as L
     from test_gpu_replay import _synthetic
-    rng = np.random.default_rng(77)
-    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 400, 0, 16, obs=64, act=8, fixed_len=64)
+    rng = np.random.default_rng(77 + obs)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 400, 0, G, obs=obs, act=act, fixed_len=64)
     N = int(lengths.sum())
-    ring = Replay.ReplayMemory(N + 1, 4096, 2)
+    ring = Replay.ReplayMemory(N + 1, 4096, T)
     ring.set_reward_op(fdql.RewardOp.bitflip(), 0.99)
     ring.add_rows(cols, episode_lengths=lengths, with_returns=True)
-    n, T = 8192, 2
     lib = fdql.lib()
     res = []
     for opt in (0, L.OPT_CORESIDENT):
         out = {k: torch.full((T, n, w), -7.0, device="cuda") for k, w in zip(ring._keys, ring._widths)}
-        aux = [torch.empty(T, n, device="cuda"), torch.empty(T - 1, n, device="cuda"), torch.empty(T - 1, n, device="cuda")]
+        aux = [torch.empty(T, n, device="cuda"), torch.empty(max(T - 1, 1), n, device="cuda"), torch.empty(max(T - 1, 1), n, device="cuda")]
         st, fl, go = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda"),
                       torch.empty(n, dtype=torch.int64, device="cuda"))
         params, n_params = ring.reward_op.c_params()
         p = lambda t: C.c_void_p(t.data_ptr())
         L.check(lib.fdql_sample_gather_draw(ring._h, n, T, L.GOAL_FUTURE, 0.8, 5, 3, None, p(st), p(fl), p(go), ring.reward_op.op, params,
-                                            n_params, 0.99, L.OPT_EMIT_LEARNER_AUX | L.OPT_EXACT_EPISODE_STEP | opt, 4096,
+                                            n_params, 0.99, (L.OPT_EMIT_LEARNER_AUX if T > 1 else 0) | L.OPT_EXACT_EPISODE_STEP | opt, 4096,
                                             L.ptr_array([out[k].data_ptr() for k in ring._keys]), *[p(t) for t in aux],
                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()
@@ -523,9 +526,13 @@ def test_coresident_option_selects_the_lean_kernel_and_matches(fdql):
     (o0, a0, s0, f0, g0), (o1, a1, s1, f1, g1) = res
     assert torch.equal(s0, s1) and torch.equal(f0, f1) and torch.equal(g0, g1) and float(f0.float().mean()) > 0.7
     for k in o0:
-        assert torch.equal(o0[k], o1[k]), k
-    for x, y in zip(a0, a1):
-        assert torch.equal(x, y)
+        if k == "mc_return":  # small batches take the warp-per-window kernel by default, whose relabelled returns come from the tail
+            np.testing.assert_allclose(npy(o0[k]), npy(o1[k]), rtol=1e-5, atol=1e-6, err_msg=k)  # scan, not from the link records
+        else:
+            assert torch.equal(o0[k], o1[k]), k
+    if T > 1:
+        for x, y in zip(a0, a1):
+            assert torch.equal(x, y)
 
 
 # ------------------------------------------------------------------------------------------------ SquashRewards on the device
