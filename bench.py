@@ -658,7 +658,10 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: kernels[k].get("ms_alone", kernels[k]["ms"]))
     total_bytes = sum(kd["bytes_per_transition"] for kd in kernels.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "frac_alone": kernels[dom].get("frac_alone"), "traffic": None, "peak_source": peak_src,
+                "note": ("launch_ms / achieved / frac: this kernel's average duration inside the timed region, where it shares every SM with "
+                         "the co-resident gather of the next pass (so they are lower than the kernel's own figures); frac_alone: the same "
+                         "launch with the GPU to itself; whole_step: both kernels' bytes over the pass time") if pipelined else None,
                 "algorithmic_bytes_per_launch": kernels[dom]["bytes_per_transition"] * M, "launch_ms": kernels[dom]["ms"],
                 "survey_bytes_per_transition": {"sample_gather_kernel": BYTES_GATHER + BYTES_RELABEL_SURVEY, "tqc_loss_kernel": BYTES_TQC},
                 "kernels": kernels,

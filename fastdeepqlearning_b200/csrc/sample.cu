@@ -1378,8 +1378,13 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
               if (part_u < vecs) cp_async16(d, p);
               if (vecs > (uint32_t)kParts) {  // (uniform)
 #pragma unroll
-                for (int j = 1; j < kMaxJ; ++j)
+                for (int j = 1; j < (kMaxJ < 4 ? kMaxJ : 4); ++j)
                   if ((uint32_t)(j * kParts) + part_u < vecs) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
+                if (vecs > (uint32_t)(4 * kParts)) {  // (uniform) a predicated-off copy still costs its issue slots: skip in blocks of four
+#pragma unroll
+                  for (int j = 4; j < kMaxJ; ++j)
+                    if ((uint32_t)(j * kParts) + part_u < vecs) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
+                }
               }
             }
           }
