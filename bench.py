@@ -77,6 +77,7 @@ def parse():
                          "the reference's value (her.py:72-83), bit for bit")
     ap.add_argument("--serial", action="store_true", help="gather and loss back to back on one stream instead of pipelined on two")
     ap.add_argument("--buffers", type=int, default=3, help="batch buffers of the pipelined schedule (gathers run up to buffers-1 passes ahead)")
+    ap.add_argument("--fused", action="store_true", help="one warp-specialised launch per pass (fdql_fused_pass: loss of pass k + gather of pass k+1)")
     ap.add_argument("--no-step-graph", action="store_true",
                     help="pipelined schedule launched from Python every step instead of one captured CUDA graph per step")
     ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
@@ -322,6 +323,36 @@ def run_ours(args):
         cur_stream.wait_event(side_join(side))
         last_buf[0] = (n_pass - 1) % NB
 
+    def run_fused(n_pass, evs=None, every=16):
+        """one stream, one launch per pass: fdql_fused_pass = loss role on pass k's batch + gather role filling the other buffer with
+        pass k+1's batch.  The first launch is a gather alone, the last one a loss alone: n_pass gathers and n_pass losses per call."""
+        cur_stream = torch.cuda.current_stream(device)
+        spx = C.c_void_p(cur_stream.cuda_stream)
+
+        def half_g(b):
+            return (h, n, T, L.GOAL_FUTURE, P_RELABEL, 7 + rank, (1 << 40) if use_ctr_dev[0] else counter[0],
+                    p(ctr_dev) if use_ctr_dev[0] else None, p(b["starts"]), p(b["flags"]), p(b["goals"]), ring.reward_op.op, params, n_params,
+                    GAMMA, opts, B, b["outp"], p(b["mask"]), p(b["contig"]), p(b["weight"]))
+
+        def half_t(b, m):
+            return (m, CQ, N_DROP, p(z), p(q), p(lp), p(b["out"]["reward"][1:]), p(b["mask"][1:]), p(b["out"]["mc_return"][1:]),
+                    p(b["weight"]), ALPHA, GAMMA, p(loss), p(grad), p(stats), spx)
+        for k in range(n_pass + 1):
+            gb, tb = bufs[k % 2], bufs[(k + 1) % 2]
+            g_half = half_g(gb)
+            if k == n_pass:  # no gather: n_windows = 0
+                g_half = (h, 0) + g_half[2:]
+            e = evs[k // every] if evs is not None and k % every == every // 2 and k // every < len(evs) else None
+            if e:
+                e[0].record(cur_stream)
+                e[2].record(cur_stream)
+            L.check(lib.fdql_fused_pass(*g_half, *half_t(tb, M if k > 0 else 0)))
+            if e:
+                e[1].record(cur_stream)
+                e[3].record(cur_stream)
+            counter[0] += 1
+        last_buf[0] = (n_pass - 1) % 2
+
     def side_join(st):
         e = torch.cuda.Event()
         e.record(st)
@@ -338,7 +369,9 @@ def run_ours(args):
 
     if pipelined:
         lib.fdql_set_coresident(1)  # the loss kernel leaves room on every SM for the co-resident gather blocks
-    run = run_pipelined if pipelined else run_serial
+    run = run_fused if args.fused else run_pipelined if pipelined else run_serial
+    if args.fused:
+        lib.fdql_set_coresident(0)
     for _ in range(max(args.warmup, 3)):
         run(P)
     torch.cuda.synchronize(device)
@@ -350,12 +383,12 @@ def run_ours(args):
         # counter); the timed region replays it K times.  Eight passes of the step carry external timing events around their two
         # kernels (event-record nodes: they take real timestamps at every replay).
         use_ctr_dev[0] = True
-        run_pipelined(2)  # the counter-from-device variant of the launch, once outside the capture
+        run(2)  # the counter-from-device variant of the launch, once outside the capture
         torch.cuda.synchronize(device)
         gev = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(4)] for _ in range(n_ev)]
         cg_step = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cg_step):
-            run_pipelined(P, gev, every=max(P // n_ev, 1))
+            run(P, gev, every=max(P // n_ev, 1))
         for _ in range(2):
             cg_step.replay()
         torch.cuda.synchronize(device)
@@ -377,7 +410,7 @@ def run_ours(args):
                 torch.cuda.current_stream(device).synchronize()
                 g_acc = np.concatenate([g_acc, [[float("nan"), e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])] for e in gev]])
         elif pipelined:
-            run_pipelined(P, evs[i * n_ev:(i + 1) * n_ev], every=max(P // n_ev, 1))
+            run(P, evs[i * n_ev:(i + 1) * n_ev], every=max(P // n_ev, 1))
         else:
             run_serial(P, [[a, b_, c] for a, b_, c, _ in evs[i * n_ev:(i + 1) * n_ev]])
     e1.record(stream)

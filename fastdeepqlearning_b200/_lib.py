@@ -66,6 +66,8 @@ _SIGNATURES = {
                                      _p, _p, _p, _p]),
     "fdql_sample_gather_draw": (C.c_int, [_p, _i64, _i32, _i32, _f32, _u64, _u64, _p, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _u32, _i32,
                                           _pp, _p, _p, _p, _p]),
+    "fdql_fused_pass": (C.c_int, [_p, _i64, _i32, _i32, _f32, _u64, _u64, _p, _p, _p, _p, _i32, C.POINTER(_f32), _i32, _f64, _u32, _i32,
+                                  _pp, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p]),
     "fdql_debug_force_generic_gather": (C.c_int, [C.c_int]),
     "fdql_set_coresident": (C.c_int, [C.c_int]),
     "fdql_debug_tqc_warp_kernel": (C.c_int, [C.c_int]),

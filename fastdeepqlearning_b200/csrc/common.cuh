@@ -193,6 +193,10 @@ struct DrawSpec {
   int64_t* starts_out;
   uint8_t* flags_out;
   int64_t* goal_out;
+  // fused pass (fdql_fused_pass): when set and the shape allows it, the gather is launched as the gather role of the fused pass
+  // kernel together with this loss (a TqcArgs of tqc_group.cuh) and *fused is set to 1; otherwise the gather launches alone
+  const void* fuse_tqc = nullptr;
+  int* fused = nullptr;
 };
 // returns FDQL_OK, an error, or (with draw != nullptr) 1 when this shape is not served by the fused kernel (nothing launched)
 int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end, int32_t T, int64_t len, const int64_t* starts,

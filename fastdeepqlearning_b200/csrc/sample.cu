@@ -11,6 +11,7 @@
 // achieved_goal slab, 32 rows per pass, and combines per-pass partial returns with a warp-shuffle scan.
 #include "common.cuh"
 #include "goal_eval.cuh"
+#include "tqc_group.cuh"
 
 namespace fdql {
 
@@ -92,17 +93,24 @@ __device__ __forceinline__ int64_t device_draw_range(const unsigned long long* c
 }
 // counter_dev (optional): {draw counter, block ticket} in device memory, so that a captured CUDA graph draws fresh streams at
 // every replay.  Every block reads the counter before it takes its ticket; the block with the last ticket advances it.
-__device__ __forceinline__ uint64_t device_draw_counter(unsigned long long* counter_dev, uint64_t counter) {
+// (role form: `tid` = thread index within the role, `n_blk` = blocks that take a ticket, `bar_id` / `n_threads` = the role's barrier,
+// see role_barrier in tqc_group.cuh; the defaults are "the whole block of an ordinary launch")
+__device__ __forceinline__ uint64_t device_draw_counter(unsigned long long* counter_dev, uint64_t counter, int tid = -1, int n_blk = 0,
+                                                        int bar_id = 0, int n_threads = 0) {
   __shared__ unsigned long long sh_ctr;
   if (counter_dev == nullptr) return counter;
-  if (threadIdx.x == 0) sh_ctr = *reinterpret_cast<volatile unsigned long long*>(counter_dev);
-  __syncthreads();
+  if (tid < 0) {
+    tid = (int)threadIdx.x;
+    n_blk = (int)gridDim.x;
+  }
+  if (tid == 0) sh_ctr = *reinterpret_cast<volatile unsigned long long*>(counter_dev);
+  role_barrier(bar_id, n_threads);
   counter += sh_ctr;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  role_barrier(bar_id, n_threads);
+  if (tid == 0) {
     __threadfence();
     const unsigned long long ticket = atomicAdd(counter_dev + 1, 1ull);
-    if (ticket == (unsigned long long)gridDim.x - 1) {
+    if (ticket == (unsigned long long)n_blk - 1) {
       counter_dev[1] = 0ull;
       counter_dev[0] = sh_ctr + 1ull;
       __threadfence();
@@ -1289,13 +1297,14 @@ __device__ __forceinline__ bool elect_one() {  // one lane of the converged warp
 #ifndef FDQL_LEAN_MAXVECS
 #define FDQL_LEAN_MAXVECS 32
 #endif
+// The kernel body as a device function (stand-alone kernel below; gather role of the fused pass kernel).  `wib`: this warp's index
+// among the role's `n_warps` warps of the block (taken through a shuffle by the caller: warp-uniform for the compiler, so the stage
+// bookkeeping and the bulk copies use uniform registers); `blk` / `n_blk`: the block's rank among the blocks that share the windows;
+// `bar_id`: 0 = the role is the whole block, otherwise its named barrier.
 template <bool HASH, bool DRAW, int kLeanStageWindows>
-__global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(const __grid_constant__ GatherArgs g) {
-  extern __shared__ __align__(128) unsigned char lean_smem[];
+__device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned char* lean_smem, const int wib, const int n_warps,
+                                                 const int blk, const int n_blk, const int bar_id) {
   const int lane = lane_id();
-  // warp index through a shuffle: the compiler then knows that it (and the stage bookkeeping derived from it) is warp-uniform, and
-  // the bulk copies below take their operands from uniform registers without a per-lane uniformisation loop
-  const int wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const int T = g.T;
   const int len32 = (int)g.len;
 
@@ -1309,10 +1318,10 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
   const uint32_t stage_bytes = g.lean_row_bytes * kLeanStageWindows;
   const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * 2u * stage_bytes;  // two stages per warp
 
-  const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter) : 0;
+  const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter, wib * 32 + lane, n_blk, bar_id, n_warps * 32) : 0;
   const int64_t n_windows = g.b_end - g.b_begin;
   const int64_t n_chunks = (n_windows + 31) / 32;
-  const int64_t warps_total = (int64_t)gridDim.x * kLeanWarps;
+  const int64_t warps_total = (int64_t)n_blk * n_warps;
   uint32_t it = 0;            // stages issued by this warp
   // the stage whose copies are in flight and whose write-back is still to be issued
   int p_t = 0, p_n = 0;
@@ -1334,7 +1343,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
       bulk_commit_group();
     }
   };
-  for (int64_t chunk = (int64_t)blockIdx.x * kLeanWarps + wib; chunk < n_chunks; chunk += warps_total) {
+  for (int64_t chunk = (int64_t)blk * n_warps + wib; chunk < n_chunks; chunk += warps_total) {
     const int64_t cb0 = g.b_begin + chunk * 32;
     const int n_here = (int)min((int64_t)32, g.b_end - cb0);
     int s = 0, grow = 0, tail_last = -1;
@@ -1405,6 +1414,35 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
     finish_stage((it - 1) & 1u, p_t, p_b0, p_n);
   }
   if (elect_one()) bulk_wait_group_read<0>();
+}
+
+template <bool HASH, bool DRAW, int kLeanStageWindows>
+__global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(const __grid_constant__ GatherArgs g) {
+  extern __shared__ __align__(128) unsigned char lean_smem_dyn[];
+  const int wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  gather_lean_body<HASH, DRAW, kLeanStageWindows>(g, lean_smem_dyn, wib, kLeanWarps, (int)blockIdx.x, (int)gridDim.x, 0);
+}
+
+// =================================================================================================
+// Fused pass kernel: ONE launch per pass does what bench.py's pipelined schedule does with two -- the loss role (16 warps:
+// tqc_group_body on batch k, whose critic outputs exist) and the gather role (8 warps: gather_lean_body samples, relabels and gathers
+// batch k+1 into the other buffer) share every SM from the first to the last cycle of the launch.  One block per SM; the roles never
+// meet (separate shared memory, separate named barriers, separate work counters).  This is the reference's prefetch thread
+// (torch_dataloader.py:22-39) as warp specialisation; consecutive passes are ordered by the stream, so no events are needed.
+// =================================================================================================
+constexpr int kFusedLossWarps = 16, kFusedGatherWarps = 8;
+
+template <int FLAGS, bool HASH, bool DRAW>
+__global__ void __launch_bounds__((kFusedLossWarps + kFusedGatherWarps) * 32, 1)
+fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ TqcArgs a) {
+  extern __shared__ __align__(128) unsigned char fused_smem[];
+  const int w = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  constexpr uint32_t kLossBytes = kFusedLossWarps * GrpCfg<128>::kWarpFloatsAlias * sizeof(float);
+  if (w < kFusedLossWarps) {
+    tqc_group_body<128, FLAGS>(a, reinterpret_cast<float*>(fused_smem), w, kFusedLossWarps, (int)blockIdx.x, (int)gridDim.x, 1);
+  } else {
+    gather_lean_body<HASH, DRAW, 8>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x, (int)gridDim.x, 2);
+  }
 }
 
 int g_tile_override = 0;
@@ -1506,6 +1544,56 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     g.lean_ag_stride = 4u * (uint32_t)a->dev.wide[a->dev.wide_ag].stride;
   }
   const bool coresident = (opts & FDQL_OPT_CORESIDENT) != 0;
+  if (lean_ok && draw != nullptr && draw->fuse_tqc != nullptr) {
+    // fused pass: this gather as the gather role, the given loss as the loss role of ONE launch (one block per SM).  Served: the
+    // 128-atom-table group kernel with aliased partial sums and full atom slots (97..128 predicted atoms, e.g. 5 x 25) on batches
+    // large enough for its one-block-per-SM form; anything else falls through to the gather alone and the caller launches the loss.
+    const TqcArgs& ta = *static_cast<const TqcArgs*>(draw->fuse_tqc);
+    int need = ta.n_atoms > ta.n_z ? ta.n_atoms : ta.n_z;
+    if (ta.n_z - ta.n_drop + 1 > need) need = ta.n_z - ta.n_drop + 1;
+    const int64_t n_groups = (ta.M + GrpCfg<128>::G - 1) / GrpCfg<128>::G;
+    if (need > 64 && need <= 128 && ta.n_atoms > 96 && ta.n_atoms >= 3 * GrpCfg<128>::kRedPitch &&
+        n_groups > (int64_t)2 * kFusedLossWarps * a->num_sms) {
+      g.use_link = link_ok;
+      g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
+      g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
+      g.dbg = 0;
+      TqcArgs t = ta;
+      t.grp_red_alias = 1;
+      const size_t smem = (size_t)kFusedLossWarps * GrpCfg<128>::kWarpFloatsAlias * sizeof(float) +
+                          (size_t)kFusedGatherWarps * 2 * 8 * 16 * wide_vecs;
+      const int flags_ = (t.mc_return ? kGrpLb : 0) | (t.stats ? kGrpStats : 0) | kGrpFull;
+      if (smem <= 227 * 1024) {
+#define FDQL_LAUNCH_FUSED(FLAGSV, HASHV)                                                                                    \
+  do {                                                                                                                      \
+    auto kern = fused_pass_kernel<FLAGSV, HASHV, true>;                                                                     \
+    static size_t smem_set = 0;                                                                                             \
+    if (smem_set != smem) {                                                                                                 \
+      FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+      FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+      smem_set = smem;                                                                                                      \
+    }                                                                                                                       \
+    kern<<<(unsigned)a->num_sms, (kFusedLossWarps + kFusedGatherWarps) * 32, smem, st>>>(g, t);                             \
+  } while (0)
+#define FDQL_FUSED_FLAGS(HASHV)                               \
+  do {                                                        \
+    switch (flags_) {                                         \
+      case 4: FDQL_LAUNCH_FUSED(4, HASHV); break;             \
+      case 5: FDQL_LAUNCH_FUSED(5, HASHV); break;             \
+      case 6: FDQL_LAUNCH_FUSED(6, HASHV); break;             \
+      default: FDQL_LAUNCH_FUSED(7, HASHV); break;            \
+    }                                                         \
+  } while (0)
+        if (hash_ok) FDQL_FUSED_FLAGS(true);
+        else FDQL_FUSED_FLAGS(false);
+#undef FDQL_FUSED_FLAGS
+#undef FDQL_LAUNCH_FUSED
+        FDQL_CUDA(cudaGetLastError());
+        *draw->fused = 1;
+        return FDQL_OK;
+      }
+    }
+  }
   if (lean_ok && (coresident || (g_force_generic_gather & 32))) {
     g.use_link = link_ok;
     g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
@@ -1694,6 +1782,51 @@ int fdql_sample_streams(const fdql_arena* a, int64_t n, int32_t T, int32_t goal_
                                                                                        starts, flags, goal_rows);
   FDQL_CUDA(cudaGetLastError());
   return FDQL_OK;
+}
+
+int fdql_fused_pass(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
+                    uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows, int32_t reward_op,
+                    const float* reward_params_host, int32_t n_params, double gamma, uint32_t opts, int32_t batch_for_weight,
+                    float* const* out, float* aux_mask, float* aux_contig, float* aux_weight, int64_t M, int32_t n_atoms, int32_t n_drop,
+                    const float* next_z, const float* q_pred, const float* next_log_pi, const float* reward, const float* mask,
+                    const float* mc_return, const float* grad_scale, float alpha, float loss_gamma, float* loss, float* grad_q,
+                    double* stats, void* stream) {
+  FDQL_REQUIRE(a != nullptr && n_windows >= 0 && M >= 0, "bad sizes");
+  FDQL_REQUIRE(n_windows == 0 || (T >= 1 && starts != nullptr && out != nullptr), "null gather argument");
+  FDQL_REQUIRE((flags == nullptr) == (goal_rows == nullptr), "flags and goal_rows come together");
+  FDQL_REQUIRE(n_windows == 0 || (goal_mode >= FDQL_GOAL_FINAL && goal_mode <= FDQL_GOAL_FUTURE), "bad goal mode");
+  if (M > 0) {
+    FDQL_REQUIRE(n_atoms >= 2 && n_atoms <= 256, "n_atoms must be in [2, 256], got %d", n_atoms);
+    FDQL_REQUIRE(n_drop >= 1 && n_drop < n_atoms, "n_drop must be in [1, n_atoms); got %d", n_drop);  // quirk Q8, as fdql_tqc_loss
+    FDQL_REQUIRE(next_z && q_pred && reward && mask && loss && grad_q, "null loss argument");
+  }
+  if (n_windows > 0 && (a->len < 1 || a->len < 2 * (int64_t)T)) {  // replay_memory.py:57-58
+    set_error("OversampleError: ring holds %lld rows, asked for %lld windows of %d", (long long)a->len, (long long)n_windows, T);
+    return FDQL_EOVERSAMPLE;
+  }
+  if (n_windows > 0 && (opts & FDQL_OPT_EMIT_LEARNER_AUX))
+    FDQL_REQUIRE(a->dev.col_task_done >= 0 && a->dev.col_ep_step >= 0, "learner aux needs task_done and episode_step keys");
+  TqcArgs t{M, n_atoms, n_atoms, n_drop, next_z, q_pred, next_log_pi, reward, mask, mc_return, grad_scale, alpha, loss_gamma, loss, grad_q,
+            nullptr, stats, nullptr, 0};
+  int fused = 0;
+  if (n_windows > 0) {
+    DrawSpec d{a->len - T, goal_mode, relabel_prob, seed, counter, reinterpret_cast<unsigned long long*>(counter_dev), starts, flags, goal_rows};
+    if (M > 0) {
+      d.fuse_tqc = &t;
+      d.fused = &fused;
+    }
+    int rc = launch_gather(a, n_windows, 0, n_windows, T, a->len, nullptr, nullptr, nullptr, reward_op, reward_params_host, n_params, gamma,
+                           opts | FDQL_OPT_CORESIDENT, batch_for_weight, out, aux_mask, aux_contig, aux_weight, (cudaStream_t)stream, &d);
+    if (rc == 1) {  // shapes the drawing kernels do not serve: streams + gather as two launches
+      rc = fdql_sample_streams(a, n_windows, T, goal_mode, relabel_prob, seed, counter, counter_dev, starts, flags, goal_rows, stream);
+      if (rc) return rc;
+      rc = launch_gather(a, n_windows, 0, n_windows, T, a->len, starts, flags, goal_rows, reward_op, reward_params_host, n_params, gamma, opts,
+                         batch_for_weight, out, aux_mask, aux_contig, aux_weight, (cudaStream_t)stream);
+    }
+    if (rc) return rc;
+  }
+  if (fused || M == 0) return FDQL_OK;
+  return launch_tqc(t, (cudaStream_t)stream);  // not fused: the loss as its own launch, after the gather on the same stream
 }
 
 int fdql_sample_gather_draw(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,

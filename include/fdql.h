@@ -183,6 +183,22 @@ int fdql_sample_gather_draw(const fdql_arena* a, int64_t n_windows, int32_t T, i
                             int32_t batch_for_weight, float* const* out, float* aux_mask, float* aux_contig, float* aux_weight,
                             void* stream);
 
+/* One pass of the learner loop as ONE launch: fdql_sample_gather_draw of batch k+1 (arguments up to aux_weight, same meaning; the
+ * reference does this in TorchDataLoader's prefetch thread one batch ahead, torch_dataloader.py:22-39) and fdql_tqc_loss of batch k
+ * (arguments from M on, same meaning; distributional_soft_actor_critic.py:50-58,70-103) in a warp-specialised persistent kernel, one
+ * block per SM: 16 loss warps + 8 gather warps with separate shared memory, named barriers and work counters.  The two halves must not
+ * alias (the loss reads batch k's reward / mask / mc_return / weight while the gather writes batch k+1 into other buffers).
+ * M == 0: the gather alone; n_windows == 0: the loss alone.  Shapes the fused kernel does not serve (loss tables other than 97..128
+ * atoms, small batches, keys wider than the lean copy plan, other reward functors) run as the separate launches, gather then loss on
+ * `stream`, with identical results. */
+int fdql_fused_pass(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
+                    uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows, int32_t reward_op,
+                    const float* reward_params_host, int32_t n_params, double gamma, uint32_t opts, int32_t batch_for_weight,
+                    float* const* out, float* aux_mask, float* aux_contig, float* aux_weight, int64_t M, int32_t n_atoms, int32_t n_drop,
+                    const float* next_z, const float* q_pred, const float* next_log_pi, const float* reward, const float* mask,
+                    const float* mc_return, const float* grad_scale, float alpha, float loss_gamma, float* loss, float* grad_q,
+                    double* stats, void* stream);
+
 /* ReplayMemory.__getitem__ / sample (replay_memory.py:48-52,68-70): out[k] is [n, width_k]. */
 int fdql_gather_rows(const fdql_arena* a, int64_t n, const int64_t* idx, float* const* out, void* stream);
 

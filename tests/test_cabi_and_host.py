@@ -123,11 +123,11 @@ def test_hindsight_goal_pick_indexing():
 
 
 def test_sort16_network_sorts_every_01_input():
-    """The in-lane sorter of the TQC group kernel is a 60-comparator network written as a macro table in csrc/tqc.cu; by the
+    """The in-lane sorter of the TQC group kernel is a 60-comparator network written as a macro table in csrc/tqc_group.cuh; by the
     0-1 principle it sorts every input iff it sorts all 2^16 binary ones."""
     import os
     import re
-    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastdeepqlearning_b200", "csrc", "tqc.cu")).read()
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastdeepqlearning_b200", "csrc", "tqc_group.cuh")).read()
     body = src[src.index("#define FDQL_SORT16_NETWORK(CE)"):src.index("__device__ __forceinline__ void grp_sort16")]
     pairs = [(int(a), int(b)) for a, b in re.findall(r"CE\((\d+), (\d+)\)", body)]
     assert len(pairs) == 60 and all(0 <= a < b < 16 for a, b in pairs)
@@ -139,13 +139,13 @@ def test_sort16_network_sorts_every_01_input():
 
 
 def test_group_kernel_row_split_is_a_conflict_free_bijection():
-    """Phase A of the TQC group kernel (csrc/tqc.cu, NT = 128) lets lane (grp, sl) read element
+    """Phase A of the TQC group kernel (csrc/tqc_group.cuh, NT = 128) lets lane (grp, sl) read element
     j = 32 (s / 4) + ((8 grp - grp nz + sl + 8 (s % 4)) mod 32) of its staged row at step s.  For every row length nz this must
     (a) visit each of the 128 slots of a row exactly once and (b) put the 32 lanes of a step on 32 different banks
     (row grp starts at float offset grp * nz); the Y / {-P1, P2} table stores of the same lanes (float offset
     grp * 129 + 4 sl + 32 (s % 4) + s / 4) must be conflict free too, the 8-byte ones per half-warp of lanes sl * 4 + grp."""
     import os
-    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastdeepqlearning_b200", "csrc", "tqc.cu")).read()
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fastdeepqlearning_b200", "csrc", "tqc_group.cuh")).read()
     assert "const int r0 = (8 * grp - grp * nz + sl) & 31;" in src and "32 * (s / 4) + ((r0 + 8 * (s % 4)) & 31)" in src
     assert "const int grp = lane % G, sl = lane / G;" in src
     grp, sl = np.meshgrid(np.arange(4), np.arange(8), indexing="ij")

@@ -535,6 +535,91 @@ def test_coresident_option_selects_the_lean_kernel_and_matches(fdql, obs, act, G
             assert torch.equal(x, y)
 
 
+# ------------------------------------------------------------------------------------------------ one launch per pass
+@pytest.mark.parametrize("n,n_atoms,n_drop,with_lb,with_stats,repeat", [
+    (24576, 125, 10, True, True, 2),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
+    (20000, 125, 10, False, False, 1),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
+    (24576, 100, 8, True, False, 1),    # fused kernel, 100 atoms (4 x 25)
+    (3000, 125, 10, True, True, 1),     # batch too small for the one-block-per-SM form: the two separate launches
+    (24576, 50, 4, True, True, 1),      # 64-entry loss tables: separate launches
+])
+def test_fused_pass_equals_the_two_launches(fdql, n, n_atoms, n_drop, with_lb, with_stats, repeat):
+    """fdql_fused_pass (loss of batch k + gather of batch k+1 in one warp-specialised launch) against fdql_sample_gather_draw and
+    fdql_tqc_loss as separate launches on the same arguments: bit-identical batch, loss, gradient; summaries to fp64 rounding.  The
+    loss half reads the PREVIOUS gather's reward / mask / mc_return / weight (other buffers), as the learner loop does."""
+    import ctypes as C
+    import torch
+    from fastdeepqlearning_b200 import Replay, _lib as L
+    from test_gpu_replay import _synthetic
+    T, G = 2, 16
+    rng = np.random.default_rng(5 + n)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 600, 0, G, obs=64, act=8, fixed_len=64)
+    N = int(lengths.sum())
+    ring = Replay.ReplayMemory(N + 1, 4096, T)
+    ring.set_reward_op(fdql.RewardOp.bitflip(), 0.99)
+    ring.add_rows(cols, episode_lengths=lengths, with_returns=True)
+    lib = fdql.lib()
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    params, n_params = ring.reward_op.c_params()
+    opts = L.OPT_EMIT_LEARNER_AUX | L.OPT_EXACT_EPISODE_STEP
+    M = (T - 1) * n
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    z = torch.randn(M, n_atoms, device="cuda", generator=gen) * 3
+    q = torch.randn(M, n_atoms, device="cuda", generator=gen) * 3
+    lp = torch.randn(M, device="cuda", generator=gen)
+
+    def buf():
+        out = {k: torch.full((T, n, w), -7.0, device="cuda") for k, w in zip(ring._keys, ring._widths)}
+        return {"out": out, "outp": L.ptr_array([out[k].data_ptr() for k in ring._keys]), "mask": torch.empty(T, n, device="cuda"),
+                "contig": torch.empty(T - 1, n, device="cuda"), "weight": torch.empty(T - 1, n, device="cuda"),
+                "st": torch.empty(n, dtype=torch.int64, device="cuda"), "fl": torch.empty(n, dtype=torch.uint8, device="cuda"),
+                "go": torch.empty(n, dtype=torch.int64, device="cuda")}
+
+    def g_half(b, ctr, n_w=n):
+        return (ring._h, n_w, T, L.GOAL_FUTURE, 0.8, 11, ctr, None, p(b["st"]), p(b["fl"]), p(b["go"]), ring.reward_op.op, params, n_params,
+                0.99, opts, 4096, b["outp"], p(b["mask"]), p(b["contig"]), p(b["weight"]))
+
+    def t_half(b, m, loss, grad, stats):
+        return (m, n_atoms, n_drop, p(z), p(q), p(lp), p(b["out"]["reward"][1:]), p(b["mask"][1:]),
+                p(b["out"]["mc_return"][1:]) if with_lb else None, p(b["weight"]), 0.2, 0.99, p(loss), p(grad),
+                p(stats) if with_stats else None)
+    # --- separate launches: gather(0), then per pass loss(k) and gather(k+1)
+    ref = [buf() for _ in range(repeat + 1)]
+    ref_loss = []
+    for k in range(repeat + 1):
+        a = g_half(ref[k], k)  # the fused entry point always asks for the co-resident gather: same kernel on both sides
+        L.check(lib.fdql_sample_gather_draw(*a[:15], opts | L.OPT_CORESIDENT, *a[16:], sp))
+    for k in range(repeat):
+        loss, grad, stats = torch.empty(M, device="cuda"), torch.empty(M, n_atoms, device="cuda"), torch.zeros(4, dtype=torch.float64, device="cuda")
+        a = t_half(ref[k], M, loss, grad, stats)
+        L.check(lib.fdql_tqc_loss(*a[:14], None, a[14], sp))
+        ref_loss.append((loss, grad, stats))
+    # --- fused: gather alone (M = 0), then `repeat` fused passes
+    got = [buf() for _ in range(repeat + 1)]
+    dummy = torch.empty(1, device="cuda")
+    L.check(lib.fdql_fused_pass(*g_half(got[0], 0), *t_half(got[0], 0, dummy, dummy, None), sp))
+    for k in range(repeat):
+        loss, grad, stats = torch.empty(M, device="cuda"), torch.empty(M, n_atoms, device="cuda"), torch.zeros(4, dtype=torch.float64, device="cuda")
+        L.check(lib.fdql_fused_pass(*g_half(got[k + 1], k + 1), *t_half(got[k], M, loss, grad, stats), sp))
+        torch.cuda.synchronize()
+        rl, rg, rs = ref_loss[k]
+        assert torch.equal(loss, rl) and torch.equal(grad, rg), k
+        if with_stats:
+            np.testing.assert_allclose(npy(stats), npy(rs), rtol=1e-12)
+    # the loss alone through the same entry point (n_windows = 0)
+    loss, grad, stats = torch.empty(M, device="cuda"), torch.empty(M, n_atoms, device="cuda"), torch.zeros(4, dtype=torch.float64, device="cuda")
+    L.check(lib.fdql_fused_pass(*g_half(got[0], 0, 0), *t_half(got[0], M, loss, grad, stats), sp))
+    torch.cuda.synchronize()
+    assert torch.equal(loss, ref_loss[0][0]) and torch.equal(grad, ref_loss[0][1])
+    for a, b in zip(ref, got):
+        assert torch.equal(a["st"], b["st"]) and torch.equal(a["fl"], b["fl"]) and torch.equal(a["go"], b["go"])
+        for k in a["out"]:
+            assert torch.equal(a["out"][k], b["out"][k]), k
+        for k in ("mask", "contig", "weight"):
+            assert torch.equal(a[k], b[k]), k
+
+
 # ------------------------------------------------------------------------------------------------ SquashRewards on the device
 @pytest.mark.parametrize("with_nstep", [True, False])
 def test_squash_rewards_in_the_append_kernel(fdql, with_nstep):
