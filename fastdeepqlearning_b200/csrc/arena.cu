@@ -459,6 +459,7 @@ int fdql_arena_create(int64_t capacity, int32_t n_keys, const int32_t* widths, c
   ok = ok && alloc(reinterpret_cast<float**>(&D.scan), (size_t)capacity * 4);
   ok = ok && alloc(reinterpret_cast<float**>(&D.link), (size_t)capacity * 4);
   ok = ok && alloc(&a->reward_params_dev, kMaxRewardParams + 4);
+  ok = ok && alloc(reinterpret_cast<float**>(&a->fused_ws), 4 * kFusedSlots + 2048);  // (+ 8 KB for probe builds)
   if (!ok) {
     set_error("cudaMalloc failed while allocating the arena (%zu bytes so far): %s", total,
               cudaGetErrorString(cudaGetLastError()));
@@ -480,6 +481,16 @@ int fdql_arena_destroy(fdql_arena* a) {
   if (a->dev.scan) cudaFree(a->dev.scan);
   if (a->dev.link) cudaFree(a->dev.link);
   if (a->reward_params_dev) cudaFree(a->reward_params_dev);
+#ifdef FDQL_FUSED_ROLE_CLOCK
+  if (a->fused_ws) {
+    unsigned long long h[5];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, reinterpret_cast<unsigned long long*>(a->fused_ws + 4 * kFusedSlots) + 3 * 256, sizeof(h), cudaMemcpyDeviceToHost);
+    if (h[2]) fprintf(stderr, "[role clock] %llu launches: gap between launches (last role end -> next block 0 start) avg %.2f us; block 0 loss role %.1f us, gather role %.1f us\n",
+                      h[2], (double)h[1] / h[2] / 1e3, (double)h[3] / (h[2] + 1) / 1e3, (double)h[4] / (h[2] + 1) / 1e3);
+  }
+#endif
+  if (a->fused_ws) cudaFree(a->fused_ws);
   if (a->stage_dev) cudaFree(a->stage_dev);
   if (a->step_dev) cudaFree(a->step_dev);
   if (a->step_sync_ready) {

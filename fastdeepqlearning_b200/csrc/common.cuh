@@ -79,6 +79,7 @@ struct SrcPtrs {
 };
 
 constexpr int kMaxRewardParams = 2 + 128;
+constexpr int kFusedSlots = 16;
 struct RewardSpec {
   int32_t op;
   int32_t n_params;
@@ -156,6 +157,7 @@ struct Arena {
   int64_t top, len, bytes;
   int32_t device;
   float* reward_params_dev;  // kMaxRewardParams floats
+  int* fused_ws;             // 4 * kFusedSlots zeroed ints: work counters of fdql_fused_pass launches (sample.cu)
   // staging for *_host entry points (allocated lazily, grown only when a larger call arrives)
   void* stage_dev;
   size_t stage_bytes;

@@ -13,6 +13,8 @@
 #include "goal_eval.cuh"
 #include "tqc_group.cuh"
 
+#include <atomic>
+
 namespace fdql {
 
 // ---- counter-based generator (Philox4x32-10) ----------------------------------------------------
@@ -184,6 +186,10 @@ struct GatherArgs {
   uint32_t lean_row_bytes;  // sum of 16 * vecs over the keys = bytes of one window row in a stage
   const char* lean_ag_base;
   uint32_t lean_ag_stride;
+#ifdef FDQL_FUSED_ROLE_CLOCK
+  unsigned long long* role_clock;
+#endif
+  int* lean_work_ctr;  // optional {next unclaimed chunk, blocks done}, zero at launch: chunks claimed across all blocks (see TqcArgs::work_ctr)
 };
 constexpr int kLeanMaxKeys = 4;
 
@@ -1343,7 +1349,16 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
       bulk_commit_group();
     }
   };
-  for (int64_t chunk = (int64_t)blk * n_warps + wib; chunk < n_chunks; chunk += warps_total) {
+  int* const wctr = g.lean_work_ctr;
+  int64_t chunk = (int64_t)blk * n_warps + wib;
+  if (wctr != nullptr) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(wctr, 1);
+    chunk = __shfl_sync(kFull, c, 0);
+  }
+  while (chunk < n_chunks) {
+    int c_next = 0;  // claimed now, looked at when this chunk is done: the atomic's round trip stays off the critical path
+    if (wctr != nullptr && lane == 0) c_next = atomicAdd(wctr, 1);
     const int64_t cb0 = g.b_begin + chunk * 32;
     const int n_here = (int)min((int64_t)32, g.b_end - cb0);
     int s = 0, grow = 0, tail_last = -1;
@@ -1408,12 +1423,24 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
         p_n = nw;
       }
     }
+    chunk = wctr != nullptr ? (int64_t)__shfl_sync(kFull, c_next, 0) : chunk + warps_total;
   }
   if (it > 0) {
     cp_async_wait_group<0>();
     finish_stage((it - 1) & 1u, p_t, p_b0, p_n);
   }
   if (elect_one()) bulk_wait_group_read<0>();
+  if (wctr != nullptr) {  // the last block to get here re-arms the counter for the next launch
+    role_barrier(bar_id, n_warps * 32);
+    if (wib == 0 && lane == 0) {
+      __threadfence();
+      if (atomicAdd(wctr + 1, 1) == n_blk - 1) {
+        wctr[0] = 0;
+        wctr[1] = 0;
+        __threadfence();
+      }
+    }
+  }
 }
 
 template <bool HASH, bool DRAW, int kLeanStageWindows>
@@ -1430,7 +1457,23 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
 // meet (separate shared memory, separate named barriers, separate work counters).  This is the reference's prefetch thread
 // (torch_dataloader.py:22-39) as warp specialisation; consecutive passes are ordered by the stream, so no events are needed.
 // =================================================================================================
-constexpr int kFusedLossWarps = 16, kFusedGatherWarps = 8;
+#ifndef FDQL_FUSED_LOSS_WARPS
+#define FDQL_FUSED_LOSS_WARPS 16
+#endif
+#ifndef FDQL_FUSED_GATHER_WARPS
+#define FDQL_FUSED_GATHER_WARPS 8
+#endif
+#ifndef FDQL_FUSED_STAGE_WINDOWS
+#define FDQL_FUSED_STAGE_WINDOWS 8
+#endif
+constexpr int kFusedLossWarps = FDQL_FUSED_LOSS_WARPS, kFusedGatherWarps = FDQL_FUSED_GATHER_WARPS, kFusedStageWindows = FDQL_FUSED_STAGE_WINDOWS;
+#ifdef FDQL_FUSED_ROLE_CLOCK
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 
 template <int FLAGS, bool HASH, bool DRAW>
 __global__ void __launch_bounds__((kFusedLossWarps + kFusedGatherWarps) * 32, 1)
@@ -1438,10 +1481,45 @@ fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ 
   extern __shared__ __align__(128) unsigned char fused_smem[];
   const int w = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   constexpr uint32_t kLossBytes = kFusedLossWarps * GrpCfg<128>::kWarpFloatsAlias * sizeof(float);
+#ifdef FDQL_FUSED_ROLE_CLOCK  // probe build: when does each role of each block end?  ({start, loss end, gather end} per block, ns)
+  unsigned long long* clk = g.role_clock + 3 * blockIdx.x;
+  unsigned long long* acc = g.role_clock + 3 * 256;  // {last end, gap sum, launches, loss sum, gather sum} accumulated by block 0
+  unsigned long long t_start = 0;
+  if (threadIdx.x == 0 || threadIdx.x == kFusedLossWarps * 32) t_start = globaltimer_ns();
+  if (threadIdx.x == 0) {
+    clk[0] = t_start;
+    if (blockIdx.x == 0) {
+      const unsigned long long le = *reinterpret_cast<volatile unsigned long long*>(acc);
+      if (le != 0 && t_start > le && t_start - le < 1000000ull) {
+        atomicAdd(acc + 1, t_start - le);
+        atomicAdd(acc + 2, 1ull);
+      }
+    }
+  }
+#endif
   if (w < kFusedLossWarps) {
     tqc_group_body<128, FLAGS>(a, reinterpret_cast<float*>(fused_smem), w, kFusedLossWarps, (int)blockIdx.x, (int)gridDim.x, 1);
+#ifdef FDQL_FUSED_ROLE_CLOCK
+    asm volatile("bar.sync 1, %0;" ::"r"(kFusedLossWarps * 32) : "memory");
+    if (threadIdx.x == 0) {
+      const unsigned long long te = globaltimer_ns();
+      clk[1] = te;
+      atomicMax(acc, te);
+      if (blockIdx.x == 0) atomicAdd(acc + 3, te - t_start);
+    }
+#endif
   } else {
-    gather_lean_body<HASH, DRAW, 8>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x, (int)gridDim.x, 2);
+    gather_lean_body<HASH, DRAW, kFusedStageWindows>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x,
+                                                     (int)gridDim.x, 2);
+#ifdef FDQL_FUSED_ROLE_CLOCK
+    asm volatile("bar.sync 2, %0;" ::"r"(kFusedGatherWarps * 32) : "memory");
+    if (threadIdx.x == kFusedLossWarps * 32) {
+      const unsigned long long te = globaltimer_ns();
+      clk[2] = te;
+      atomicMax(acc, te);
+      if (blockIdx.x == 0) atomicAdd(acc + 4, te - t_start);
+    }
+#endif
   }
 }
 
@@ -1560,8 +1638,19 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
       g.dbg = 0;
       TqcArgs t = ta;
       t.grp_red_alias = 1;
+      // work counters of this launch: one of kFusedSlots {loss next, loss done, gather next, gather done} quadruples of the arena, taken
+      // in turn (launches that share a slot are kFusedSlots launches apart; each launch leaves its slot zeroed)
+      static std::atomic<unsigned> slot_turn{0};
+      int* ws = a->fused_ws + 4 * (slot_turn.fetch_add(1) % kFusedSlots);
+#ifdef FDQL_FUSED_ROLE_CLOCK
+      g.role_clock = reinterpret_cast<unsigned long long*>(a->fused_ws + 4 * kFusedSlots);
+#endif
+#ifndef FDQL_FUSED_STATIC_SPLIT
+      t.work_ctr = ws;
+      g.lean_work_ctr = ws + 2;
+#endif
       const size_t smem = (size_t)kFusedLossWarps * GrpCfg<128>::kWarpFloatsAlias * sizeof(float) +
-                          (size_t)kFusedGatherWarps * 2 * 8 * 16 * wide_vecs;
+                          (size_t)kFusedGatherWarps * 2 * kFusedStageWindows * 16 * wide_vecs;
       const int flags_ = (t.mc_return ? kGrpLb : 0) | (t.stats ? kGrpStats : 0) | kGrpFull;
       if (smem <= 227 * 1024) {
 #define FDQL_LAUNCH_FUSED(FLAGSV, HASHV)                                                                                    \
@@ -1589,6 +1678,28 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
 #undef FDQL_FUSED_FLAGS
 #undef FDQL_LAUNCH_FUSED
         FDQL_CUDA(cudaGetLastError());
+#ifdef FDQL_FUSED_ROLE_CLOCK
+        {
+          static int calls = 0;
+          cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+          cudaStreamIsCapturing(st, &cap);
+          if (cap == cudaStreamCaptureStatusNone && ++calls % 97 == 0) {
+            unsigned long long hc[3 * 256];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hc, g.role_clock, sizeof(unsigned long long) * 3 * a->num_sms, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int b = 0; b < a->num_sms; ++b) t0 = hc[3 * b] < t0 ? hc[3 * b] : t0;
+            double sl = 0, sg = 0, ml = 0, mg = 0, ss = 0;
+            for (int b = 0; b < a->num_sms; ++b) {
+              const double l = (double)(hc[3 * b + 1] - t0), gg = (double)(hc[3 * b + 2] - t0);
+              sl += l; sg += gg; ss += (double)(hc[3 * b] - t0);
+              ml = l > ml ? l : ml; mg = gg > mg ? gg : mg;
+            }
+            fprintf(stderr, "[role clock] start +%.1f us | loss role ends avg %.1f max %.1f us | gather role ends avg %.1f max %.1f us\n",
+                    ss / a->num_sms / 1e3, sl / a->num_sms / 1e3, ml / 1e3, sg / a->num_sms / 1e3, mg / 1e3);
+          }
+        }
+#endif
         *draw->fused = 1;
         return FDQL_OK;
       }

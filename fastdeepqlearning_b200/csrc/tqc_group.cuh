@@ -24,6 +24,10 @@ struct TqcArgs {
   double* stats;
   const float* alpha_dev;  // when set, overrides alpha
   int32_t grp_red_alias;   // group kernel: the per-lane partial sums live in the dead rows of the q_pred staging (see GrpCfg)
+  // group kernel, optional: {next unclaimed group, blocks done} in device memory, both zero at launch.  When set, the warps of ALL blocks
+  // claim their groups from this one counter (the SMs then finish together whatever their memory latencies were; the claims still form
+  // one dense moving front) and the last block to finish zeroes the pair for the next launch.
+  int* work_ctr;
 };
 
 __device__ __forceinline__ float2 lds2_at(uint32_t addr) {
@@ -356,7 +360,17 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
   // (a contiguous run per block made 148 x 3 separate DRAM streams and was 10 % slower at 800K transitions)
   const int64_t n_groups = (a.M + G - 1) / G;
   const int64_t g_begin = blk, g_step = n_blk;
-  int64_t gi = g_begin + wib * g_step;
+  int* const wctr = a.work_ctr;
+  auto claim_group = [&]() -> int64_t {
+    int claimed = 0;
+    if (wctr != nullptr) {
+      if (lane == 0) claimed = atomicAdd(wctr, 1);
+      return (int64_t)__shfl_sync(kFull, claimed, 0);
+    }
+    if (lane == 0) claimed = atomicAdd(&sm_next, 1);
+    return g_begin + __shfl_sync(kFull, claimed, 0) * g_step;
+  };
+  int64_t gi = wctr != nullptr ? claim_group() : g_begin + wib * g_step;
   int buf = 0;
   uint32_t it = 0;  // round counter: the barrier of next_z buffer b completes once per use (parity (it >> 1) & 1), q_pred's every round
   bool z_bulk = false;
@@ -495,9 +509,7 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
     fence_proxy_async_smem();  // the tables were written through the generic proxy, the bulk copy below overwrites the older ones
     __syncwarp();
     {  // next round's next_z rows into the other buffer (its tables are dead)
-      int claimed = 0;
-      if (lane == 0) claimed = atomicAdd(&sm_next, 1);
-      gnext = g_begin + __shfl_sync(kFull, claimed, 0) * g_step;
+      gnext = claim_group();
       z_bulk = false;
       if (gnext < n_groups) {
         z_bulk = grp_stage_rows(W + (buf ^ 1) * C::kZY, a.next_z, gnext * G, nz, (int)min((int64_t)G, a.M - gnext * G), G, zal, lane,
@@ -622,6 +634,17 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
     __syncwarp();  // the q_pred staging, the scalars and `red` are rewritten in the next round
   }
   cp_async_wait<0>();
+  if (wctr != nullptr) {  // every warp of this block has made its last claim: the last block re-arms the counter for the next launch
+    role_barrier(bar_id, n_warps * 32);
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(wctr + 1, 1) == n_blk - 1) {
+        wctr[0] = 0;
+        wctr[1] = 0;
+        __threadfence();
+      }
+    }
+  }
   if constexpr (STATS) {
     const int vsum = __reduce_add_sync(kFull, viol);
 #pragma unroll

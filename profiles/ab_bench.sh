@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of library builds under bench.py's headline schedule: profiles/ab_bench.sh <reps> <steps> <lib> [<lib> ...]
 reps=$1; steps=$2; shift 2
-F="--steps $steps --no-cpu-baseline --no-e2e --no-extra --no-updates --no-secondary --no-small --no-parity-check"
+F="$AB_FLAGS --steps $steps --no-cpu-baseline --no-e2e --no-extra --no-updates --no-secondary --no-small --no-parity-check"
 for r in $(seq 1 $reps); do
   for lib in "$@"; do
     FDQL_LIB=$lib python bench.py $F 2>/dev/null | python -c "
