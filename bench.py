@@ -9,9 +9,11 @@ One pass of the hot path = `batches_per_step` batches of 4096 sampled windows (T
                         n-step lower bound) on synthetic critic outputs resident in HBM             [targeted]
 on a 1e7-row ring (obs 64, act 8, goal 16+16, 5 scalars; fp32).  One step = `passes_per_step` such passes, so that the timed
 region of a 20-step run is about half a second.  By default the passes are pipelined the way the reference pipelines sampling
-and training (torch_dataloader.py:22-39: a prefetch thread keeps one sampled batch ahead of the learner): the gather of pass
-k+1 runs on a second stream, as two small co-resident blocks per SM (FDQL_OPT_CORESIDENT), under the loss of pass k; every pass
-is complete inside the timed region (K gathers and K losses).  --serial runs the two kernels back to back on one stream.
+and training (torch_dataloader.py:22-39: a prefetch thread keeps one sampled batch ahead of the learner): ONE launch per pass,
+fdql_fused_pass, whose loss role (16 warps per SM) works on pass k while its gather role (8 warps per SM) samples, relabels and
+gathers pass k+1 into the other batch buffer; every pass is complete inside the timed region (K gathers and K losses: the first
+launch of a step is a gather alone, the last one a loss alone).  --two-streams is the round-2a schedule (the gather of pass k+1 on
+a second stream, two small co-resident blocks per SM, under the loss kernel of pass k); --serial runs the two kernels back to back.
 `value` is device-timed with everything resident in HBM; `e2e` is the same pass through the host-buffer C-ABI call
 fdql_hotpath_step_host (index streams and critic outputs from pinned host memory, loss and dloss/dq back to host memory).
 `--impl reference` times the CPU restatement of the reference path (oracle/, numpy + torch-CPU, all host cores) on a bounded
@@ -77,7 +79,10 @@ def parse():
                          "the reference's value (her.py:72-83), bit for bit")
     ap.add_argument("--serial", action="store_true", help="gather and loss back to back on one stream instead of pipelined on two")
     ap.add_argument("--buffers", type=int, default=3, help="batch buffers of the pipelined schedule (gathers run up to buffers-1 passes ahead)")
-    ap.add_argument("--fused", action="store_true", help="one warp-specialised launch per pass (fdql_fused_pass: loss of pass k + gather of pass k+1)")
+    ap.add_argument("--two-streams", action="store_true",
+                    help="gather of pass k+1 on a second stream under the loss kernel of pass k (two launches per pass) instead of the "
+                         "default one warp-specialised launch per pass (fdql_fused_pass: loss of pass k + gather of pass k+1)")
+    ap.add_argument("--fused", action="store_true", help="(default; kept for older command lines)")
     ap.add_argument("--no-step-graph", action="store_true",
                     help="pipelined schedule launched from Python every step instead of one captured CUDA graph per step")
     ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
@@ -226,6 +231,7 @@ def run_ours(args):
     ctr_dev = torch.zeros(4, dtype=torch.int64, device=device)  # device-side draw counter of the captured step
     use_ctr_dev = [False]
     pipelined = not args.serial and not args.separate_streams
+    fused = pipelined and not args.two_streams
     step_graph = pipelined and not args.no_step_graph
     P = args.passes_per_step or 64
 
@@ -369,8 +375,8 @@ def run_ours(args):
 
     if pipelined:
         lib.fdql_set_coresident(1)  # the loss kernel leaves room on every SM for the co-resident gather blocks
-    run = run_fused if args.fused else run_pipelined if pipelined else run_serial
-    if args.fused:
+    run = run_fused if fused else run_pipelined if pipelined else run_serial
+    if fused:
         lib.fdql_set_coresident(0)
     for _ in range(max(args.warmup, 3)):
         run(P)
@@ -681,6 +687,26 @@ def run_ours(args):
     for kd in kernels.values():
         kd["note"] = ("ms = average launch duration inside the timed region, where the two kernels share every SM; ms_alone = the same "
                       "launch with the GPU to itself") if pipelined else "ms = average launch duration inside the timed region"
+    alone = None
+    if fused:
+        # one launch per pass: the two stand-alone kernels only appear as the first / last launch of a step; their figures alone stay
+        # in the line as `alone`, the kernel of the timed region is the fused one with both roles' algorithmic bytes
+        alone = {k: {"ms_alone": kd["ms_alone"], "bytes_per_transition": kd["bytes_per_transition"], "symbol": kd["symbol"],
+                     "frac_alone": kd["bytes_per_transition"] * M / (kd["ms_alone"] * 1e-3) / 1e9 / peak} for k, kd in kernels.items()}
+        alone["sample_gather_kernel"]["symbol"] = "fdql::sample_gather_tile_kernel (draws its own index / goal streams)"
+        kernels = {"fused_pass_kernel": {
+            "ms": float(k_ms[2]), "bytes_per_transition": sum(kd["bytes_per_transition"] for kd in kernels.values()),
+            "symbol": "fdql::fused_pass_kernel<7, true, true>",
+            "roles": {"loss": "16 warps per SM: tqc_group_body on pass k (pool, sort, drop, soft target, quantile-Huber fwd+bwd, lower bound): %d B"
+                              % BYTES_TQC,
+                      "gather": "8 warps per SM: gather_lean_body on pass k+1 (draw, window gather through cp.async staging + bulk "
+                                "shared->global write-back, HER relabel, reward / return recompute, learner aux): %.1f B"
+                                % (BYTES_GATHER + bytes_relabel + 17)},
+            "limiter": "instruction issue: 242 M warp instructions per launch (loss 214 M + gather 26 M), issue slots 79 % active (ncu, "
+                       "profiles/r2_fused_*); shared-memory wavefronts 70 % of the LSU data pipe; DRAM 41 %.  The gather role ends after "
+                       "~195 us of the ~270 us launch (role-clock probe build), the loss role runs the rest alone",
+            "note": "ms = average launch duration inside the timed region (CUDA-event nodes around 8 of the 64 launches of a step; a "
+                    "launch between event nodes cannot overlap its neighbours' ramps, so this is a little above ms_per_pass)"}}
     if args.separate_streams:
         kernels["sample_streams_kernel"] = {"ms": float(k_ms[0]), "bytes_per_transition": BYTES_STREAMS, "symbol": "fdql::sample_streams_kernel"}
     for kd in kernels.values():
@@ -692,12 +718,14 @@ def run_ours(args):
     total_bytes = sum(kd["bytes_per_transition"] for kd in kernels.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "frac_alone": kernels[dom].get("frac_alone"), "traffic": None, "peak_source": peak_src,
-                "note": ("launch_ms / achieved / frac: this kernel's average duration inside the timed region, where it shares every SM with "
+                "note": ("one launch per pass (loss role on pass k + gather role on pass k+1): achieved = both roles' algorithmic bytes over "
+                         "the launch duration; `alone` = the two stand-alone kernels with the GPU to themselves") if fused else
+                        ("launch_ms / achieved / frac: this kernel's average duration inside the timed region, where it shares every SM with "
                          "the co-resident gather of the next pass (so they are lower than the kernel's own figures); frac_alone: the same "
                          "launch with the GPU to itself; whole_step: both kernels' bytes over the pass time") if pipelined else None,
                 "algorithmic_bytes_per_launch": kernels[dom]["bytes_per_transition"] * M, "launch_ms": kernels[dom]["ms"],
                 "survey_bytes_per_transition": {"sample_gather_kernel": BYTES_GATHER + BYTES_RELABEL_SURVEY, "tqc_loss_kernel": BYTES_TQC},
-                "kernels": kernels,
+                "kernels": kernels, "alone": alone,
                 "whole_step": {"bytes_per_transition": total_bytes, "achieved_gbs": total_bytes * M / (ms_pass * 1e-3) / 1e9,
                                "frac": total_bytes * M / (ms_pass * 1e-3) / 1e9 / peak, "ms_per_pass": ms_pass,
                                "note": "both kernels' algorithmic bytes over the time of one pass of the pipelined schedule"},
@@ -726,7 +754,12 @@ def run_ours(args):
                                    % (len(ring) + 1),
                        "batch": B, "temporal_len": T, "batches_per_step": D, "passes_per_step": P, "transitions_per_step_per_gpu": M * P,
                        "transitions_per_pass_per_gpu": M,
-                       "schedule": ("pipelined on two streams over %d batch buffers: gather of pass k+1 (FDQL_OPT_CORESIDENT, two 4-warp blocks per SM) "
+                       "schedule": ("one launch per pass (fdql_fused_pass, one persistent 24-warp block per SM): the loss role (16 warps) works on pass k "
+                                    "while the gather role (8 warps) draws, gathers and relabels pass k+1 into the other batch buffer, as the "
+                                    "reference's prefetch thread does (torch_dataloader.py:22-39); every pass complete inside the timed region "
+                                    "(first launch of a step = gather alone, last = loss alone)" +
+                                    ("; one step = one captured CUDA graph, replayed" if step_graph else "; launched from Python")) if fused else
+                                   ("pipelined on two streams over %d batch buffers: gather of pass k+1 (FDQL_OPT_CORESIDENT, two 4-warp blocks per SM) "
                                     "under the loss of pass k, as the reference's prefetch thread does (torch_dataloader.py:22-39); every pass complete "
                                     "inside the timed region" + ("; one step = one captured CUDA graph, replayed" if step_graph else
                                                                   "; launched from Python")) % NB if pipelined
@@ -736,7 +769,7 @@ def run_ours(args):
                              % ((len(ring) + 1) * (ROW_BYTES + 16) / 1e9, M * CQ * 8 // 2 ** 20),
                        "exact_episode_step": bool(exact), "parallelism": f"replay shards x{world}, no data-path collective",
                        "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
-            "roofline": roofline, "gpu_launches": (3 if args.separate_streams else 2) * K * P, "clocks": clk,
+            "roofline": roofline, "gpu_launches": (P + 1) * K if fused else (3 if args.separate_streams else 2) * K * P, "clocks": clk,
             "ms_per_pass": ms_pass,
             "single_batch_launches": {"windows_per_launch": B, "ms_per_batch": small_ms, "transitions_per_s": world * B / (small_ms * 1e-3),
                                       "note": "2 launches per 4096-window batch from Python (gather with fused draw, loss), launch-latency bound",

@@ -483,11 +483,17 @@ int fdql_arena_destroy(fdql_arena* a) {
   if (a->reward_params_dev) cudaFree(a->reward_params_dev);
 #ifdef FDQL_FUSED_ROLE_CLOCK
   if (a->fused_ws) {
-    unsigned long long h[5];
+    unsigned long long h[40];
     cudaDeviceSynchronize();
     cudaMemcpy(h, reinterpret_cast<unsigned long long*>(a->fused_ws + 4 * kFusedSlots) + 3 * 256, sizeof(h), cudaMemcpyDeviceToHost);
     if (h[2]) fprintf(stderr, "[role clock] %llu launches: gap between launches (last role end -> next block 0 start) avg %.2f us; block 0 loss role %.1f us, gather role %.1f us\n",
                       h[2], (double)h[1] / h[2] / 1e3, (double)h[3] / (h[2] + 1) / 1e3, (double)h[4] / (h[2] + 1) / 1e3);
+    if (h[2]) {
+      fprintf(stderr, "[role clock] gap histogram (us: launches):");
+      for (int i = 0; i < 32; ++i)
+        if (h[8 + i]) fprintf(stderr, " %d:%llu", i, h[8 + i]);
+      fprintf(stderr, "\n");
+    }
   }
 #endif
   if (a->fused_ws) cudaFree(a->fused_ws);

@@ -1493,6 +1493,8 @@ fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ 
       if (le != 0 && t_start > le && t_start - le < 1000000ull) {
         atomicAdd(acc + 1, t_start - le);
         atomicAdd(acc + 2, 1ull);
+        const unsigned long long us = (t_start - le) / 1000ull;  // histogram of the gap in microseconds, 0..31+
+        atomicAdd(acc + 8 + (us < 31ull ? us : 31ull), 1ull);
       }
     }
   }
