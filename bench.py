@@ -85,7 +85,7 @@ def parse():
     ap.add_argument("--fused", action="store_true", help="(default; kept for older command lines)")
     ap.add_argument("--no-step-graph", action="store_true",
                     help="pipelined schedule launched from Python every step instead of one captured CUDA graph per step")
-    ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (64; 4 with --serial-events)")
+    ap.add_argument("--passes-per-step", type=int, default=0, help="passes of batches_per_step batches per step, 0 = auto (128 fused, 64 otherwise)")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE.json configs[0..2] sections (Pendulum / CartPole / 64-bit HER shapes)")
     ap.add_argument("--no-graph", action="store_true", help="learner step launched eagerly instead of as one CUDA graph")
@@ -233,7 +233,7 @@ def run_ours(args):
     pipelined = not args.serial and not args.separate_streams
     fused = pipelined and not args.two_streams
     step_graph = pipelined and not args.no_step_graph
-    P = args.passes_per_step or 64
+    P = args.passes_per_step or (128 if fused else 64)  # the fused schedule pays one unfused gather and one unfused loss per step
 
     # argument tuples are built once per (buffer, stream): the pipelined schedule needs ~6000 launches per second from this loop
     _args = {}

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 out = [f"# per-line instruction / shared-memory view ({tag}); report {os.path.basename(rep)}; all figures per unit "
        f"(= per transition / window, {units} per launch)\n"]
 for kern, label in (("tqc_loss_group", "tqc_loss_group_kernel"), ("sample_gather_tile", "sample_gather_tile_kernel"),
-                    ("sample_gather_lean", "sample_gather_lean_kernel")):
+                    ("sample_gather_lean", "sample_gather_lean_kernel"), ("fused_pass", "fused_pass_kernel")):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))

@@ -51,7 +51,8 @@ for hdr, units, data in reports:
                   pass
       if "dram__bytes_read.sum" in vals:
           tot = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-          key = "sample_gather_kernel" if "sample_gather" in name else "tqc_loss_kernel" if "tqc_loss" in name else name.split("<")[0]
+          key = ("fused_pass_kernel" if "fused_pass" in name else "sample_gather_kernel" if "sample_gather" in name else
+                 "tqc_loss_kernel" if "tqc_loss" in name else name.split("<")[0])
           traffic[key] = tot
           if "smsp__inst_executed.sum" in vals:
               traffic.setdefault("warp_instructions", {})[key] = vals["smsp__inst_executed.sum"]
