@@ -450,32 +450,49 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
       int kkl = kk;
       asm volatile("" : "+r"(kkl));  // keeps the `s < kk` compares below the shuffle
 
-      // soft target (:50-58) in the reference's operator order; raw mode (quantile_huber_loss_f): targets as given
-      if (a.reward) {
-        if (a.next_log_pi) {
-#pragma unroll
-          for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(e[s], ent)));
-          c0 = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(c0, ent)));
-        } else {
-#pragma unroll
-          for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, e[s]));
-          c0 = __fadd_rn(rew, __fmul_rn(mg, c0));
-        }
-      }
-      if (a.td_target && live) {
-#pragma unroll
-        for (int s = 0; s < E; ++s)
-          if (s < kkl) a.td_target[(m0 + grp) * K + sl * E + s] = e[s];
-      }
-      // cut the top n_drop (+inf), centre, this lane's sums of y and y^2.
-      // Entries at sorted index >= K hold +inf and make every later prefix non-finite; no search ever lands past K.
+      // soft target (:50-58); raw mode (quantile_huber_loss_f): targets as given.  Then cut the top n_drop (+inf), centre, this lane's
+      // sums of y and y^2.  Entries at sorted index >= K hold +inf and make every later prefix non-finite; no search ever lands past K.
       float l1 = 0.f, l2 = 0.f;
+#ifdef FDQL_TQC_NO_FOLD  // (A/B builds)
+      if (true) {
+#else
+      if (a.td_target != nullptr) {  // the targets themselves are wanted: the reference's operator order, bit for bit
+#endif
+        if (a.reward) {
+          if (a.next_log_pi) {
 #pragma unroll
-      for (int s = 0; s < E; ++s) {
-        const float y = s < kkl ? e[s] - c0 : CUDART_INF_F;
-        e[s] = y;
-        l1 += y;
-        l2 = fmaf(y, y, l2);
+            for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(e[s], ent)));
+            c0 = __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(c0, ent)));
+          } else {
+#pragma unroll
+            for (int s = 0; s < E; ++s) e[s] = __fadd_rn(rew, __fmul_rn(mg, e[s]));
+            c0 = __fadd_rn(rew, __fmul_rn(mg, c0));
+          }
+        }
+        if (a.td_target != nullptr && live) {
+#pragma unroll
+          for (int s = 0; s < E; ++s)
+            if (s < kkl) a.td_target[(m0 + grp) * K + sl * E + s] = e[s];
+        }
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+          const float y = s < kkl ? e[s] - c0 : CUDART_INF_F;
+          e[s] = y;
+          l1 += y;
+          l2 = fmaf(y, y, l2);
+        }
+      } else {
+        // only the loss is wanted: the centred target directly, y_k - y_c = mask gamma (z_k - z_c) -- the reward and the entropy
+        // term cancel, two operations per atom instead of four, and no cancellation between large offsets
+        const float zc = c0, scale = a.reward ? mg : 1.f;
+        if (a.reward) c0 = a.next_log_pi ? __fadd_rn(rew, __fmul_rn(mg, __fadd_rn(c0, ent))) : __fadd_rn(rew, __fmul_rn(mg, c0));
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+          const float y = s < kkl ? (e[s] - zc) * scale : CUDART_INF_F;
+          e[s] = y;
+          l1 += y;
+          l2 = fmaf(y, y, l2);
+        }
       }
       float x1 = l1, x2 = l2;  // inclusive scan over the LPT lanes of the transition
 #pragma unroll
