@@ -190,7 +190,8 @@ int fdql_sample_gather_draw(const fdql_arena* a, int64_t n_windows, int32_t T, i
  * alias (the loss reads batch k's reward / mask / mc_return / weight while the gather writes batch k+1 into other buffers).
  * M == 0: the gather alone; n_windows == 0: the loss alone.  Shapes the fused kernel does not serve (loss tables other than 97..128
  * atoms, small batches, keys wider than the lean copy plan, other reward functors) run as the separate launches, gather then loss on
- * `stream`, with identical results. */
+ * `stream`, with identical results.  The fused kernel claims its work from counters in a 16-slot workspace of the arena, one slot per
+ * launch in turn: at most 16 fused passes of one arena may be in flight at a time (passes on one stream never are). */
 int fdql_fused_pass(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
                     uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows, int32_t reward_op,
                     const float* reward_params_host, int32_t n_params, double gamma, uint32_t opts, int32_t batch_for_weight,
