@@ -580,12 +580,55 @@ def run_ours(args):
                  "tqc": {"bytes_per_transition": BYTES_TQC, "achieved": BYTES_TQC * M2 / (acc2[1] / reps2 * 1e-3) / 1e9,
                          "frac": BYTES_TQC * M2 / (acc2[1] / reps2 * 1e-3) / 1e9 / peak2},
                  "whole_step": {"bytes_per_transition": gb2 + BYTES_TQC, "frac": (gb2 + BYTES_TQC) * M2 / (ms2 * 1e-3) / 1e9 / peak2}}
+        # the same pass through the fused schedule of the headline: loss role on pass k + gather role on pass k+1, one launch per pass
+        # (two batch buffers; first launch = gather alone, last = loss alone: R gathers and R losses inside the timed region)
+        fused50 = None
+        if fused:
+            b50 = [{"out": out2, "outp": outp2, "mask": mask2, "contig": contig2, "weight": weight2, "st": st2, "fl": fl2, "go": go2}]
+            o3 = {k: torch.empty((T2, n2, w), device=device) for k, w in zip(keys, ring._widths)}
+            b50.append({"out": o3, "outp": L.ptr_array([o3[k].data_ptr() for k in keys]), "mask": torch.empty(T2, n2, device=device),
+                        "contig": torch.empty(T2 - 1, n2, device=device), "weight": torch.empty(T2 - 1, n2, device=device),
+                        "st": torch.empty(n2, dtype=torch.int64, device=device), "fl": torch.empty(n2, dtype=torch.uint8, device=device),
+                        "go": torch.empty(n2, dtype=torch.int64, device=device)})
+
+            def pass50(k, n_w, m):
+                gb, tb = b50[k % 2], b50[(k + 1) % 2]
+                L.check(lib.fdql_fused_pass(h, n_w, T2, L.GOAL_FUTURE, P_RELABEL, 31 + rank, 60_000 + k, None, p(gb["st"]), p(gb["fl"]),
+                                            p(gb["go"]), ring.reward_op.op, params, n_params, GAMMA, opts, B, gb["outp"], p(gb["mask"]),
+                                            p(gb["contig"]), p(gb["weight"]), m, CQ, N_DROP, p(z2), p(q2), p(lp2), p(tb["out"]["reward"][1:]),
+                                            p(tb["mask"][1:]), p(tb["out"]["mc_return"][1:]), p(tb["weight"]), ALPHA, GAMMA, p(loss2),
+                                            p(grad2), None, sp))
+
+            def run50(R):
+                pass50(0, n2, 0)
+                for k in range(1, R):
+                    pass50(k, n2, M2)
+                pass50(R, 0, M2)
+            run50(3)
+            torch.cuda.synchronize(device)
+            R50 = 20
+            e0.record(stream)
+            run50(R50)
+            e1.record(stream)
+            torch.cuda.synchronize(device)
+            ms50 = e0.elapsed_time(e1) / R50
+            if dist:
+                tm = torch.tensor([ms50], device=device)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                ms50 = float(tm.item())
+            fused50 = {"ms_per_pass": ms50, "transitions_per_s": world * M2 / (ms50 * 1e-3), "passes": R50,
+                       "frac": (gb2 + BYTES_TQC) * M2 / (ms50 * 1e-3) / 1e9 / peak2,
+                       "schedule": "fdql_fused_pass, one launch per pass (loss of pass k + draw / gather / relabel of pass k+1), launched from "
+                                   "Python; first launch = gather alone, last = loss alone"}
+            del o3, b50
         secondary = {"temporal_len": T2, "windows_per_step": n2, "transitions_per_step_per_gpu": M2, "ms_per_step": ms2, "roofline": roof2,
+                     "fused": fused50,
                      "transitions_per_s": world * M2 / (ms2 * 1e-3), "rows_gathered_per_s": world * T2 * n2 / (acc2[0] / reps2 * 1e-3),
                      "gather_ms": float(acc2[0] / reps2), "tqc_ms": float(acc2[1] / reps2), "loss_mean": float(loss2.mean()),
                      "note": "reference default temporal_len (conf.py:38): one window gives 49 TD pairs, so the gather is amortised and "
-                             "the loss kernel is the step; streams drawn by fdql_sample_streams, relabelled returns by the tail scan "
-                             "(link records serve T <= 32)"}
+                             "the loss kernel is the step; transitions_per_s / gather_ms / tqc_ms: one serial pass (streams drawn by "
+                             "fdql_sample_streams, relabelled returns by the tail scan: link records serve T <= 32); fused: the headline's "
+                             "schedule at this temporal_len"}
         del out2, z2, q2, grad2, loss2, lp2
 
     # ---- e2e: the host-buffer C-ABI call, pinned host inputs, host outputs ---------------------------------------------

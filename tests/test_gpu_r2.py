@@ -536,14 +536,16 @@ def test_coresident_option_selects_the_lean_kernel_and_matches(fdql, obs, act, G
 
 
 # ------------------------------------------------------------------------------------------------ one launch per pass
-@pytest.mark.parametrize("n,n_atoms,n_drop,with_lb,with_stats,repeat", [
-    (24576, 125, 10, True, True, 2),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
-    (20000, 125, 10, False, False, 1),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
-    (24576, 100, 8, True, False, 1),    # fused kernel, 100 atoms (4 x 25)
-    (3000, 125, 10, True, True, 1),     # batch too small for the one-block-per-SM form: the two separate launches
-    (24576, 50, 4, True, True, 1),      # 64-entry loss tables: separate launches
+@pytest.mark.parametrize("n,T,n_atoms,n_drop,with_lb,with_stats,repeat", [
+    (24576, 2, 125, 10, True, True, 2),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
+    (20000, 2, 125, 10, False, False, 1),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
+    (24576, 2, 100, 8, True, False, 1),    # fused kernel, 100 atoms (4 x 25)
+    (6001, 5, 125, 10, True, True, 1),     # fused kernel, five-row windows (link records), ragged
+    (1024, 50, 125, 10, True, True, 2),    # fused kernel at the reference's default temporal_len (tail scan: windows past the hit mask)
+    (3000, 2, 125, 10, True, True, 1),     # batch too small for the one-block-per-SM form: the two separate launches
+    (24576, 2, 50, 4, True, True, 1),      # 64-entry loss tables: separate launches
 ])
-def test_fused_pass_equals_the_two_launches(fdql, n, n_atoms, n_drop, with_lb, with_stats, repeat):
+def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb, with_stats, repeat):
     """fdql_fused_pass (loss of batch k + gather of batch k+1 in one warp-specialised launch) against fdql_sample_gather_draw and
     fdql_tqc_loss as separate launches on the same arguments: bit-identical batch, loss, gradient; summaries to fp64 rounding.  The
     loss half reads the PREVIOUS gather's reward / mask / mc_return / weight (other buffers), as the learner loop does."""
@@ -551,7 +553,7 @@ def test_fused_pass_equals_the_two_launches(fdql, n, n_atoms, n_drop, with_lb, w
     import torch
     from fastdeepqlearning_b200 import Replay, _lib as L
     from test_gpu_replay import _synthetic
-    T, G = 2, 16
+    G = 16
     rng = np.random.default_rng(5 + n)
     cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 600, 0, G, obs=64, act=8, fixed_len=64)
     N = int(lengths.sum())
