@@ -961,7 +961,7 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
   // ---- link path (common.cuh): the rows that hit g* are the chain of bit-identical achieved goals through the goal row, so
   // the relabelled return of window row t is GA_t + sum_{hits m >= t} gamma^(m-t); nothing is read from the rest of the tail
   bool linked = false;
-  uint32_t inwin = 0;  // bit t: window row t hits the goal
+  uint64_t inwin = 0;  // bit t: window row t hits the goal (link records serve windows of up to 64 rows)
   double W = 0.0;      // sum over the hits m >= 0 (relative to the window start) of gamma^m
   int seg_first = -1;  // first row of the synthetic episode the window starts in, episode-relative (exact mode)
   int j0 = 0;
@@ -977,7 +977,7 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
         auto visit = [&](int m) {
           if (m >= 0) {
             W += exp2((double)m * g.log2_gamma);
-            if (m < T) inwin |= 1u << m;
+            if (m < T) inwin |= 1ull << m;
           } else {
             near_before = max(near_before, m);
           }
@@ -1067,7 +1067,7 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
       bool m;
       if (linked) {
         const float4 lt = __ldg(A.link + ring_row32(s, t, cap32));
-        m = ((inwin >> t) & 1u) != 0u;
+        m = ((inwin >> t) & 1ull) != 0ull;
         v_rew = (float)((double)lt.y + (m ? 0.0 : -1.0));
         if (o_ret != nullptr) st_stream1(o_ret + (int64_t)t * g.n + b, (float)((double)lt.x + gi * (W - Wsub)));
         if (m) Wsub += gp;
@@ -1593,8 +1593,11 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   // small tail-scanning launches are latency-bound and run faster with one warp per window (measured: 4096 windows 20 us vs 29 us);
   // from ~48K windows on, the tile kernel's lower instruction count wins (262144 windows: 209 us vs 261 us)
   // link records (chain of equal achieved goals + goal-agnostic return) serve equality rewards when they were built with this
-  // discount and the window fits the 32-bit hit mask; otherwise the kernels scan the episode tail
-  const bool link_ok = hash_ok && a->link_state == 1 && a->link_gamma == gamma && gamma > 0.0 && T <= 32 && !(g_force_generic_gather & 16);
+  // discount and the window fits the 64-bit hit mask; otherwise the kernels scan the episode tail
+  // (the lean / fused kernels take them up to 64 window rows; the tile kernel, thread per window with T link records each, is
+  // faster through the tail scan beyond 32: measured at T = 50, 16384 windows, 0.267 against 0.440 ms)
+  const bool link_ok64 = hash_ok && a->link_state == 1 && a->link_gamma == gamma && gamma > 0.0 && T <= 64 && !(g_force_generic_gather & 16);
+  const bool link_ok = link_ok64 && T <= 32;
   // with link records the tile kernel has no tail loop and wins from ~1K windows on (measured 4096 windows: 14.7 us vs 19.5 us per call)
   const bool big = (b_end - b_begin) >= 49152 || (link_ok && (b_end - b_begin) >= 1024) || g_tile_override != 0;
   // lean kernel (wide keys through cp.async staging + bulk write-back): asked for by FDQL_OPT_CORESIDENT (one block per SM, next to
@@ -1634,7 +1637,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     const int64_t n_groups = (ta.M + GrpCfg<128>::G - 1) / GrpCfg<128>::G;
     if (need > 64 && need <= 128 && ta.n_atoms > 96 && ta.n_atoms >= 3 * GrpCfg<128>::kRedPitch &&
         n_groups > (int64_t)2 * kFusedLossWarps * a->num_sms) {
-      g.use_link = link_ok;
+      g.use_link = link_ok64;
       g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
       g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
       g.dbg = 0;
@@ -1708,7 +1711,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     }
   }
   if (lean_ok && (coresident || (g_force_generic_gather & 32))) {
-    g.use_link = link_ok;
+    g.use_link = link_ok64;
     g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
     g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
     const int stage_w = coresident ? 8 : 16;  // co-resident: two blocks of half-size stages per SM (eight warps in 54 KB)
