@@ -481,7 +481,12 @@ def test_lean_kernel_vs_oracle_and_tile_kernel(fdql, T, G, obs, act, B, links):
         else:
             np.testing.assert_array_equal(npy(got[k]), want[k], err_msg=k)
     for k in tile:
-        assert torch_equal(tile[k], got[k]), k
+        if k == "mc_return" and links and T > 32:
+            # beyond 32 window rows the tile kernel recomputes the returns from the tail scan, the lean kernel still from the link
+            # records (64-bit hit mask): both within tolerance of the oracle (checked above), not bit-identical to each other
+            np.testing.assert_allclose(npy(tile[k]), npy(got[k]), rtol=1e-5, atol=1e-6, err_msg=k)
+        else:
+            assert torch_equal(tile[k], got[k]), k
     idx = np.arange(T)[:, None] + starts[None]
     for k in cols:
         np.testing.assert_array_equal(npy(plain[k]), cols[k][idx], err_msg=k)
