@@ -193,6 +193,8 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fdql_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=device)
     lib = pkg.lib()
+    if os.environ.get("FDQL_PROBE_DBG"):  # profiles/: probe switches of the gather role (GatherArgs.dbg); results are then NOT valid batches
+        lib.fdql_debug_force_generic_gather(int(os.environ["FDQL_PROBE_DBG"]) << 6)
     D = args.batches_per_step
     n = D * B
     M = (T - 1) * n

@@ -882,6 +882,13 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3) sample_gather_fast_ker
   }
 }
 
+// probe switches (GatherArgs.dbg) exist only in probe builds (profiles/build_variant.sh ... -DFDQL_PROBES): dead branches inside the
+// hot loops cost instruction-cache lines even when they are never taken
+#ifdef FDQL_PROBES
+#define FDQL_DBG(g) ((g).dbg)
+#else
+#define FDQL_DBG(g) 0
+#endif
 constexpr int kTileWindows = 256;
 #ifndef TILE_MINB
 #define TILE_MINB 4
@@ -896,11 +903,89 @@ constexpr int kTileWindows = 256;
 // Phase 1 of the tile / lean kernels for ONE window (one thread): everything scalar -- index / goal streams (drawn here when DRAW),
 // episode extents, hindsight reward / task_done / episode_step, the relabelled return, every scalar key and the learner aux are
 // written to the time-major outputs; returns what the wide-key phase needs (start row, goal row, last in-episode window row or -1).
-template <bool HASH, bool DRAW>
+// the hindsight predicate of one tail row: R(ag_j, g*) == 0  <=>  achieved_goal[row] == achieved_goal[goal_row]; `gsc` = scan record of
+// the goal row, `gd` = its offset from the window start.  A hash match is verified on the full vectors, except for the goal row
+// itself, which is equal unless it holds a NaN.
+__device__ __forceinline__ bool scan_matches(const ArenaDev& A, int s, int grow, int cap32, const float4& gsc, int gd, int j, const float4& r) {
+  bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+  if (m) {
+    if (j == gd) m = (__float_as_uint(r.w) & 1u) == 0u;
+    else m = rows_equal(A, ring_row32(s, j, cap32), grow);
+  }
+  return m;
+}
+// The tail-scan form of the relabelled return for ONE window (one thread): return-to-go over the whole real episode with relabelled
+// rewards (quirk Q5), newest row first, each step in fp64 and rounded to fp32 on store exactly like nstep_return.py:69-72; rows inside
+// the window are written to `o_ret`.  Returns the first row of the synthetic episode the window starts in (exact mode scans the
+// episode prefix, her.py:72-83), or -1.
+__device__ __forceinline__ int tail_scan_window(const GatherArgs& g, int s, int grow, int tail_last, int ep_first, int j0, int T,
+                                                float* o_ret, int64_t b, float4& gsc, int& gd) {
+  const ArenaDev& A = g.A;
+  const int cap32 = (int)A.capacity;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  gsc = __ldg(A.scan + grow);
+  gd = grow - s + (grow < s ? cap32 : 0);
+  float acc = 0.f;
+  bool first = true;
+  constexpr int UR = TAIL_UNROLL;  // scan records in flight per thread (per-thread L2 prefetches were measured slower)
+  for (int jt = tail_last; jt >= 0; jt -= UR) {
+    float4 r4[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) r4[u] = jt - u >= 0 ? __ldg(A.scan + ring_row32(s, jt - u, cap32)) : zero4;
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int j = jt - u;
+      if (j < 0) break;
+      const bool m = scan_matches(A, s, grow, cap32, gsc, gd, j, r4[u]);
+      const float rnew = (float)((double)r4[u].z + (m ? 0.0 : -1.0));
+      acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
+      first = false;
+      if (j < T && o_ret != nullptr) st_stream1(o_ret + (int64_t)j * g.n + b, acc);
+    }
+  }
+  int seg_first = -1;
+  if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
+    seg_first = 0;
+    for (int j = j0 - 1; j >= 0; --j) {
+      const int row = ring_row32(ep_first, j, cap32);
+      const float4 r = __ldg(A.scan + row);
+      bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
+      if (m) {
+        if (row == grow) m = (__float_as_uint(r.w) & 1u) == 0u;
+        else m = rows_equal(A, row, grow);
+      }
+      if (m) {
+        seg_first = j + 1;
+        break;
+      }
+    }
+  }
+  return seg_first;
+}
+// The same two steps as calls, for the kernels specialised on a window length (TC > 0: link records serve every window except those of
+// episodes without a chain -- longer than 32767 rows --, so the scan is cold code there and stays out of the hot loop's instruction
+// stream; the goal row's scan record is simply fetched again per row).
+__device__ __noinline__ int tail_scan_window_cold(const GatherArgs& g, int s, int grow, int tail_last, int ep_first, int j0, int T,
+                                                  float* o_ret, int64_t b) {
+  float4 gsc;
+  int gd;
+  return tail_scan_window(g, s, grow, tail_last, ep_first, j0, T, o_ret, b, gsc, gd);
+}
+__device__ __noinline__ bool scan_row_matches_cold(const GatherArgs& g, int s, int grow, int t) {
+  const ArenaDev& A = g.A;
+  const int cap32 = (int)A.capacity;
+  const float4 gsc = __ldg(A.scan + grow);
+  const int gd = grow - s + (grow < s ? cap32 : 0);
+  return scan_matches(A, s, grow, cap32, gsc, gd, t, __ldg(A.scan + ring_row32(s, t, cap32)));
+}
+
+// TC > 0: the window length is the compile-time constant TC, scalar records are 8 floats and the link records are valid (the launcher
+// checks all three); TC = 0: everything at run time.
+template <bool HASH, bool DRAW, int TC = 0>
 __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t b, uint64_t draw_ctr, int& s_out, int& grow_out,
                                                     int& tail_out) {
   const ArenaDev& A = g.A;
-  const int T = g.T;
+  const int T = TC > 0 ? TC : g.T;
   const int cap32 = (int)A.capacity, len32 = (int)g.len;
   const bool want_aux = (g.opts & FDQL_OPT_EMIT_LEARNER_AUX) != 0;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -908,7 +993,7 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
   bool relabel = false;
   int tail_last = -1, ep_first = 0, grow = 0;
   // 8-float scalar records (<= 6 scalar keys + the two extents) travel whole, one 256-bit load per row
-  const bool vec8 = A.rec_stride == 8;
+  const bool vec8 = TC > 0 ? true : A.rec_stride == 8;
   float rv0[8];
   bool have0 = false;
   if (DRAW) {  // fused draw: same generator, same streams as sample_streams_kernel
@@ -949,15 +1034,6 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
 
   float4 gsc = zero4;
   int gd = -1;
-  // the hindsight predicate of one tail row: R(ag_j, g*) == 0  <=>  achieved_goal[row] == achieved_goal[goal_row]
-  auto matches = [&](int j, const float4& r) {
-    bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
-    if (m) {  // hash match: the goal row itself is equal unless it holds a NaN; any other row is verified
-      if (j == gd) m = (__float_as_uint(r.w) & 1u) == 0u;
-      else m = rows_equal(A, ring_row32(s, j, cap32), grow);
-    }
-    return m;
-  };
   // ---- link path (common.cuh): the rows that hit g* are the chain of bit-identical achieved goals through the goal row, so
   // the relabelled return of window row t is GA_t + sum_{hits m >= t} gamma^(m-t); nothing is read from the rest of the tail
   bool linked = false;
@@ -966,7 +1042,7 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
   int seg_first = -1;  // first row of the synthetic episode the window starts in, episode-relative (exact mode)
   int j0 = 0;
   if (HASH && relabel) j0 = s - ep_first + (s < ep_first ? cap32 : 0);
-  if (HASH && relabel && g.use_link) {
+  if (HASH && relabel && (TC > 0 || g.use_link)) {
     const int jg = grow - ep_first + (grow < ep_first ? cap32 : 0);
     const float4 lg = __ldg(A.link + grow);
     const int pk = __float_as_int(lg.z);
@@ -1004,45 +1080,8 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
     }
   }
   if (HASH && relabel && !linked) {
-    gsc = __ldg(A.scan + grow);
-    gd = grow - s + (grow < s ? cap32 : 0);
-    // return-to-go over the whole real episode with relabelled rewards (quirk Q5), newest row first, each step in fp64
-    // and rounded to fp32 on store exactly like nstep_return.py:69-72
-    float acc = 0.f;
-    bool first = true;
-    constexpr int UR = TAIL_UNROLL;  // scan records in flight per thread (per-thread L2 prefetches were measured slower)
-    for (int jt = tail_last; jt >= 0; jt -= UR) {
-      float4 r4[UR];
-#pragma unroll
-      for (int u = 0; u < UR; ++u) r4[u] = jt - u >= 0 ? __ldg(A.scan + ring_row32(s, jt - u, cap32)) : zero4;
-#pragma unroll
-      for (int u = 0; u < UR; ++u) {
-        const int j = jt - u;
-        if (j < 0) break;
-        const bool m = matches(j, r4[u]);
-        const float rnew = (float)((double)r4[u].z + (m ? 0.0 : -1.0));
-        acc = first ? rnew : (float)__dadd_rn((double)rnew, __dmul_rn((double)acc, g.gamma));
-        first = false;
-        if (j < T && o_ret != nullptr) st_stream1(o_ret + (int64_t)j * g.n + b, acc);
-      }
-    }
-    // first row of the synthetic episode the window starts in (exact mode scans the episode prefix, her.py:72-83)
-    if (g.opts & FDQL_OPT_EXACT_EPISODE_STEP) {
-      seg_first = 0;
-      for (int j = j0 - 1; j >= 0; --j) {
-        const int row = ring_row32(ep_first, j, cap32);
-        const float4 r = __ldg(A.scan + row);
-        bool m = __float_as_uint(r.x) == __float_as_uint(gsc.x) && __float_as_uint(r.y) == __float_as_uint(gsc.y);
-        if (m) {
-          if (row == grow) m = (__float_as_uint(r.w) & 1u) == 0u;
-          else m = rows_equal(A, row, grow);
-        }
-        if (m) {
-          seg_first = j + 1;
-          break;
-        }
-      }
-    }
+    if constexpr (TC > 0) seg_first = tail_scan_window_cold(g, s, grow, tail_last, ep_first, j0, T, o_ret, b);
+    else seg_first = tail_scan_window(g, s, grow, tail_last, ep_first, j0, T, o_ret, b, gsc, gd);
   }
   double gp = 1.0, gi = 1.0, Wsub = 0.0;  // gamma^t, gamma^-t, hits before window row t
   // forward over the window rows: scalar keys (with the hindsight overrides) and the learner aux
@@ -1073,9 +1112,12 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
         if (m) Wsub += gp;
         gp *= g.gamma;
         gi *= g.inv_gamma;
+      } else if constexpr (TC > 0) {  // (cold: see tail_scan_window_cold; the link record carries the same goal-agnostic reward)
+        m = scan_row_matches_cold(g, s, grow, t);
+        v_rew = (float)((double)__ldg(A.link + ring_row32(s, t, cap32)).y + (m ? 0.0 : -1.0));
       } else {
         const float4 r = __ldg(A.scan + ring_row32(s, t, cap32));
-        m = matches(t, r);
+        m = scan_matches(A, s, grow, cap32, gsc, gd, t, r);
         v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
       }
       v_done = m ? 1.f : 0.f;
@@ -1307,11 +1349,11 @@ __device__ __forceinline__ bool elect_one() {  // one lane of the converged warp
 // among the role's `n_warps` warps of the block (taken through a shuffle by the caller: warp-uniform for the compiler, so the stage
 // bookkeeping and the bulk copies use uniform registers); `blk` / `n_blk`: the block's rank among the blocks that share the windows;
 // `bar_id`: 0 = the role is the whole block, otherwise its named barrier.
-template <bool HASH, bool DRAW, int kLeanStageWindows>
+template <bool HASH, bool DRAW, int kLeanStageWindows, int TC = 0, int kStages = 2>
 __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned char* lean_smem, const int wib, const int n_warps,
                                                  const int blk, const int n_blk, const int bar_id) {
   const int lane = lane_id();
-  const int T = g.T;
+  const int T = TC > 0 ? TC : g.T;  // (TC: see window_scalar_phase)
   const int len32 = (int)g.len;
 
   // ---- lane plan: lane = window-in-stage * kParts + part; a lane moves float4 part, part + kParts, ... of every wide key of its
@@ -1322,7 +1364,9 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
   uint32_t wl_u = (uint32_t)wl, part_u = (uint32_t)(lane % kParts), part16 = 16u * part_u;
   asm volatile("" : "+r"(wl_u), "+r"(part_u), "+r"(part16));  // held in registers (the compiler otherwise re-derives them per stage)
   const uint32_t stage_bytes = g.lean_row_bytes * kLeanStageWindows;
-  const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * 2u * stage_bytes;  // two stages per warp
+  // kStages stages per warp: two = the fills of one stage fly while the previous one is written back; one = a stage is filled, then
+  // written back, and the other warps of the role cover its latencies (same shared memory for stages of twice the windows)
+  const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * (uint32_t)kStages * stage_bytes;
 
   const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter, wib * 32 + lane, n_blk, bar_id, n_warps * 32) : 0;
   const int64_t n_windows = g.b_end - g.b_begin;
@@ -1341,7 +1385,7 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
       const int64_t orow = (int64_t)t * g.n + b0;
 #pragma unroll
       for (int k = 0; k < kLeanMaxKeys; ++k) {
-        if (k < g.lean_nk && !(g.dbg & 16)) {
+        if (k < g.lean_nk && !(FDQL_DBG(g) & 16)) {
           const uint32_t row_bytes = 16u * g.lean_key[k].vecs;
           bulk_store_s2g(g.lean_key[k].out + orow * (int64_t)row_bytes, sb + g.lean_key[k].stage_off * kLeanStageWindows, (uint32_t)nw * row_bytes);
         }
@@ -1362,18 +1406,25 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
     const int64_t cb0 = g.b_begin + chunk * 32;
     const int n_here = (int)min((int64_t)32, g.b_end - cb0);
     int s = 0, grow = 0, tail_last = -1;
-    if (g.dbg & 4) {  // probe: the issue load of the scalar phase (~70 warp instructions per window) as a tiny loop of dependent FMAs
+    if (FDQL_DBG(g) & 4) {  // probe: the issue load of the scalar phase (~70 warp instructions per window) as a tiny loop of dependent FMAs
       float x = (float)lane;
+#ifdef FDQL_PROBE_BIGCODE  // the same issue load as straight-line code (35 KB): what the instruction cache costs the co-run
+#pragma unroll
       for (int i = 0; i < 2240; ++i) x = fmaf(x, 1.0001f, 0.5f);
+#else
+#pragma unroll 1
+      for (int i = 0; i < 2240; ++i) x = fmaf(x, 1.0001f, 0.5f);
+#endif
       if (x == 12345.f) g.aux_mask[0] = x;
     }
-    if (g.dbg & 2) s = (int)(((cb0 + lane) * 7919) % (len32 - T));
-    else if (lane < n_here) window_scalar_phase<HASH, DRAW>(g, cb0 + lane, draw_ctr, s, grow, tail_last);
+    if (FDQL_DBG(g) & 2) s = (int)(((cb0 + lane) * 7919) % (len32 - T));
+    else if (lane < n_here) window_scalar_phase<HASH, DRAW, TC>(g, cb0 + lane, draw_ctr, s, grow, tail_last);
     __syncwarp();
-    for (int t = 0; t < ((g.dbg & 1) ? 0 : T); ++t) {
+#pragma unroll 1
+    for (int t = 0; t < ((FDQL_DBG(g) & 1) ? 0 : T); ++t) {
       for (int w0 = 0; w0 < n_here; w0 += kLeanStageWindows, ++it) {
         const int nw = min(kLeanStageWindows, n_here - w0);
-        const uint32_t buf = it & 1u;
+        const uint32_t buf = kStages == 2 ? (it & 1u) : 0u;
         // the bulk write-back that read this buffer (issued one stage ago, for the stage before that) must be done reading it
         if (elect_one()) bulk_wait_group_read<0>();
         __syncwarp();
@@ -1394,7 +1445,7 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
             if (HASH && g.lean_key[k].is_dg && relab) p = g.lean_ag_base + (uint64_t)(unsigned)gw * g.lean_ag_stride;
             p += part16;
             const uint32_t d = dl + g.lean_key[k].stage_off * kLeanStageWindows + wl_u * (16u * g.lean_key[k].vecs);
-            if (!(g.dbg & 8)) {
+            if (!(FDQL_DBG(g) & 8)) {
               // every round is one instruction predicated on "this lane has a float4 in it": no branches inside a stage, except that
               // keys of a single round skip the other slots (measured: a jump table over the round count, and rotating the rounds per
               // window so that the shared-memory writes are conflict free, both made the co-run slower)
@@ -1414,18 +1465,23 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
           }
         }
         cp_async_commit_group();
-        if (it > 0) {  // the previous stage has had a whole stage of issue time to land
-          cp_async_wait_group<1>();
-          finish_stage(buf ^ 1u, p_t, p_b0, p_n);
+        if constexpr (kStages == 1) {
+          cp_async_wait_group<0>();
+          finish_stage(0u, t, cb0 + w0, nw);
+        } else {
+          if (it > 0) {  // the previous stage has had a whole stage of issue time to land
+            cp_async_wait_group<1>();
+            finish_stage(buf ^ 1u, p_t, p_b0, p_n);
+          }
+          p_t = t;
+          p_b0 = cb0 + w0;
+          p_n = nw;
         }
-        p_t = t;
-        p_b0 = cb0 + w0;
-        p_n = nw;
       }
     }
     chunk = wctr != nullptr ? (int64_t)__shfl_sync(kFull, c_next, 0) : chunk + warps_total;
   }
-  if (it > 0) {
+  if (kStages == 2 && it > 0) {
     cp_async_wait_group<0>();
     finish_stage((it - 1) & 1u, p_t, p_b0, p_n);
   }
@@ -1466,7 +1522,11 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
 #ifndef FDQL_FUSED_STAGE_WINDOWS
 #define FDQL_FUSED_STAGE_WINDOWS 8
 #endif
-constexpr int kFusedLossWarps = FDQL_FUSED_LOSS_WARPS, kFusedGatherWarps = FDQL_FUSED_GATHER_WARPS, kFusedStageWindows = FDQL_FUSED_STAGE_WINDOWS;
+#ifndef FDQL_FUSED_STAGES
+#define FDQL_FUSED_STAGES 2
+#endif
+constexpr int kFusedLossWarps = FDQL_FUSED_LOSS_WARPS, kFusedGatherWarps = FDQL_FUSED_GATHER_WARPS, kFusedStageWindows = FDQL_FUSED_STAGE_WINDOWS,
+              kFusedStages = FDQL_FUSED_STAGES;
 #ifdef FDQL_FUSED_ROLE_CLOCK
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -1475,7 +1535,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #endif
 
-template <int FLAGS, bool HASH, bool DRAW>
+template <int FLAGS, bool HASH, bool DRAW, int TC = 0>
 __global__ void __launch_bounds__((kFusedLossWarps + kFusedGatherWarps) * 32, 1)
 fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ TqcArgs a) {
   extern __shared__ __align__(128) unsigned char fused_smem[];
@@ -1511,7 +1571,7 @@ fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ 
     }
 #endif
   } else {
-    gather_lean_body<HASH, DRAW, kFusedStageWindows>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x,
+    gather_lean_body<HASH, DRAW, kFusedStageWindows, TC, kFusedStages>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x,
                                                      (int)gridDim.x, 2);
 #ifdef FDQL_FUSED_ROLE_CLOCK
     asm volatile("bar.sync 2, %0;" ::"r"(kFusedGatherWarps * 32) : "memory");
@@ -1640,7 +1700,7 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
       g.use_link = link_ok64;
       g.log2_gamma = gamma > 0.0 ? log2(gamma) : 0.0;
       g.inv_gamma = gamma > 0.0 ? 1.0 / gamma : 0.0;
-      g.dbg = 0;
+      g.dbg = (g_force_generic_gather >> 6) & 31;  // probe switches, see GatherArgs.dbg (0 outside profiles/)
       TqcArgs t = ta;
       t.grp_red_alias = 1;
       // work counters of this launch: one of kFusedSlots {loss next, loss done, gather next, gather done} quadruples of the arena, taken
@@ -1655,12 +1715,12 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
       g.lean_work_ctr = ws + 2;
 #endif
       const size_t smem = (size_t)kFusedLossWarps * GrpCfg<128>::kWarpFloatsAlias * sizeof(float) +
-                          (size_t)kFusedGatherWarps * 2 * kFusedStageWindows * 16 * wide_vecs;
+                          (size_t)kFusedGatherWarps * kFusedStages * kFusedStageWindows * 16 * wide_vecs;
       const int flags_ = (t.mc_return ? kGrpLb : 0) | (t.stats ? kGrpStats : 0) | kGrpFull;
       if (smem <= 227 * 1024) {
-#define FDQL_LAUNCH_FUSED(FLAGSV, HASHV)                                                                                    \
+#define FDQL_LAUNCH_FUSED(FLAGSV, HASHV, TCV)                                                                               \
   do {                                                                                                                      \
-    auto kern = fused_pass_kernel<FLAGSV, HASHV, true>;                                                                     \
+    auto kern = fused_pass_kernel<FLAGSV, HASHV, true, TCV>;                                                                \
     static size_t smem_set = 0;                                                                                             \
     if (smem_set != smem) {                                                                                                 \
       FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
@@ -1669,17 +1729,21 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     }                                                                                                                       \
     kern<<<(unsigned)a->num_sms, (kFusedLossWarps + kFusedGatherWarps) * 32, smem, st>>>(g, t);                             \
   } while (0)
-#define FDQL_FUSED_FLAGS(HASHV)                               \
+#define FDQL_FUSED_FLAGS(HASHV, TCV)                          \
   do {                                                        \
     switch (flags_) {                                         \
-      case 4: FDQL_LAUNCH_FUSED(4, HASHV); break;             \
-      case 5: FDQL_LAUNCH_FUSED(5, HASHV); break;             \
-      case 6: FDQL_LAUNCH_FUSED(6, HASHV); break;             \
-      default: FDQL_LAUNCH_FUSED(7, HASHV); break;            \
+      case 4: FDQL_LAUNCH_FUSED(4, HASHV, TCV); break;        \
+      case 5: FDQL_LAUNCH_FUSED(5, HASHV, TCV); break;        \
+      case 6: FDQL_LAUNCH_FUSED(6, HASHV, TCV); break;        \
+      default: FDQL_LAUNCH_FUSED(7, HASHV, TCV); break;       \
     }                                                         \
   } while (0)
-        if (hash_ok) FDQL_FUSED_FLAGS(true);
-        else FDQL_FUSED_FLAGS(false);
+        // TD pairs (T = 2: one transition per window, the shape the learner and the headline use) take the build with the window
+        // length, the 8-float scalar record and valid link records known at compile time
+        const bool spec2 = hash_ok && T == 2 && a->dev.rec_stride == 8 && g.use_link && !(g_force_generic_gather & 2048);
+        if (spec2) FDQL_FUSED_FLAGS(true, 2);
+        else if (hash_ok) FDQL_FUSED_FLAGS(true, 0);
+        else FDQL_FUSED_FLAGS(false, 0);
 #undef FDQL_FUSED_FLAGS
 #undef FDQL_LAUNCH_FUSED
         FDQL_CUDA(cudaGetLastError());
@@ -1866,9 +1930,10 @@ int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
   g_tile_override = (on >> 8) & 0x1e0;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
   g_tile_ctas_per_sm = (on >> 20) & 0xf;  // bits 20..23: resident tile-kernel blocks per SM (0 = as many as fit)
-  g_force_generic_gather = on & (509 | (3 << 9));  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
+  g_force_generic_gather = on & (509 | (7 << 9));  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
                                      // bit 3: warp-per-window kernels instead of the tile kernel, bit 4: tile kernel without link records,
-                                     // bit 5: lean kernel (cp.async staging + bulk write-back) wherever it can serve
+                                     // bit 5: lean kernel (cp.async staging + bulk write-back) wherever it can serve,
+                                     // bits 6..10: probe switches (probe builds only), bit 11: fused pass without the T = 2 build
   g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }

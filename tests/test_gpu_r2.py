@@ -541,16 +541,17 @@ def test_coresident_option_selects_the_lean_kernel_and_matches(fdql, obs, act, G
 
 
 # ------------------------------------------------------------------------------------------------ one launch per pass
-@pytest.mark.parametrize("n,T,n_atoms,n_drop,with_lb,with_stats,repeat", [
-    (24576, 2, 125, 10, True, True, 2),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
-    (20000, 2, 125, 10, False, False, 1),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
-    (24576, 2, 100, 8, True, False, 1),    # fused kernel, 100 atoms (4 x 25)
-    (6001, 5, 125, 10, True, True, 1),     # fused kernel, five-row windows (link records), ragged
-    (1024, 50, 125, 10, True, True, 2),    # fused kernel at the reference's default temporal_len (tail scan: windows past the hit mask)
-    (3000, 2, 125, 10, True, True, 1),     # batch too small for the one-block-per-SM form: the two separate launches
-    (24576, 2, 50, 4, True, True, 1),      # 64-entry loss tables: separate launches
+@pytest.mark.parametrize("n,T,n_atoms,n_drop,with_lb,with_stats,repeat,ep_len", [
+    (24576, 2, 125, 10, True, True, 2, 64),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
+    (24576, 2, 125, 10, True, True, 1, 40000),  # episodes without a chain of equal goals (> 32767 rows): the T = 2 build's out-of-line tail scan
+    (20000, 2, 125, 10, False, False, 1, 64),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
+    (24576, 2, 100, 8, True, False, 1, 64),    # fused kernel, 100 atoms (4 x 25)
+    (6001, 5, 125, 10, True, True, 1, 64),     # fused kernel, five-row windows (link records), ragged
+    (1024, 50, 125, 10, True, True, 2, 64),    # fused kernel at the reference's default temporal_len (tail scan: windows past the hit mask)
+    (3000, 2, 125, 10, True, True, 1, 64),     # batch too small for the one-block-per-SM form: the two separate launches
+    (24576, 2, 50, 4, True, True, 1, 64),      # 64-entry loss tables: separate launches
 ])
-def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb, with_stats, repeat):
+def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb, with_stats, repeat, ep_len):
     """fdql_fused_pass (loss of batch k + gather of batch k+1 in one warp-specialised launch) against fdql_sample_gather_draw and
     fdql_tqc_loss as separate launches on the same arguments: bit-identical batch, loss, gradient; summaries to fp64 rounding.  The
     loss half reads the PREVIOUS gather's reward / mask / mc_return / weight (other buffers), as the learner loop does."""
@@ -560,7 +561,7 @@ def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb
     from test_gpu_replay import _synthetic
     G = 16
     rng = np.random.default_rng(5 + n)
-    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 600, 0, G, obs=64, act=8, fixed_len=64)
+    cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 600 * 64 // ep_len + 1, 0, G, obs=64, act=8, fixed_len=ep_len)
     N = int(lengths.sum())
     ring = Replay.ReplayMemory(N + 1, 4096, T)
     ring.set_reward_op(fdql.RewardOp.bitflip(), 0.99)
