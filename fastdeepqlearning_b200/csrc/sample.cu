@@ -1345,11 +1345,44 @@ __device__ __forceinline__ bool elect_one() {  // one lane of the converged warp
 #ifndef FDQL_LEAN_MAXVECS
 #define FDQL_LEAN_MAXVECS 32
 #endif
+// 16-byte asynchronous copy predicated on `on` (a predicated instruction, never a branch: every basic block that holds an LDGSTS
+// starts with three dummy LDS on sm_100a, so the copies of a stage want to sit in ONE block)
+__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, bool on) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}" ::"r"(dst), "l"(src),
+               "r"((uint32_t)on)
+               : "memory");
+}
+// Copy plan known at compile time (PLAN != 0): hex digit k (most significant first) = copy rounds of wide key k = ceil(vecs / kParts),
+// 0 = no such key.  The fills of one key of a stage, straight-line: all rounds but the last are whole (every lane has a float4 in
+// them), the last one is predicated.
+template <int ROUNDS, bool HASH, int kParts, int kLeanStageWindows>
+__device__ __forceinline__ void lean_fill_key(const GatherArgs& g, const int k, const unsigned row, const unsigned gw, const bool relab,
+                                              const uint32_t dl, const uint32_t wl_u, const uint32_t part_u, const uint32_t part16) {
+  if constexpr (ROUNDS > 0) {
+    const GatherArgs::LeanKey& K = g.lean_key[k];
+    const char* p = K.base + (uint64_t)row * K.stride;
+    if (HASH && K.is_dg && relab) p = g.lean_ag_base + (uint64_t)gw * g.lean_ag_stride;
+    p += part16;
+    const uint32_t d = dl + K.stage_off * kLeanStageWindows + wl_u * (16u * K.vecs);
+#pragma unroll
+    for (int j = 0; j < ROUNDS - 1; ++j) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
+    cp_async16_if(d + 16u * kParts * (ROUNDS - 1), p + 16 * kParts * (ROUNDS - 1), (uint32_t)((ROUNDS - 1) * kParts) + part_u < K.vecs);
+  }
+}
+// (the launcher takes a compiled plan only when T * n * 16 * vecs fits 32 bits: the output offset is then one 32 x 32 -> 64 multiply-add)
+template <int ROUNDS, int kLeanStageWindows>
+__device__ __forceinline__ void lean_store_key(const GatherArgs& g, const int k, const uint32_t orow, const uint32_t sb, const uint32_t nw) {
+  if constexpr (ROUNDS > 0) {
+    const GatherArgs::LeanKey& K = g.lean_key[k];
+    const uint32_t row_bytes = 16u * K.vecs;
+    bulk_store_s2g(K.out + orow * row_bytes, sb + K.stage_off * kLeanStageWindows, nw * row_bytes);
+  }
+}
 // The kernel body as a device function (stand-alone kernel below; gather role of the fused pass kernel).  `wib`: this warp's index
 // among the role's `n_warps` warps of the block (taken through a shuffle by the caller: warp-uniform for the compiler, so the stage
 // bookkeeping and the bulk copies use uniform registers); `blk` / `n_blk`: the block's rank among the blocks that share the windows;
 // `bar_id`: 0 = the role is the whole block, otherwise its named barrier.
-template <bool HASH, bool DRAW, int kLeanStageWindows, int TC = 0, int kStages = 2>
+template <bool HASH, bool DRAW, int kLeanStageWindows, int TC = 0, int kStages = 2, int PLAN = 0>
 __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned char* lean_smem, const int wib, const int n_warps,
                                                  const int blk, const int n_blk, const int bar_id) {
   const int lane = lane_id();
@@ -1383,6 +1416,13 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
     if (elect_one()) {  // one bulk copy per key: its rows are contiguous in the stage and in the time-major output
       const uint32_t sb = warp_smem + buf * stage_bytes;
       const int64_t orow = (int64_t)t * g.n + b0;
+      if constexpr (PLAN != 0) {
+        const uint32_t orow32 = (uint32_t)t * (uint32_t)g.n + (uint32_t)b0;
+        lean_store_key<(PLAN >> 12) & 15, kLeanStageWindows>(g, 0, orow32, sb, (uint32_t)nw);
+        lean_store_key<(PLAN >> 8) & 15, kLeanStageWindows>(g, 1, orow32, sb, (uint32_t)nw);
+        lean_store_key<(PLAN >> 4) & 15, kLeanStageWindows>(g, 2, orow32, sb, (uint32_t)nw);
+        lean_store_key<PLAN & 15, kLeanStageWindows>(g, 3, orow32, sb, (uint32_t)nw);
+      } else
 #pragma unroll
       for (int k = 0; k < kLeanMaxKeys; ++k) {
         if (k < g.lean_nk && !(FDQL_DBG(g) & 16)) {
@@ -1438,6 +1478,12 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
         if (row >= (unsigned)len32) row -= (unsigned)len32;
         const bool relab = HASH && t <= tlw;
         const uint32_t dl = warp_smem + buf * stage_bytes + part16;
+        if constexpr (PLAN != 0) {
+          lean_fill_key<(PLAN >> 12) & 15, HASH, kParts, kLeanStageWindows>(g, 0, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
+          lean_fill_key<(PLAN >> 8) & 15, HASH, kParts, kLeanStageWindows>(g, 1, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
+          lean_fill_key<(PLAN >> 4) & 15, HASH, kParts, kLeanStageWindows>(g, 2, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
+          lean_fill_key<PLAN & 15, HASH, kParts, kLeanStageWindows>(g, 3, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
+        } else
 #pragma unroll
         for (int k = 0; k < kLeanMaxKeys; ++k) {
           if (k < g.lean_nk) {
@@ -1525,6 +1571,9 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
 #ifndef FDQL_FUSED_STAGES
 #define FDQL_FUSED_STAGES 2
 #endif
+#ifndef FDQL_FUSED_PLAN
+#define FDQL_FUSED_PLAN 0x4111  // the copy plan compiled into the T = 2 build of the fused pass (see gather_lean_body)
+#endif
 constexpr int kFusedLossWarps = FDQL_FUSED_LOSS_WARPS, kFusedGatherWarps = FDQL_FUSED_GATHER_WARPS, kFusedStageWindows = FDQL_FUSED_STAGE_WINDOWS,
               kFusedStages = FDQL_FUSED_STAGES;
 #ifdef FDQL_FUSED_ROLE_CLOCK
@@ -1535,7 +1584,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #endif
 
-template <int FLAGS, bool HASH, bool DRAW, int TC = 0>
+template <int FLAGS, bool HASH, bool DRAW, int TC = 0, int PLAN = 0>
 __global__ void __launch_bounds__((kFusedLossWarps + kFusedGatherWarps) * 32, 1)
 fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ TqcArgs a) {
   extern __shared__ __align__(128) unsigned char fused_smem[];
@@ -1571,7 +1620,7 @@ fused_pass_kernel(const __grid_constant__ GatherArgs g, const __grid_constant__ 
     }
 #endif
   } else {
-    gather_lean_body<HASH, DRAW, kFusedStageWindows, TC, kFusedStages>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x,
+    gather_lean_body<HASH, DRAW, kFusedStageWindows, TC, kFusedStages, PLAN>(g, fused_smem + kLossBytes, w - kFusedLossWarps, kFusedGatherWarps, (int)blockIdx.x,
                                                      (int)gridDim.x, 2);
 #ifdef FDQL_FUSED_ROLE_CLOCK
     asm volatile("bar.sync 2, %0;" ::"r"(kFusedGatherWarps * 32) : "memory");
@@ -1718,9 +1767,9 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
                           (size_t)kFusedGatherWarps * kFusedStages * kFusedStageWindows * 16 * wide_vecs;
       const int flags_ = (t.mc_return ? kGrpLb : 0) | (t.stats ? kGrpStats : 0) | kGrpFull;
       if (smem <= 227 * 1024) {
-#define FDQL_LAUNCH_FUSED(FLAGSV, HASHV, TCV)                                                                               \
+#define FDQL_LAUNCH_FUSED(FLAGSV, HASHV, TCV, PLANV)                                                                        \
   do {                                                                                                                      \
-    auto kern = fused_pass_kernel<FLAGSV, HASHV, true, TCV>;                                                                \
+    auto kern = fused_pass_kernel<FLAGSV, HASHV, true, TCV, PLANV>;                                                         \
     static size_t smem_set = 0;                                                                                             \
     if (smem_set != smem) {                                                                                                 \
       FDQL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
@@ -1729,21 +1778,28 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
     }                                                                                                                       \
     kern<<<(unsigned)a->num_sms, (kFusedLossWarps + kFusedGatherWarps) * 32, smem, st>>>(g, t);                             \
   } while (0)
-#define FDQL_FUSED_FLAGS(HASHV, TCV)                          \
-  do {                                                        \
-    switch (flags_) {                                         \
-      case 4: FDQL_LAUNCH_FUSED(4, HASHV, TCV); break;        \
-      case 5: FDQL_LAUNCH_FUSED(5, HASHV, TCV); break;        \
-      case 6: FDQL_LAUNCH_FUSED(6, HASHV, TCV); break;        \
-      default: FDQL_LAUNCH_FUSED(7, HASHV, TCV); break;       \
-    }                                                         \
+#define FDQL_FUSED_FLAGS(HASHV, TCV, PLANV)                          \
+  do {                                                               \
+    switch (flags_) {                                                \
+      case 4: FDQL_LAUNCH_FUSED(4, HASHV, TCV, PLANV); break;        \
+      case 5: FDQL_LAUNCH_FUSED(5, HASHV, TCV, PLANV); break;        \
+      case 6: FDQL_LAUNCH_FUSED(6, HASHV, TCV, PLANV); break;        \
+      default: FDQL_LAUNCH_FUSED(7, HASHV, TCV, PLANV); break;       \
+    }                                                                \
   } while (0)
         // TD pairs (T = 2: one transition per window, the shape the learner and the headline use) take the build with the window
         // length, the 8-float scalar record and valid link records known at compile time
         const bool spec2 = hash_ok && T == 2 && a->dev.rec_stride == 8 && g.use_link && !(g_force_generic_gather & 2048);
-        if (spec2) FDQL_FUSED_FLAGS(true, 2);
-        else if (hash_ok) FDQL_FUSED_FLAGS(true, 0);
-        else FDQL_FUSED_FLAGS(false, 0);
+        // copy plan of the gather role: rounds per wide key (hex digits), compiled for one long vector plus up to three vectors of
+        // one round each (an observation next to action / goals of <= 16 floats); any other layout runs the run-time plan
+        unsigned plan = 0;
+        for (int k = 0; k < kLeanMaxKeys; ++k)
+          plan = (plan << 4) | (k < g.lean_nk ? (g.lean_key[k].vecs + (32 / kFusedStageWindows) - 1) / (32 / kFusedStageWindows) : 0u);
+        const bool out32 = (uint64_t)T * (uint64_t)n * 16u * FDQL_LEAN_MAXVECS < (1ull << 32);  // (see lean_store_key)
+        if (spec2 && out32 && plan == FDQL_FUSED_PLAN && !(g_force_generic_gather & 4096)) FDQL_FUSED_FLAGS(true, 2, FDQL_FUSED_PLAN);
+        else if (spec2) FDQL_FUSED_FLAGS(true, 2, 0);
+        else if (hash_ok) FDQL_FUSED_FLAGS(true, 0, 0);
+        else FDQL_FUSED_FLAGS(false, 0, 0);
 #undef FDQL_FUSED_FLAGS
 #undef FDQL_LAUNCH_FUSED
         FDQL_CUDA(cudaGetLastError());
@@ -1930,10 +1986,10 @@ int fdql_debug_force_generic_gather(int on) {
   const int old = g_force_generic_gather | (g_force_full_vector_relabel << 1);
   g_tile_override = (on >> 8) & 0x1e0;  // bits 8..16: tile size override (32/64/128/256), 0 = automatic
   g_tile_ctas_per_sm = (on >> 20) & 0xf;  // bits 20..23: resident tile-kernel blocks per SM (0 = as many as fit)
-  g_force_generic_gather = on & (509 | (7 << 9));  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
+  g_force_generic_gather = on & (509 | (15 << 9));  // bit 0: descriptor-walking kernel, bit 2: per-pass suffix scan instead of Horner,
                                      // bit 3: warp-per-window kernels instead of the tile kernel, bit 4: tile kernel without link records,
                                      // bit 5: lean kernel (cp.async staging + bulk write-back) wherever it can serve,
-                                     // bits 6..10: probe switches (probe builds only), bit 11: fused pass without the T = 2 build
+                                     // bits 6..10: probe switches (probe builds only), bit 11: fused pass without the T = 2 build, bit 12: without the compiled copy plan
   g_force_full_vector_relabel = (on >> 1) & 1;
   return old;
 }
