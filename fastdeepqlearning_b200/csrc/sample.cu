@@ -52,6 +52,9 @@ __device__ __forceinline__ float pick8(const float (&r)[8], int c) {  // r[c] fo
 
 // one window's streams: start ~ U[0, range), flag ~ Bernoulli(p) (never for rows of uncommitted episodes), goal row by mode
 // (rec8: when given, the start row's scalar record is 8 floats wide and is returned whole for the caller's own use)
+// record columns of the builds specialised on a window length (window_scalar_phase, TC > 0)
+constexpr int kCanonReward = 0, kCanonTaskDone = 1, kCanonEpStep = 3, kCanonMcReturn = 4, kCanonScal = 5, kCanonEpStart = 5, kCanonEpEnd = 6;
+template <int TC = 0>
 __device__ __forceinline__ void draw_window(const ArenaDev& A, int64_t b, int64_t range, int goal_mode, float relabel_prob, uint64_t seed,
                                             uint64_t counter, bool want_flags, int64_t& s, bool& f, int64_t& g, int& es, int& ee,
                                             float (*rec8)[8] = nullptr) {
@@ -66,8 +69,8 @@ __device__ __forceinline__ void draw_window(const ArenaDev& A, int64_t b, int64_
   const float* rec = A.rec + s * (int64_t)A.rec_stride;
   if (rec8 != nullptr) {
     ld_rec8(rec, *rec8);
-    es = __float_as_int(pick8(*rec8, A.col_ep_start));
-    ee = __float_as_int(pick8(*rec8, A.col_ep_end));
+    es = __float_as_int(pick8(*rec8, TC > 0 ? kCanonEpStart : A.col_ep_start));
+    ee = __float_as_int(pick8(*rec8, TC > 0 ? kCanonEpEnd : A.col_ep_end));
   } else {
     es = __float_as_int(__ldg(rec + A.col_ep_start));
     ee = __float_as_int(__ldg(rec + A.col_ep_end));
@@ -994,6 +997,12 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
   int tail_last = -1, ep_first = 0, grow = 0;
   // 8-float scalar records (<= 6 scalar keys + the two extents) travel whole, one 256-bit load per row
   const bool vec8 = TC > 0 ? true : A.rec_stride == 8;
+  // TC > 0 also fixes the record columns (the launcher checks them): the reference's transition keys in their usual order
+  // {reward, task_done, episode_done, episode_step, mc_return} followed by the two episode extents -- the column picks out of the
+  // 8-float record and the per-key stores then need no select chains
+  const int n_scal = TC > 0 ? kCanonScal : A.n_scal;
+  const int col_reward = TC > 0 ? kCanonReward : A.col_reward, col_task_done = TC > 0 ? kCanonTaskDone : A.col_task_done;
+  const int col_ep_step = TC > 0 ? kCanonEpStep : A.col_ep_step, col_mc_return = TC > 0 ? kCanonMcReturn : A.col_mc_return;
   float rv0[8];
   bool have0 = false;
   if (DRAW) {  // fused draw: same generator, same streams as sample_streams_kernel
@@ -1001,8 +1010,8 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
     bool f;
     int es, ee;
     have0 = HASH && vec8;
-    draw_window(A, b, device_draw_range(g.counter_dev, g.draw_range, T), g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64,
-                es, ee, have0 ? &rv0 : nullptr);
+    draw_window<TC>(A, b, device_draw_range(g.counter_dev, g.draw_range, T), g.goal_mode, g.relabel_prob, g.seed, draw_ctr, HASH, s64, f, g64,
+                    es, ee, have0 ? &rv0 : nullptr);
     if (g.starts_out) g.starts_out[b] = s64;
     if (g.flags_out) g.flags_out[b] = f ? 1 : 0;
     if (g.goal_out) g.goal_out[b] = g64;
@@ -1030,7 +1039,7 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
   s_out = s;
   grow_out = grow;
   tail_out = tail_last;
-  float* o_ret = A.col_mc_return >= 0 ? g.out.p[A.scal_key[A.col_mc_return]] : nullptr;
+  float* o_ret = col_mc_return >= 0 ? g.out.p[A.scal_key[col_mc_return]] : nullptr;
 
   float4 gsc = zero4;
   int gd = -1;
@@ -1099,8 +1108,8 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
         ld_rec8(rec, rv);
       }
     }
-    float v_step = A.col_ep_step >= 0 ? (vec8 ? pick8(rv, A.col_ep_step) : __ldg(rec + A.col_ep_step)) : 0.f;
-    float v_done = A.col_task_done >= 0 ? (vec8 ? pick8(rv, A.col_task_done) : __ldg(rec + A.col_task_done)) : 0.f;
+    float v_step = col_ep_step >= 0 ? (vec8 ? pick8(rv, col_ep_step) : __ldg(rec + col_ep_step)) : 0.f;
+    float v_done = col_task_done >= 0 ? (vec8 ? pick8(rv, col_task_done) : __ldg(rec + col_task_done)) : 0.f;
     float v_rew = 0.f;
     if (in_ep) {
       bool m;
@@ -1121,33 +1130,33 @@ __device__ __forceinline__ void window_scalar_phase(const GatherArgs& g, int64_t
         v_rew = (float)((double)r.z + (m ? 0.0 : -1.0));
       }
       v_done = m ? 1.f : 0.f;
-      if (seg_first >= 0 && A.col_ep_step >= 0)
-        v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + A.col_ep_step);
+      if (seg_first >= 0 && col_ep_step >= 0)
+        v_step -= __ldg(A.rec + (int64_t)ring_row32(ep_first, seg_first, cap32) * A.rec_stride + col_ep_step);
       if (m) seg_first = j0 + t + 1;
     }
     if (vec8) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        if (c >= A.n_scal) break;
+        if (c >= n_scal) break;
         float* o = g.out.p[A.scal_key[c]];
         if (o == nullptr) continue;
         float val;
-        if (c == A.col_ep_step) val = v_step;
-        else if (c == A.col_task_done) val = v_done;
-        else if (in_ep && c == A.col_reward) val = v_rew;
-        else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
+        if (c == col_ep_step) val = v_step;
+        else if (c == col_task_done) val = v_done;
+        else if (in_ep && c == col_reward) val = v_rew;
+        else if (in_ep && c == col_mc_return) continue;  // written by the return recurrence above
         else val = rv[c];
         st_stream1(o + (int64_t)t * g.n + b, val);
       }
     } else {
-      for (int c = 0; c < A.n_scal; ++c) {
+      for (int c = 0; c < n_scal; ++c) {
         float* o = g.out.p[A.scal_key[c]];
         if (o == nullptr) continue;
         float val;
-        if (c == A.col_ep_step) val = v_step;
-        else if (c == A.col_task_done) val = v_done;
-        else if (in_ep && c == A.col_reward) val = v_rew;
-        else if (in_ep && c == A.col_mc_return) continue;  // written by the return recurrence above
+        if (c == col_ep_step) val = v_step;
+        else if (c == col_task_done) val = v_done;
+        else if (in_ep && c == col_reward) val = v_rew;
+        else if (in_ep && c == col_mc_return) continue;  // written by the return recurrence above
         else val = __ldg(rec + c);
         st_stream1(o + (int64_t)t * g.n + b, val);
       }
@@ -1789,7 +1798,11 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
   } while (0)
         // TD pairs (T = 2: one transition per window, the shape the learner and the headline use) take the build with the window
         // length, the 8-float scalar record and valid link records known at compile time
-        const bool spec2 = hash_ok && T == 2 && a->dev.rec_stride == 8 && g.use_link && !(g_force_generic_gather & 2048);
+        const ArenaDev& D = a->dev;
+        const bool canon = D.rec_stride == 8 && D.n_scal == kCanonScal && D.col_reward == kCanonReward && D.col_task_done == kCanonTaskDone &&
+                           D.col_ep_step == kCanonEpStep && D.col_mc_return == kCanonMcReturn && D.col_ep_start == kCanonEpStart &&
+                           D.col_ep_end == kCanonEpEnd;
+        const bool spec2 = hash_ok && T == 2 && canon && g.use_link && !(g_force_generic_gather & 2048);
         // copy plan of the gather role: rounds per wide key (hex digits), compiled for one long vector plus up to three vectors of
         // one round each (an observation next to action / goals of <= 16 floats); any other layout runs the run-time plan
         unsigned plan = 0;
