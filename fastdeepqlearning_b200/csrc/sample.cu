@@ -1361,18 +1361,18 @@ __device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, boo
                "r"((uint32_t)on)
                : "memory");
 }
-// Copy plan known at compile time (PLAN != 0): hex digit k (most significant first) = copy rounds of wide key k = ceil(vecs / kParts),
-// 0 = no such key.  The fills of one key of a stage, straight-line: all rounds but the last are whole (every lane has a float4 in
+// Copy plan known at compile time (PLAN != 0): hex digits 3..0 = copy rounds of wide keys 0..3 = ceil(vecs / kParts), 0 = no such
+// key; digit 4 = index of the desired_goal key + 1 (0 = none).  The fills of one key of a stage, straight-line: all rounds but the last are whole (every lane has a float4 in
 // them), the last one is predicated.
-template <int ROUNDS, bool HASH, int kParts, int kLeanStageWindows>
+template <int ROUNDS, bool HASH, bool IS_DG, int kParts, int kLeanStageWindows>
 __device__ __forceinline__ void lean_fill_key(const GatherArgs& g, const int k, const unsigned row, const unsigned gw, const bool relab,
-                                              const uint32_t dl, const uint32_t wl_u, const uint32_t part_u, const uint32_t part16) {
+                                              const uint32_t dl, const uint32_t wl16, const uint32_t part_u, const uint32_t part16) {
   if constexpr (ROUNDS > 0) {
     const GatherArgs::LeanKey& K = g.lean_key[k];
     const char* p = K.base + (uint64_t)row * K.stride;
-    if (HASH && K.is_dg && relab) p = g.lean_ag_base + (uint64_t)gw * g.lean_ag_stride;
+    if (HASH && IS_DG && relab) p = g.lean_ag_base + (uint64_t)gw * g.lean_ag_stride;  // (the plan names the desired_goal key)
     p += part16;
-    const uint32_t d = dl + K.stage_off * kLeanStageWindows + wl_u * (16u * K.vecs);
+    const uint32_t d = wl16 * K.vecs + (dl + K.stage_off * kLeanStageWindows);
 #pragma unroll
     for (int j = 0; j < ROUNDS - 1; ++j) cp_async16(d + 16u * kParts * j, p + 16 * kParts * j);
     cp_async16_if(d + 16u * kParts * (ROUNDS - 1), p + 16 * kParts * (ROUNDS - 1), (uint32_t)((ROUNDS - 1) * kParts) + part_u < K.vecs);
@@ -1383,8 +1383,9 @@ template <int ROUNDS, int kLeanStageWindows>
 __device__ __forceinline__ void lean_store_key(const GatherArgs& g, const int k, const uint32_t orow, const uint32_t sb, const uint32_t nw) {
   if constexpr (ROUNDS > 0) {
     const GatherArgs::LeanKey& K = g.lean_key[k];
-    const uint32_t row_bytes = 16u * K.vecs;
-    bulk_store_s2g(K.out + orow * row_bytes, sb + K.stage_off * kLeanStageWindows, nw * row_bytes);
+    const uint32_t row_bytes = 16u * K.vecs, units = nw * K.vecs;  // (units: the copy size in 16-byte units, as the instruction wants it)
+    __builtin_assume(units < (1u << 20));
+    bulk_store_s2g(K.out + orow * row_bytes, sb + K.stage_off * kLeanStageWindows, units << 4);
   }
 }
 // The kernel body as a device function (stand-alone kernel below; gather role of the fused pass kernel).  `wib`: this warp's index
@@ -1408,7 +1409,8 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
   const uint32_t stage_bytes = g.lean_row_bytes * kLeanStageWindows;
   // kStages stages per warp: two = the fills of one stage fly while the previous one is written back; one = a stage is filled, then
   // written back, and the other warps of the role cover its latencies (same shared memory for stages of twice the windows)
-  const uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * (uint32_t)kStages * stage_bytes;
+  uint32_t warp_smem = (uint32_t)__cvta_generic_to_shared(lean_smem) + (uint32_t)wib * (uint32_t)kStages * stage_bytes;
+  if constexpr (PLAN != 0) asm volatile("" : "+r"(warp_smem));  // kept in a register (otherwise re-derived from the CTA id in every stage)
 
   const uint64_t draw_ctr = DRAW ? device_draw_counter(g.counter_dev, g.counter, wib * 32 + lane, n_blk, bar_id, n_warps * 32) : 0;
   const int64_t n_windows = g.b_end - g.b_begin;
@@ -1488,10 +1490,12 @@ __device__ __forceinline__ void gather_lean_body(const GatherArgs& g, unsigned c
         const bool relab = HASH && t <= tlw;
         const uint32_t dl = warp_smem + buf * stage_bytes + part16;
         if constexpr (PLAN != 0) {
-          lean_fill_key<(PLAN >> 12) & 15, HASH, kParts, kLeanStageWindows>(g, 0, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
-          lean_fill_key<(PLAN >> 8) & 15, HASH, kParts, kLeanStageWindows>(g, 1, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
-          lean_fill_key<(PLAN >> 4) & 15, HASH, kParts, kLeanStageWindows>(g, 2, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
-          lean_fill_key<PLAN & 15, HASH, kParts, kLeanStageWindows>(g, 3, row, (unsigned)gw, relab, dl, wl_u, part_u, part16);
+          constexpr int kDg = ((PLAN >> 16) & 7) - 1;  // which key is desired_goal (-1: none)
+          const uint32_t wl16 = 16u * wl_u;
+          lean_fill_key<(PLAN >> 12) & 15, HASH, kDg == 0, kParts, kLeanStageWindows>(g, 0, row, (unsigned)gw, relab, dl, wl16, part_u, part16);
+          lean_fill_key<(PLAN >> 8) & 15, HASH, kDg == 1, kParts, kLeanStageWindows>(g, 1, row, (unsigned)gw, relab, dl, wl16, part_u, part16);
+          lean_fill_key<(PLAN >> 4) & 15, HASH, kDg == 2, kParts, kLeanStageWindows>(g, 2, row, (unsigned)gw, relab, dl, wl16, part_u, part16);
+          lean_fill_key<PLAN & 15, HASH, kDg == 3, kParts, kLeanStageWindows>(g, 3, row, (unsigned)gw, relab, dl, wl16, part_u, part16);
         } else
 #pragma unroll
         for (int k = 0; k < kLeanMaxKeys; ++k) {
@@ -1581,7 +1585,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 5) sample_gather_lean_kernel(
 #define FDQL_FUSED_STAGES 2
 #endif
 #ifndef FDQL_FUSED_PLAN
-#define FDQL_FUSED_PLAN 0x4111  // the copy plan compiled into the T = 2 build of the fused pass (see gather_lean_body)
+#define FDQL_FUSED_PLAN 0x44111  // the copy plan compiled into the T = 2 build of the fused pass (see gather_lean_body)
 #endif
 constexpr int kFusedLossWarps = FDQL_FUSED_LOSS_WARPS, kFusedGatherWarps = FDQL_FUSED_GATHER_WARPS, kFusedStageWindows = FDQL_FUSED_STAGE_WINDOWS,
               kFusedStages = FDQL_FUSED_STAGES;
@@ -1805,9 +1809,12 @@ int launch_gather(const fdql_arena* a, int64_t n, int64_t b_begin, int64_t b_end
         const bool spec2 = hash_ok && T == 2 && canon && g.use_link && !(g_force_generic_gather & 2048);
         // copy plan of the gather role: rounds per wide key (hex digits), compiled for one long vector plus up to three vectors of
         // one round each (an observation next to action / goals of <= 16 floats); any other layout runs the run-time plan
-        unsigned plan = 0;
-        for (int k = 0; k < kLeanMaxKeys; ++k)
+        unsigned plan = 0, dg_key = 0;
+        for (int k = 0; k < kLeanMaxKeys; ++k) {
           plan = (plan << 4) | (k < g.lean_nk ? (g.lean_key[k].vecs + (32 / kFusedStageWindows) - 1) / (32 / kFusedStageWindows) : 0u);
+          if (k < g.lean_nk && g.lean_key[k].is_dg) dg_key = (unsigned)k + 1u;
+        }
+        plan |= dg_key << 16;  // (digit 4: the desired_goal key + 1, 0 = none)
         const bool out32 = (uint64_t)T * (uint64_t)n * 16u * FDQL_LEAN_MAXVECS < (1ull << 32);  // (see lean_store_key)
         if (spec2 && out32 && plan == FDQL_FUSED_PLAN && !(g_force_generic_gather & 4096)) FDQL_FUSED_FLAGS(true, 2, FDQL_FUSED_PLAN);
         else if (spec2) FDQL_FUSED_FLAGS(true, 2, 0);
