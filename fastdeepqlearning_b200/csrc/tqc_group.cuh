@@ -326,11 +326,10 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
   double st_sum = 0.0, st_var = 0.0;
   int viol = 0;
   // phase B constants of this lane: :98, tau over the pooled atoms: fl32(fl32(j / n) + fl32(1/2/n)) for j = lane + 32 s
-  float taus[R], omts[R], validf[R];
+  float taus[R], validf[R];
 #pragma unroll
   for (int s = 0; s < R; ++s) {
     taus[s] = __fadd_rn(__fdiv_rn((float)(lane + 32 * s), (float)n), half_over_n);
-    omts[s] = 1.f - taus[s];
     validf[s] = lane + 32 * s < n ? 1.f : 0.f;
   }
   // phase A constants
@@ -593,10 +592,10 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
         const float kc = Kf - ic;
         const float neg = fmaf(0.5f, Fb - Fa, fmaf(-0.5f, ia, La));       // delta < 0 : weight 1 - tau
         const float pos = fmaf(0.5f, Fc - Fb, fmaf(-0.5f, kc, Lc - LK));  // delta >= 0: weight tau
-        const float lj = fmaf(omts[s], neg, taus[s] * pos);
+        const float lj = fmaf(taus[s], pos - neg, neg);  // (1 - tau) neg + tau pos, without a register for 1 - tau
         const float gneg = ia + (Lb - La);
         const float gpos = (Lc - Lb) - kc;
-        const float gj = fmaf(omts[s], gneg, taus[s] * gpos);
+        const float gj = fmaf(taus[s], gpos - gneg, gneg);
         float gl = 0.f;
         if constexpr (LB) {  // :76-79 lower bound relu(mc_return - q)
           const float lbj = fmaxf(Gc - qc, 0.f);
