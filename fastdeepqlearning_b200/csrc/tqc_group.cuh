@@ -183,6 +183,40 @@ __device__ __forceinline__ void grp_search_top2(uint32_t& addr, float x, float p
                  : "+r"(addr)
                  : "f"(x), "f"(piv1), "f"(piv2lo), "f"(piv2hi), "r"(one), "n"(ADV1), "n"(ADV2));
 }
+// The same two functions on byte offsets RELATIVE to the table (`base` = the table's shared-memory address, warp-uniform: the probe
+// address base + offset + constant goes into the load's [register + uniform register + immediate] form, so the offset costs no
+// instruction; the search then starts without a copy of the base and ends without subtracting it again).
+template <int R, int STEP, bool LE>
+__device__ __forceinline__ void grp_search_steps_rel(uint32_t& off, uint32_t base, float x, uint32_t one) {
+  constexpr int kProbe = STEP >= R ? (R - 1) * 32 + STEP / R - 1 : (STEP - 1) * 32;
+  constexpr int kAdvance = STEP >= R ? STEP / R : STEP * 32;
+  if constexpr (LE)
+    asm volatile("{\n .reg .pred p;\n .reg .f32 v;\n .reg .u32 a;\n add.u32 a, %0, %5;\n ld.shared.f32 v, [a+%3];\n setp.le.f32 p, v, %1;\n"
+                 " @p mad.lo.u32 %0, %2, %4, %0;\n}"
+                 : "+r"(off)
+                 : "f"(x), "r"(one), "n"(4 * kProbe), "n"(4 * kAdvance), "r"(base));
+  else
+    asm volatile("{\n .reg .pred p;\n .reg .f32 v;\n .reg .u32 a;\n add.u32 a, %0, %5;\n ld.shared.f32 v, [a+%3];\n setp.lt.f32 p, v, %1;\n"
+                 " @p mad.lo.u32 %0, %2, %4, %0;\n}"
+                 : "+r"(off)
+                 : "f"(x), "r"(one), "n"(4 * kProbe), "n"(4 * kAdvance), "r"(base));
+  if constexpr (STEP > 1) grp_search_steps_rel<R, STEP / 2, LE>(off, base, x, one);
+}
+template <int ADV1, int ADV2, bool LE>
+__device__ __forceinline__ uint32_t grp_search_top2_rel(float x, float piv1, float piv2lo, float piv2hi, uint32_t one) {
+  uint32_t off;
+  if constexpr (LE)
+    asm volatile("{\n .reg .pred p, q;\n .reg .f32 v;\n setp.le.f32 p, %2, %1;\n selp.f32 v, %4, %3, p;\n selp.u32 %0, %6, 0, p;\n"
+                 " setp.le.f32 q, v, %1;\n @q mad.lo.u32 %0, %5, %7, %0;\n}"
+                 : "=&r"(off)
+                 : "f"(x), "f"(piv1), "f"(piv2lo), "f"(piv2hi), "r"(one), "n"(ADV1), "n"(ADV2));
+  else
+    asm volatile("{\n .reg .pred p, q;\n .reg .f32 v;\n setp.lt.f32 p, %2, %1;\n selp.f32 v, %4, %3, p;\n selp.u32 %0, %6, 0, p;\n"
+                 " setp.lt.f32 q, v, %1;\n @q mad.lo.u32 %0, %5, %7, %0;\n}"
+                 : "=&r"(off)
+                 : "f"(x), "f"(piv1), "f"(piv2lo), "f"(piv2hi), "r"(one), "n"(ADV1), "n"(ADV2));
+  return off;
+}
 // byte offset 4*phys -> sorted index: phys = row * 32 + col, i = col * R + row
 // (o = 128 row + 4 col  ->  i = o R / 4 - (32 R - 1) row, written as multiply-high / multiply-add so that it runs down the FMA
 // pipe: the ALU pipe is the busier one in this kernel)
@@ -567,6 +601,20 @@ __device__ __forceinline__ void tqc_group_body(const TqcArgs& a, float* grp_smem
         const bool ok = (FULL && s < R - 1) ? true : validf[s] != 0.f;
         const float qc = ok ? qrow[32 * s] - c0 : 0.f;
         uint32_t oa = aYt, ob = aYt, oc = aYt;
+#ifndef FDQL_TQC_ABS_SEARCH
+        if constexpr (NT >= 128) {  // (offsets relative to the table: see grp_search_steps_rel)
+          const float xa = qc - 1.f, xc = qc + 1.f;
+          oa = grp_search_top2_rel<kAdv1, kAdv2, false>(xa, piv1, piv2lo, piv2hi, one);
+          ob = grp_search_top2_rel<kAdv1, kAdv2, false>(qc, piv1, piv2lo, piv2hi, one);
+          oc = grp_search_top2_rel<kAdv1, kAdv2, true>(xc, piv1, piv2lo, piv2hi, one);
+          grp_search_steps_rel<R, NT / 8, false>(oa, aYt, xa, one);  // a = #(y < q-1)
+          grp_search_steps_rel<R, NT / 8, false>(ob, aYt, qc, one);  // b = #(y < q)
+          grp_search_steps_rel<R, NT / 8, true>(oc, aYt, xc, one);   // c = #(y <= q+1)
+          oa += aYt;
+          ob += aYt;
+          oc += aYt;  // (cancels against the subtraction below at compile time)
+        } else
+#endif
         if constexpr (NT >= 128) {  // levels 1-2 from the three pivots in registers, levels 3.. from the table
           const float xa = qc - 1.f, xc = qc + 1.f;
           grp_search_top2<kAdv1, kAdv2, false>(oa, xa, piv1, piv2lo, piv2hi, one);
