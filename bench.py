@@ -741,15 +741,16 @@ def run_ours(args):
         alone["sample_gather_kernel"]["symbol"] = "fdql::sample_gather_tile_kernel (draws its own index / goal streams)"
         kernels = {"fused_pass_kernel": {
             "ms": float(k_ms[2]), "bytes_per_transition": sum(kd["bytes_per_transition"] for kd in kernels.values()),
-            "symbol": "fdql::fused_pass_kernel<7, true, true>",
+            "symbol": "fdql::fused_pass_kernel<7, true, true, 2, 0x44111> (T = 2 build: window length, record columns and copy plan "
+                      "at compile time; the launcher falls back to the general build when any of them does not hold)",
             "roles": {"loss": "16 warps per SM: tqc_group_body on pass k (pool, sort, drop, soft target, quantile-Huber fwd+bwd, lower bound): %d B"
                               % BYTES_TQC,
                       "gather": "8 warps per SM: gather_lean_body on pass k+1 (draw, window gather through cp.async staging + bulk "
                                 "shared->global write-back, HER relabel, reward / return recompute, learner aux): %.1f B"
                                 % (BYTES_GATHER + bytes_relabel + 17)},
-            "limiter": "instruction issue: 242 M warp instructions per launch (loss 214 M + gather 26 M), issue slots 79 % active (ncu, "
-                       "profiles/r2_fused_*); shared-memory wavefronts 70 % of the LSU data pipe; DRAM 41 %.  The gather role ends after "
-                       "~195 us of the ~270 us launch (role-clock probe build), the loss role runs the rest alone",
+            "limiter": "instruction issue: 224 M warp instructions per launch (loss 209 M + gather 15 M), issue slots 76-78 % active (ncu, "
+                       "profiles/r2_fused_*); LSU data pipe 78 %; DRAM 46 %.  Launch duration = instructions / issue rate with the gather "
+                       "role's phases switched off one at a time (DESIGN 4.1f)",
             "note": "ms = average launch duration inside the timed region (CUDA-event nodes around 8 of the 64 launches of a step; a "
                     "launch between event nodes cannot overlap its neighbours' ramps, so this is a little above ms_per_pass)"}}
     if args.separate_streams:
