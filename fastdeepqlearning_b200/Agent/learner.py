@@ -57,6 +57,7 @@ class Learner:
         self.train_steps = 0
         self._flat = None
         self._side = None
+        self._buckets = None  # (critic parameters, all the others): the two gradient buckets of the split backward
         self._prefetched = {}  # replay -> batch sampled during the previous step's gradient all-reduce
         self.last_summaries = {}
 
@@ -78,9 +79,11 @@ class Learner:
             curr[k], nxt[k] = v[:-1], v[1:]
         return curr, nxt
 
-    def get_losses(self, xp):
+    def get_losses(self, xp, parts=False):
         """deepQlearning.py:198-249.  `xp` is a sampled [T, B, .] dict; it is mutated like in the reference (mask,
-        is_contiguous, state).  When the gather kernel already emitted mask / is_contiguous (aux=True) they are used as is."""
+        is_contiguous, state).  When the gather kernel already emitted mask / is_contiguous (aux=True) they are used as is.
+        `parts=True` (folded reduce only) returns (critic part, actor + temperature part) of the same scalar: their backward passes
+        touch disjoint parameters, which `_one_update` uses to overlap the critic gradients' all-reduce with the actor's backward."""
         conf = self.conf
         if "mask" not in xp:
             xp["mask"] = torch.logical_not(xp["task_done"] != 0).to(xp["task_done"].dtype)
@@ -101,7 +104,11 @@ class Learner:
             q_sum, summ = self.actor_critic.q_loss_reduced(curr, nxt, weight)
             pi_loss, alpha_loss, asumm = self.actor_critic.actor_loss(curr)
             self.last_summaries = {**summ, **asumm, "Valid_Portion": is_contiguous.mean()}
+            if parts:
+                return q_sum, ((pi_loss + alpha_loss) * weight).sum()
             return q_sum + ((pi_loss + alpha_loss) * weight).sum()
+        if parts:
+            return None
         q_loss, bound, summ = self.actor_critic.q_loss(curr, nxt)
         pi_loss, alpha_loss, asumm = self.actor_critic.actor_loss(curr)
         loss = ((q_loss + pi_loss + alpha_loss) * is_contiguous).sum(0) / (is_contiguous.sum(0) + 1e-4)   # :222-225
@@ -111,15 +118,20 @@ class Learner:
         self.last_summaries = {**summ, **asumm, "Valid_Portion": is_contiguous.mean()}
         return loss / conf.temporal_len                                                                # :249
 
-    def _allreduce_grads(self):
+    def _allreduce_grads(self, params=None, bucket=0):
+        """Mean of the gradients over the ranks: one flat bucket, one all-reduce (`params`: a subset with its own bucket)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
-        grads = [p.grad for p in self.params if p.grad is not None]
+        grads = [p.grad for p in (self.params if params is None else params) if p.grad is not None]
+        if not grads:
+            return
         n = sum(g.numel() for g in grads)
-        if self._flat is None or self._flat.numel() != n:
-            self._flat = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
-        flat = self._flat
+        if not isinstance(self._flat, dict):
+            self._flat = {}
+        if bucket not in self._flat or self._flat[bucket].numel() != n:
+            self._flat[bucket] = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
+        flat = self._flat[bucket]
         torch._foreach_copy_(list(flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat.div_(dist.get_world_size())
@@ -133,9 +145,41 @@ class Learner:
         xp = self._prefetched.pop(key, None)
         if xp is None:
             xp = replay.temporal_sample(**sample_kw)
+        overlap = self._world_size() > 1 and getattr(self.conf, "overlap_allreduce", True)
+        split = None
+        sb = getattr(self.conf, "split_backward", True)  # True: with the overlapped all-reduce; "force": always (tests); False: never
+        if ((overlap and sb) or sb == "force") and self.device.type == "cuda" and not any(p.requires_grad for p in self.encoder.parameters()):
+            split = self.get_losses(xp, parts=True)  # None when the reduce is not folded (then: one backward, one bucket)
+        if split is not None:
+            # critic gradients first; their all-reduce (most of the bytes) runs on the side stream under the actor's backward
+            q_part, pi_part = split
+            cur = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            if self._buckets is None:
+                crit = list(self.actor_critic.critic.parameters())
+                ids = {id(p) for p in crit}
+                self._buckets = (crit, [p for p in self.params if id(p) not in ids])
+            crit, rest = self._buckets
+            torch.autograd.backward(q_part, inputs=crit)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._allreduce_grads(crit, bucket=1)
+            torch.autograd.backward(pi_part, inputs=rest)
+            loss = q_part.detach() + pi_part.detach()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._allreduce_grads(rest, bucket=2)
+            self._prefetched[key] = replay.temporal_sample(**sample_kw)
+            cur.wait_stream(self._side)
+            if self.conf.clip_grad_norm:
+                torch.nn.utils.clip_grad_norm_(self.params, self.conf.clip_grad_norm)
+            self.optimizer.step()
+            self.actor_critic.update_target()
+            return loss
         loss = self.get_losses(xp)
         loss.backward()
-        if self._world_size() > 1 and getattr(self.conf, "overlap_allreduce", True):
+        if overlap:
             cur = torch.cuda.current_stream(self.device)
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)

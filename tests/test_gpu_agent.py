@@ -206,6 +206,44 @@ def test_graphed_learner_is_captured_once_while_the_ring_fills(fdql):
     assert seen > 20000, "the captured launch must sample the rows added after the capture"
 
 
+def test_split_backward_is_the_same_update(fdql):
+    """Learner._one_update under torch.distributed backpropagates the critic part first, so that the critic bucket's all-reduce runs
+    under the actor's backward (two backward calls on disjoint parameters, two buckets).  Forced on one GPU: the weights after four
+    updates equal those of the single-backward learner from the same state, eagerly and as a captured graph."""
+    import torch
+    from fastdeepqlearning_b200 import Agent, Replay
+    rng = np.random.default_rng(1)
+    Lep, n_eps = 32, 300
+    N = Lep * n_eps
+    ag = rng.integers(0, 2, (N, 16)).astype(np.float32)
+    dg = np.repeat(rng.integers(0, 2, (n_eps, 16)).astype(np.float32), Lep, 0)
+    hit = (ag == dg).all(-1, keepdims=True).astype(np.float32)
+    step = (np.arange(N) % Lep).astype(np.float32).reshape(-1, 1)
+    cols = {"obs_1d": rng.standard_normal((N, 64)).astype(np.float32), "action": rng.uniform(-1, 1, (N, 8)).astype(np.float32),
+            "achieved_goal": ag, "desired_goal": dg, "reward": hit - 1, "task_done": hit,
+            "episode_done": (step == Lep - 1).astype(np.float32), "episode_step": step}
+
+    def run(split, graph):
+        torch.manual_seed(0)
+        conf = make_conf(Agent, replay_size=N + 1, use_HER=True, her_mode="future", num_instances=1, temporal_len=2, batch_size=256,
+                         use_cuda_graph=graph, split_backward=split)
+        read, write = Replay.make(conf, compute_reward=fdql.RewardOp.bitflip())
+        write[0].add_rows(cols, episode_lengths=[Lep] * n_eps)
+        learner = Agent.Learner(conf, read)
+        losses = [float(learner.train_step()) for _ in range(1 if graph else 4)]  # (a graphed learner's first step = 3 eager + 1 replay)
+        return learner, losses
+
+    base, l0 = run(False, False)
+    for split, graph in (("force", False), ("force", True)):
+        other, l1 = run(split, graph)
+        assert other._buckets is not None and len(other._buckets[0]) > 0 and len(other._buckets[1]) > 0
+        if not graph:
+            np.testing.assert_allclose(l1, l0, rtol=1e-5)
+        for (n1, p1), (n2, p2) in zip(base.actor_critic.state_dict().items(), other.actor_critic.state_dict().items()):
+            assert n1 == n2
+            np.testing.assert_allclose(p1.detach().float().cpu().numpy(), p2.detach().float().cpu().numpy(), rtol=2e-5, atol=2e-6, err_msg=n1)
+
+
 def test_data_parallel_gradients_equal_the_concatenated_batch(fdql, monkeypatch):
     """DP over N shards steps on the AVERAGE of the ranks' gradients; that equals one learner on the
     concatenation of the ranks' injected batches (the loss is a mean over the batch), <= 1e-5 of each gradient's scale.  Two
