@@ -190,7 +190,10 @@ int fdql_sample_gather_draw(const fdql_arena* a, int64_t n_windows, int32_t T, i
  * alias (the loss reads batch k's reward / mask / mc_return / weight while the gather writes batch k+1 into other buffers).
  * M == 0: the gather alone; n_windows == 0: the loss alone.  Shapes the fused kernel does not serve (loss tables other than 97..128
  * atoms, small batches, keys wider than the lean copy plan, other reward functors) run as the separate launches, gather then loss on
- * `stream`, with identical results.  The fused kernel claims its work from counters in a 16-slot workspace of the arena, one slot per
+ * `stream`, with identical results.  TD pairs (T == 2) over the reference's usual record ({reward, task_done, episode_done,
+ * episode_step, mc_return}, valid link records) and one long vector + up to three vectors of <= 16 floats take a build with these facts
+ * compiled in; any other arena runs the general build, with identical results (tests/test_gpu_r2.py).  The fused kernel claims its
+ * work from counters in a 16-slot workspace of the arena, one slot per
  * launch in turn: at most 16 fused passes of one arena may be in flight at a time (passes on one stream never are). */
 int fdql_fused_pass(const fdql_arena* a, int64_t n_windows, int32_t T, int32_t goal_mode, float relabel_prob, uint64_t seed,
                     uint64_t counter, uint64_t* counter_dev, int64_t* starts, uint8_t* flags, int64_t* goal_rows, int32_t reward_op,
@@ -218,7 +221,9 @@ int fdql_sample_gather(const fdql_arena* a, int64_t n_windows, int32_t T, int64_
  * descriptor-walking kernel that serves rows wider than 128 float4; bit 1 makes the bitflip functor take the full-vector
  * relabel scan instead of the hash-assisted one; bit 2 makes the hash-assisted scan use the per-pass suffix scan for the
  * returns instead of the scan-free (Horner + one reduction) form; bit 3 routes plain and bitflip gathers through the
- * warp-per-window kernels instead of the tile kernel */
+ * warp-per-window kernels instead of the tile kernel; bit 4: tile kernel without link records; bit 5: lean kernel wherever it can
+ * serve; bits 6..10: probe switches of the gather role (probe builds, -DFDQL_PROBES, only); bit 11: fused pass without the T == 2
+ * build; bit 12: without the compiled copy plan */
 int fdql_debug_force_generic_gather(int on);
 
 /* test hook (returns the previous setting): 1 routes the TQC / quantile-Huber losses through the warp-per-transition kernel
