@@ -157,9 +157,9 @@ class Learner:
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
             if self._buckets is None:
-                crit = list(self.actor_critic.critic.parameters())
+                crit = [p for p in self.actor_critic.critic.parameters() if p.requires_grad]
                 ids = {id(p) for p in crit}
-                self._buckets = (crit, [p for p in self.params if id(p) not in ids])
+                self._buckets = (crit, [p for p in self.params if id(p) not in ids and p.requires_grad])
             crit, rest = self._buckets
             torch.autograd.backward(q_part, inputs=crit)
             self._side.wait_stream(cur)
