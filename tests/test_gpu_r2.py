@@ -541,17 +541,18 @@ def test_coresident_option_selects_the_lean_kernel_and_matches(fdql, obs, act, G
 
 
 # ------------------------------------------------------------------------------------------------ one launch per pass
-@pytest.mark.parametrize("n,T,n_atoms,n_drop,with_lb,with_stats,repeat,ep_len", [
-    (24576, 2, 125, 10, True, True, 2, 64),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
-    (24576, 2, 125, 10, True, True, 1, 40000),  # episodes without a chain of equal goals (> 32767 rows): the T = 2 build's out-of-line tail scan
-    (20000, 2, 125, 10, False, False, 1, 64),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
-    (24576, 2, 100, 8, True, False, 1, 64),    # fused kernel, 100 atoms (4 x 25)
-    (6001, 5, 125, 10, True, True, 1, 64),     # fused kernel, five-row windows (link records), ragged
-    (1024, 50, 125, 10, True, True, 2, 64),    # fused kernel at the reference's default temporal_len (tail scan: windows past the hit mask)
-    (3000, 2, 125, 10, True, True, 1, 64),     # batch too small for the one-block-per-SM form: the two separate launches
-    (24576, 2, 50, 4, True, True, 1, 64),      # 64-entry loss tables: separate launches
+@pytest.mark.parametrize("n,T,n_atoms,n_drop,with_lb,with_stats,repeat,ep_len,permute", [
+    (24576, 2, 125, 10, True, True, 2, 64, False),    # the fused kernel (16 loss warps + 8 gather warps per SM), headline shape, two passes
+    (24576, 2, 125, 10, True, True, 1, 40000, False),  # episodes without a chain of equal goals (> 32767 rows): the T = 2 build's out-of-line tail scan
+    (20000, 2, 125, 10, False, False, 1, 64, False),  # fused kernel, flavour without lower bound / summaries, ragged last group and chunk
+    (24576, 2, 100, 8, True, False, 1, 64, False),    # fused kernel, 100 atoms (4 x 25)
+    (6001, 5, 125, 10, True, True, 1, 64, False),     # fused kernel, five-row windows (link records), ragged
+    (1024, 50, 125, 10, True, True, 2, 64, False),    # fused kernel at the reference's default temporal_len (tail scan: windows past the hit mask)
+    (3000, 2, 125, 10, True, True, 1, 64, False),     # batch too small for the one-block-per-SM form: the two separate launches
+    (24576, 2, 50, 4, True, True, 1, 64, False),      # 64-entry loss tables: separate launches
+    (24576, 2, 125, 10, True, True, 1, 64, True),  # scalar keys in another order: not the compiled record columns -> the general build
 ])
-def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb, with_stats, repeat, ep_len):
+def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb, with_stats, repeat, ep_len, permute):
     """fdql_fused_pass (loss of batch k + gather of batch k+1 in one warp-specialised launch) against fdql_sample_gather_draw and
     fdql_tqc_loss as separate launches on the same arguments: bit-identical batch, loss, gradient; summaries to fp64 rounding.  The
     loss half reads the PREVIOUS gather's reward / mask / mc_return / weight (other buffers), as the learner loop does."""
@@ -563,6 +564,9 @@ def test_fused_pass_equals_the_two_launches(fdql, n, T, n_atoms, n_drop, with_lb
     rng = np.random.default_rng(5 + n)
     cols, lengths, starts_ep, ends, ep_of = _synthetic(rng, 600 * 64 // ep_len + 1, 0, G, obs=64, act=8, fixed_len=ep_len)
     N = int(lengths.sum())
+    if permute:
+        order = ["obs_1d", "episode_step", "action", "mc_return", "achieved_goal", "task_done", "desired_goal", "reward", "episode_done"]
+        cols = {k: cols[k] for k in order}
     ring = Replay.ReplayMemory(N + 1, 4096, T)
     ring.set_reward_op(fdql.RewardOp.bitflip(), 0.99)
     ring.add_rows(cols, episode_lengths=lengths, with_returns=True)
